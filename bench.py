@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the fused colour stage (BASELINE.json metric: 4K 10-bit frames/s and Gpix/s per GPU, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3] [--content natural|noise]
+
+A step = one pass of the hot path over one batch of `frames_per_step` distinct synthetic frames that are already
+resident in HBM (working set >> L2, so no L2 flush is needed between steps).  Prints ONE JSON line (rank 0).
+For N > 1 launch under torchrun: every rank owns one GPU and a contiguous frame range (no collective on the path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # BASELINE.json configs[0..3]; cfg3 is the one the metric is quoted on
+    "cfg1": dict(pix_fmt="yuv420p", w=1920, h=1080, lut=33, interp="tetrahedral", in_range="tv", norm_range="tv",
+                 frames_per_step=256, desc="1080p yuv420p 8-bit, 33-point look .cube, tetrahedral, bt709 tv"),
+    "cfg2": dict(pix_fmt="yuv420p", w=1920, h=1080, lut=33, interp="trilinear", in_range="pc", norm_range="tv",
+                 frames_per_step=256, desc="1080p yuv420p full-range source, pc->tv pass, bt709 forced, 33-point, trilinear"),
+    "cfg3": dict(pix_fmt="yuv422p10le", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv", norm_range="tv",
+                 frames_per_step=64, desc="4K UHD yuv422p10le, 65-point look .cube, tetrahedral, bt709 tv->tv"),
+    "cfg4": dict(pix_fmt="yuv422p10le", w=7680, h=4320, lut=65, interp="tetrahedral", in_range="tv", norm_range="tv",
+                 frames_per_step=16, desc="8K yuv422p10le, 65-point look .cube, tetrahedral, frame-range sharded"),
+}
+BYTES_PER_PIXEL = {"yuv420p": 1.5, "yuv422p10le": 4.0}  # per side; algorithmic bytes/frame = (in + out) * w * h
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic(config_name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists for this config."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(config_name)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._nv:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_lut_table(n):
+    from lut_renderer_b200 import synth
+    return synth.look_lut(n).astype(np.float32)
+
+
+def make_host_frames(cfg, content, count):
+    from lut_renderer_b200 import synth
+    if content == "noise":
+        return [synth.noise_frame(cfg["pix_fmt"], cfg["w"], cfg["h"], seed=1 + i) for i in range(count)]
+    return [synth.natural_frame(cfg["pix_fmt"], cfg["w"], cfg["h"], t=7 * i, seed=0, full_range=cfg["in_range"] == "pc")
+            for i in range(count)]
+
+
+def device_frames(cfg, content, nframes, device, rank):
+    """`nframes` distinct packed frames in one device buffer: a few CPU-generated base frames, the rest derived from
+    them on the GPU by rolling the planes (keeps the content class, makes every frame's bytes distinct)."""
+    import torch
+    from lut_renderer_b200 import synth
+    base = make_host_frames(cfg, content, 4)
+    shapes, dt = synth.plane_shapes(cfg["pix_fmt"], cfg["w"], cfg["h"])
+    item = np.dtype(dt).itemsize
+    fb = base[0].nbytes
+    buf = torch.empty(nframes * fb, dtype=torch.uint8, device=device)
+    dev_base = [torch.from_numpy(b).to(device) for b in base]
+    for i in range(nframes):
+        src = dev_base[i % 4]
+        k = i // 4 + 13 * rank
+        off = 0
+        for p, (r, c) in enumerate(shapes):
+            n = r * c * item
+            plane = src[off:off + n].view(r, c * item)
+            # roll by an even number of samples / rows so chroma siting stays consistent
+            sx = (8 * k if p == 0 else 4 * k) * item
+            sy = 2 * k if (p == 0 or cfg["pix_fmt"] != "yuv420p") else k
+            buf[i * fb + off:i * fb + off + n].view(r, c * item).copy_(torch.roll(plane, shifts=(sy % r, sx % (c * item)), dims=(0, 1)))
+            off += n
+    return buf, base
+
+
+def run_reference(args, cfg, rank, world):
+    """--impl reference: the reference's CPU path (see oracle/cpu_baseline.py) on the host cores, same metric/config."""
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as C
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    lut = O.OracleLut.from_table(make_lut_table(cfg["lut"]))
+    frames = make_host_frames(cfg, args.content, 4)
+    # a step = a bounded sample: every host thread converts frames for `sample_s` seconds
+    sample_s = max(1.0, min(8.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        C.time_cpu_path(cfg["pix_fmt"], cfg["w"], cfg["h"], lut, frames, seconds=min(sample_s, 1.0), interp=cfg["interp"])
+    total_frames, total_s, legs = 0, 0.0, ""
+    for _ in range(args.steps):
+        r = C.time_cpu_path(cfg["pix_fmt"], cfg["w"], cfg["h"], lut, frames, seconds=sample_s, interp=cfg["interp"])
+        total_frames += r["frames"]
+        total_s += r["seconds"]
+        legs = r["legs"]
+    fps = total_frames / total_s
+    mpix = cfg["w"] * cfg["h"] / 1e6
+    line = {
+        "impl": "reference", "metric": "4K 10-bit frames/s" if args.config == "cfg3" else f"{args.config} frames/s",
+        "value": round(fps, 3), "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 * total_s / max(1, args.steps), 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16+f32" if cfg["pix_fmt"] == "yuv422p10le" else "u8+f32", "data": "synthetic",
+        "gpix_per_s": round(fps * mpix / 1e3, 4),
+        "config": {"workload": cfg["desc"], "content": args.content, "frames_per_step": round(total_frames / max(1, args.steps), 1)},
+        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{legs}; {cores} frame-parallel threads x {sample_s:.1f}s per step, {total_frames} frames total"},
+        "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--content", default="natural", choices=["natural", "noise"])
+    ap.add_argument("--float-mode", default="c", choices=["c", "fma"])
+    ap.add_argument("--frames-per-step", type=int, default=0)
+    ap.add_argument("--rows-per-cta", type=int, default=0)
+    ap.add_argument("--band-rows", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.frames_per_step:
+        cfg["frames_per_step"] = args.frames_per_step
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lut_renderer_b200.stage import ColourStage
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    F = cfg["frames_per_step"]
+    stage = ColourStage(cfg["w"], cfg["h"], cfg["pix_fmt"], in_range=cfg["in_range"], norm_range=cfg["norm_range"],
+                        interp=cfg["interp"], float_mode=args.float_mode, device=local_rank)
+    if args.rows_per_cta:
+        stage.set_option("rows_per_cta", args.rows_per_cta)
+    if args.band_rows:
+        stage.set_option("band_rows", args.band_rows)
+    table = make_lut_table(cfg["lut"])
+    lut = stage.ctx.lut_from_table(table)
+    # this rank's contiguous frame range of the (world * F)-frame clip, resident in HBM
+    src, base_frames = device_frames(cfg, args.content, F, device, rank)
+    dst = torch.empty(F * stage.out_frame_bytes, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        stage.run(lut, src, dst, F, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    launches0 = stage.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = stage.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=device)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+
+    # spot check: the timed outputs are the right pixels (first frame of this rank against the oracle)
+    parity = None
+    if rank == 0:
+        try:
+            from oracle import oracle as O
+            from lut_renderer_b200 import synth
+            got = dst[:stage.out_frame_bytes].cpu().numpy()
+            first = src[:stage.in_frame_bytes].cpu().numpy()
+            L = O.OracleLut.from_table(table)
+            Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(first, cfg["pix_fmt"], cfg["w"], cfg["h"])]
+            if cfg["pix_fmt"] == "yuv422p10le":
+                exp = O.stage_yuv422p10(L, Y, U, V, interp=cfg["interp"])
+            else:
+                exp = O.stage_yuv420p(L, Y, U, V, interp=cfg["interp"], range_pass=cfg["in_range"] == "pc" and cfg["norm_range"] == "tv")
+            parity = "bit-exact" if np.array_equal(got, synth.pack_planes(exp)) else "MISMATCH"
+        except Exception as exc:  # the checker is optional for the measurement
+            parity = f"unchecked ({exc})"
+
+    # end to end: the call a user makes (ColourStage.run_host) on pinned host frames, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        Fe = max(1, min(F, 16 if cfg["pix_fmt"] == "yuv422p10le" else 64))
+        pin_in = stage.ctx.pinned_buffer(Fe * stage.in_frame_bytes)
+        pin_out = stage.ctx.pinned_buffer(Fe * stage.out_frame_bytes)
+        for i in range(Fe):
+            pin_in.array[i * stage.in_frame_bytes:(i + 1) * stage.in_frame_bytes] = base_frames[i % len(base_frames)]
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            stage.run_host(lut, pin_in, pin_out, Fe)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            stage.run_host(lut, pin_in, pin_out, Fe)   # synchronous: output bytes are in host memory on return
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": round(world * Fe * e2e_steps / dt, 2), "unit": "frames/s", "h2d_bytes_per_step": Fe * stage.in_frame_bytes,
+               "d2h_bytes_per_step": Fe * stage.out_frame_bytes, "frames_per_step": Fe, "steps": e2e_steps,
+               "api": "ColourStage.run_host -> lutr_stage_run_host (pinned host buffers)"}
+        pin_in.close()
+        pin_out.close()
+
+    if rank == 0:
+        fps = world * F * args.steps / (ms / 1e3)
+        mpix = cfg["w"] * cfg["h"] / 1e6
+        bytes_per_frame = 2 * BYTES_PER_PIXEL[cfg["pix_fmt"]] * cfg["w"] * cfg["h"]
+        per_launch_ms = ms / args.steps
+        achieved = bytes_per_frame * F / (per_launch_ms / 1e3) / 1e9
+        peak, peak_src = measured_peak_hbm()
+        kernel = "k_yuv422p10" if cfg["pix_fmt"] == "yuv422p10le" else "k_yuv420p8"
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cpu_baseline as C
+            from oracle import oracle as O
+            r = C.time_cpu_path(cfg["pix_fmt"], cfg["w"], cfg["h"], O.OracleLut.from_table(table), base_frames,
+                                seconds=args.cpu_seconds, interp=cfg["interp"])
+            cpu = {"value": round(r["fps"], 3), "unit": "frames/s", "cores": r["threads"], "kind": "port",
+                   "sample": f"{r['legs']}; {r['frames']} frames of the same workload in {r['seconds']:.1f}s, "
+                             f"{r['threads']} frame-parallel threads"}
+        line = {
+            "metric": "4K 10-bit frames/s" if args.config == "cfg3" else f"{args.config} frames/s",
+            "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(per_launch_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u16+f32" if cfg["pix_fmt"] == "yuv422p10le" else "u8+f32", "data": "synthetic",
+            "gpix_per_s": round(fps * mpix / 1e3, 3),
+            "config": {"workload": cfg["desc"], "content": args.content, "frames_per_step": F, "float_mode": args.float_mode,
+                       "l2": f"inputs larger than L2 ({F * bytes_per_frame / 2 / 1e6:.0f} MB read + same written per step)",
+                       "sharding": "contiguous frame range per GPU, no collective", "parity_spot_check": parity},
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1),
+                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": ncu_traffic(args.config), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(bytes_per_frame * F), "frac_of_8TBs_nominal": round(achieved / 8000.0, 4), "per": "GPU"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    stage.close()
+    lut.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,163 @@
+/*
+ * lutr.h -- C-ABI of the B200-native 3D-LUT colour stage (drop-in for the per-pixel work LUT-renderer
+ * delegates to FFmpeg).
+ *
+ * The reference has no FFI: its boundary for this path is the `-vf` sub-chain that
+ * build_command() assembles (reference src/lut_renderer/ffmpeg.py:195-247, 304-310) and that
+ * TaskRunner._run_stage() hands to an `ffmpeg` subprocess (task_manager.py:145-151):
+ *
+ *     [scale=in_range=pc:out_range=R[:in_color_matrix=M:out_color_matrix=M],format=yuv4xxp,]   ffmpeg.py:212-233
+ *     [scale=in_color_matrix=M:out_color_matrix=M,]                                            ffmpeg.py:234-236
+ *     lut3d=file='X.cube':interp=I                                                             ffmpeg.py:242-247
+ *     [,format=PIXFMT]   -pix_fmt PIXFMT                                                        ffmpeg.py:304-310
+ *
+ * Each entry point below replaces one node of that chain (cited per function).  Plain pointers and
+ * sizes only; no torch / C++ types.  All functions returning int return LUTR_OK (0) or a negative
+ * lutr_status; the message for the last failure on the calling thread is lutr_last_error().
+ *
+ * Threading: a lutr_ctx and a lutr_lut may be shared by threads that run different stages on
+ * different streams; a lutr_stage is single-threaded.  The caller owns frame buffers; the library
+ * owns LUT device memory and staging buffers.  There is NO CPU fallback: every compute entry point
+ * fails with LUTR_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef LUTR_H
+#define LUTR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define LUTR_API __declspec(dllexport)
+#else
+#define LUTR_API __attribute__((visibility("default")))
+#endif
+
+#define LUTR_VERSION 100 /* 0.1.0, tracks reference src/lut_renderer/__init__.py:2 */
+
+typedef enum lutr_status {
+    LUTR_OK = 0,
+    LUTR_ERR_INVALID_ARG = -1,  /* NULL handle, bad enum, bad geometry                                   */
+    LUTR_ERR_INVALID_DATA = -2, /* .cube: garbled data line / unexpected EOF / empty LUT  (lut3d: AVERROR_INVALIDDATA) */
+    LUTR_ERR_LUT_SIZE = -3,     /* .cube: LUT_3D_SIZE < 2 or > 256  (lut3d: "Too large or invalid 3D LUT size", EINVAL) */
+    LUTR_ERR_IO = -4,           /* .cube file cannot be opened / read                                    */
+    LUTR_ERR_NOMEM = -5,
+    LUTR_ERR_CUDA = -6,         /* no device, wrong architecture, or a CUDA runtime error                */
+    LUTR_ERR_UNSUPPORTED = -7   /* valid request outside what the kernels implement      */
+} lutr_status;
+
+/* Pixel formats of the stage input / output (`format=` / `-pix_fmt`, ffmpeg.py:233, 287-310). */
+typedef enum lutr_pix_fmt {
+    LUTR_PIX_YUV420P = 0,     /* 8-bit 4:2:0 planar  (fast-delivery default / force_8bit)                 */
+    LUTR_PIX_YUV422P10LE = 1  /* 10-bit 4:2:2 planar in LE u16 (pro-mode ProRes master, ffmpeg.py:417-433) */
+} lutr_pix_fmt;
+
+typedef enum lutr_range { LUTR_RANGE_TV = 0, LUTR_RANGE_PC = 1 } lutr_range;
+
+/* YUV<->RGB matrices (`in_color_matrix` / `out_color_matrix`, ffmpeg.py:113-126, 201-209). */
+typedef enum lutr_matrix {
+    LUTR_MATRIX_BT709 = 0,
+    LUTR_MATRIX_BT601 = 1,    /* smpte170m / bt470bg / FFmpeg's default when nothing is forced ("none") */
+    LUTR_MATRIX_BT2020 = 2,   /* bt2020nc / bt2020c */
+    LUTR_MATRIX_FCC = 3,
+    LUTR_MATRIX_SMPTE240M = 4
+} lutr_matrix;
+
+/* lut3d `interp=` (ffmpeg.py:242-246; GUI offers tetrahedral / trilinear, main_window.py:649-652). */
+typedef enum lutr_interp { LUTR_INTERP_NEAREST = 0, LUTR_INTERP_TRILINEAR = 1, LUTR_INTERP_TETRAHEDRAL = 2 } lutr_interp;
+
+/* Float evaluation order of the LUT blend.  C = FFmpeg's C code (separate mul and add; what packed
+ * rgb24 always uses and the documented semantics of this library).  FMA = contracted multiply-adds
+ * in the same operand order (what FFmpeg's x86 AVX2 assembly does for planar formats). */
+typedef enum lutr_float_mode { LUTR_FLOAT_C = 0, LUTR_FLOAT_FMA = 1 } lutr_float_mode;
+
+/* One colour stage = everything between the decoder's raw frame and the encoder's raw frame. */
+typedef struct lutr_stage_desc {
+    uint32_t struct_size; /* sizeof(lutr_stage_desc), for ABI growth */
+    int32_t width, height;
+    int32_t in_fmt;       /* lutr_pix_fmt of the decoded source frames                                      */
+    int32_t out_fmt;      /* lutr_pix_fmt after `format=`                                                    */
+    int32_t in_range;     /* lutr_range of the source samples (VideoInfo.color_range / yuvj*, ffmpeg.py:129-134) */
+    int32_t norm_range;   /* range after the reference's `scale=in_range=pc:out_range=R` pass (ffmpeg.py:213-225);
+                             == in_range when the source is tv.  pc -> tv re-quantises to 8 bit like format=yuv4xxp */
+    int32_t in_matrix;    /* lutr_matrix for YUV->RGB in front of lut3d                                      */
+    int32_t out_matrix;   /* lutr_matrix for RGB->YUV behind lut3d (output tag policy, ffmpeg.py:348-383)    */
+    int32_t out_range;    /* lutr_range of the output (LUTR_RANGE_TV for tags=bt709)                          */
+    int32_t interp;       /* lutr_interp                                                                     */
+    int32_t float_mode;   /* lutr_float_mode, 0 = C semantics                                                */
+    int32_t reserved[4];
+} lutr_stage_desc;
+
+/* A batch of planar frames: plane p of frame f starts at data[p] + f * frame_step, rows `stride[p]` bytes apart. */
+typedef struct lutr_planes {
+    void *data[3];      /* Y, U, V */
+    int32_t stride[3];  /* bytes per row */
+    int64_t frame_step; /* bytes between consecutive frames (ignored when nframes == 1) */
+} lutr_planes;
+
+typedef struct lutr_ctx lutr_ctx;
+typedef struct lutr_lut lutr_lut;
+typedef struct lutr_stage lutr_stage;
+
+/* ---- library ------------------------------------------------------------------------------------- */
+LUTR_API int lutr_version(void);
+LUTR_API const char *lutr_status_string(int status);
+LUTR_API const char *lutr_last_error(void); /* thread-local; replaces ffmpeg's stderr text (task_manager.py:105-112) */
+
+/* ---- .cube parsing: replaces vf_lut3d's parse_cube() behind `lut3d=file=...` (ffmpeg.py:246) ---------
+ * Host only (usable without a GPU).  On success *table is a malloc'd float[size^3*3] in lut3d's memory
+ * order [r][g][b] (release with lutr_free), scale[c] = clip(1/(DOMAIN_MAX[c]-DOMAIN_MIN[c]), 0, 1). */
+LUTR_API int lutr_cube_parse(const char *text, size_t len, int32_t *size, float scale[3], float **table);
+LUTR_API int lutr_cube_parse_file(const char *path, int32_t *size, float scale[3], float **table);
+LUTR_API void lutr_free(void *p);
+
+/* ---- device context ------------------------------------------------------------------------------ */
+LUTR_API int lutr_device_count(int32_t *count);
+LUTR_API int lutr_ctx_create(int32_t device, lutr_ctx **out);
+LUTR_API void lutr_ctx_destroy(lutr_ctx *ctx);
+LUTR_API int lutr_ctx_info(const lutr_ctx *ctx, int32_t *device, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+/* pinned host memory for the raw-pipe ring (decode -> GPU -> encode re-plumb of task_manager.py:134-190) */
+LUTR_API int lutr_host_alloc(lutr_ctx *ctx, size_t bytes, void **out);
+LUTR_API void lutr_host_free(lutr_ctx *ctx, void *p);
+
+/* ---- LUT upload: once per device and per distinct LUT --------------------------------------------- */
+LUTR_API int lutr_lut_load_cube(lutr_ctx *ctx, const char *path, lutr_lut **out);
+LUTR_API int lutr_lut_load_cube_memory(lutr_ctx *ctx, const char *text, size_t len, lutr_lut **out);
+LUTR_API int lutr_lut_from_table(lutr_ctx *ctx, int32_t size, const float *rgb, const float scale[3], lutr_lut **out);
+LUTR_API int lutr_lut_size(const lutr_lut *lut);
+LUTR_API void lutr_lut_destroy(lutr_lut *lut);
+
+/* ---- the stage: replaces scale/format/lut3d/format between decode and encode ----------------------- */
+LUTR_API int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **out);
+LUTR_API void lutr_stage_destroy(lutr_stage *stage);
+/* bytes of one tightly packed frame (Y plane, then U, then V; rows unpadded) on each side */
+LUTR_API int lutr_stage_frame_bytes(const lutr_stage *stage, size_t *in_bytes, size_t *out_bytes);
+/* fill a lutr_planes for `base` holding tightly packed frames (input side: which=0, output side: which=1) */
+LUTR_API int lutr_stage_packed_planes(const lutr_stage *stage, int32_t which, void *base, lutr_planes *planes);
+
+/* Device-resident frames: enqueue the fused kernel for `nframes` frames on `cuda_stream`
+ * (a cudaStream_t passed as void*, NULL = the stage's own stream).  Asynchronous. */
+LUTR_API int lutr_stage_run(lutr_stage *stage, const lutr_lut *lut, const lutr_planes *in, const lutr_planes *out,
+                            int32_t nframes, void *cuda_stream);
+/* Host frames (tightly packed, pinned or pageable): H2D -> kernel -> D2H, chunked and overlapped on the
+ * stage's copy/compute streams.  Synchronous: `out_host` is complete on return. */
+LUTR_API int lutr_stage_run_host(lutr_stage *stage, const lutr_lut *lut, const void *in_host, void *out_host,
+                                 int32_t nframes);
+LUTR_API int lutr_stage_sync(lutr_stage *stage);
+/* number of kernel launches this stage has enqueued so far (bench.py's gpu_launches) */
+LUTR_API int64_t lutr_stage_launch_count(const lutr_stage *stage);
+/* run-time tunables, for benchmarking: "rows_per_cta", "band_rows", "l2_persist" (0/1) */
+LUTR_API int lutr_stage_set_option(lutr_stage *stage, const char *name, int32_t value);
+
+/* ---- coefficient tables (exposed so the parity tests can pin them against libswscale) --------------- */
+/* yuv2rgb: out[7] = yC, yO8, vr, ub, ug, vg, yOff10;   rgb2yuv: out[9] = ry gy by ru gu bu rv gv bv */
+LUTR_API int lutr_tables_yuv2rgb(int32_t matrix, int32_t full_range, int32_t out[7]);
+LUTR_API int lutr_tables_rgb2yuv(int32_t matrix, int32_t out[9]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUTR_H */

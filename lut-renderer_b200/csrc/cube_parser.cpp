@@ -1,0 +1,180 @@
+// .cube reader for the device LUT upload.  Behaviour follows what the reference gets from
+// `lut3d=file='X.cube'` (reference src/lut_renderer/ffmpeg.py:246), i.e. FFmpeg vf_lut3d's parse_cube():
+//   * everything before the first line starting with "LUT_3D_SIZE" is ignored (so TITLE / DOMAIN_* lines
+//     placed before it have no effect);
+//   * size = strtol(base 0) of the text after the keyword; 2 <= size <= 256 or "invalid 3D LUT size";
+//   * then size^3 data lines, red index fastest in the file, stored [r][g][b];
+//     while reading data: blank / whitespace-only / '#' lines are skipped, "TITLE..." lines are skipped,
+//     "DOMAIN_MIN " / "DOMAIN_MAX " update the domain, any other "DOMAIN_*" is invalid data,
+//     any other line must scan as three floats or the file is invalid; running out of lines is invalid;
+//   * lines are consumed in pieces of at most 511 bytes, as a 512-byte fgets() buffer would deliver them;
+//   * scale[c] = clip(1 / (max[c] - min[c]), 0, 1); the minimum itself is not subtracted.
+// One deliberate deviation: non-finite table entries are rejected (the kernels rely on 0 * entry == 0).
+#include <cerrno>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "lutr_internal.h"
+
+namespace lutr {
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+// Hands out the pieces a 512-byte fgets() would: up to 511 bytes, ending after '\n' if one is found.
+class LineReader {
+  public:
+    LineReader(const char *text, size_t len) : p_(text), end_(text + len) {}
+    bool next(char (&buf)[512]) {
+        if (p_ >= end_) return false;
+        size_t n = 0;
+        while (p_ < end_ && n < 511) {
+            char ch = *p_++;
+            buf[n++] = ch;
+            if (ch == '\n') break;
+        }
+        buf[n] = 0;
+        return true;
+    }
+
+  private:
+    const char *p_, *end_;
+};
+
+bool starts_with(const char *s, const char *prefix) { return std::strncmp(s, prefix, std::strlen(prefix)) == 0; }
+
+bool is_blank_or_comment(const char *s) {
+    while (*s == ' ' || *s == '\f' || *s == '\n' || *s == '\r' || *s == '\t' || *s == '\v') ++s;
+    return *s == 0 || *s == '#';
+}
+
+// "%f %f %f": three floats separated by optional whitespace; returns how many were converted.
+int scan3(const char *s, float v[3]) {
+    int got = 0;
+    for (; got < 3; ++got) {
+        char *e = nullptr;
+        errno = 0;
+        float f = std::strtof(s, &e);
+        if (e == s) break;
+        v[got] = f;
+        s = e;
+    }
+    return got;
+}
+
+float clip01_recip(float mn, float mx) {
+    float s = (float)(1. / ((double)mx - (double)mn));  // double division of the float difference promoted, as upstream
+    // av_clipf(x, 0, 1) = min(max(x, 0), 1); NaN stays out of the way of max()
+    float m = s > 0.f ? s : 0.f;
+    return m > 1.f ? 1.f : m;
+}
+
+}  // namespace
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+const char *get_error() { return g_error; }
+
+int parse_cube(const char *text, size_t len, CubeLut &out) {
+    if (!text) {
+        set_error("cube: NULL text");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    LineReader rd(text, len);
+    char line[512];
+    float dmin[3] = {0.f, 0.f, 0.f}, dmax[3] = {1.f, 1.f, 1.f};
+    out = CubeLut();
+
+    bool found = false;
+    while (rd.next(line)) {
+        if (starts_with(line, "LUT_3D_SIZE")) {
+            found = true;
+            break;
+        }
+    }
+    if (!found) {
+        set_error("cube: 3D LUT is empty (no LUT_3D_SIZE line)");
+        return LUTR_ERR_INVALID_DATA;
+    }
+    const long size = std::strlen(line) > 12 ? std::strtol(line + 12, nullptr, 0) : 0;
+    if (size < 2 || size > 256) {
+        set_error("cube: Too large or invalid 3D LUT size (%ld)", size);
+        return LUTR_ERR_LUT_SIZE;
+    }
+    const size_t n = (size_t)size, n2 = n * n;
+    out.size = (int)size;
+    out.rgb.assign(n2 * n * 3, 0.f);
+
+    for (size_t b = 0; b < n; ++b)
+        for (size_t g = 0; g < n; ++g)
+            for (size_t r = 0; r < n; ++r) {
+                for (;;) {
+                    if (!rd.next(line)) {
+                        set_error("cube: Unexpected EOF after %zu of %zu entries", (b * n + g) * n + r, n2 * n);
+                        return LUTR_ERR_INVALID_DATA;
+                    }
+                    if (starts_with(line, "DOMAIN_")) {
+                        float *dst = nullptr;
+                        if (starts_with(line + 7, "MIN ")) dst = dmin;
+                        else if (starts_with(line + 7, "MAX ")) dst = dmax;
+                        if (!dst) {
+                            set_error("cube: invalid DOMAIN_ keyword");
+                            return LUTR_ERR_INVALID_DATA;
+                        }
+                        float v[3];
+                        int k = scan3(line + 11, v);
+                        for (int i = 0; i < k; ++i) dst[i] = v[i];
+                        continue;
+                    }
+                    if (starts_with(line, "TITLE")) continue;
+                    if (!is_blank_or_comment(line)) break;
+                }
+                float v[3];
+                if (scan3(line, v) != 3) {
+                    set_error("cube: invalid data line at entry %zu", (b * n + g) * n + r);
+                    return LUTR_ERR_INVALID_DATA;
+                }
+                if (!std::isfinite(v[0]) || !std::isfinite(v[1]) || !std::isfinite(v[2])) {
+                    set_error("cube: non-finite value at entry %zu", (b * n + g) * n + r);
+                    return LUTR_ERR_INVALID_DATA;
+                }
+                float *dstv = &out.rgb[3 * (r * n2 + g * n + b)];
+                dstv[0] = v[0], dstv[1] = v[1], dstv[2] = v[2];
+            }
+    for (int c = 0; c < 3; ++c) out.scale[c] = clip01_recip(dmin[c], dmax[c]);
+    return LUTR_OK;
+}
+
+int parse_cube_file(const char *path, CubeLut &out) {
+    if (!path) {
+        set_error("cube: NULL path");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    FILE *f = std::fopen(path, "rb");
+    if (!f) {
+        set_error("cube: cannot open '%s': %s", path, std::strerror(errno));
+        return LUTR_ERR_IO;
+    }
+    std::string buf;
+    char chunk[65536];
+    size_t got;
+    while ((got = std::fread(chunk, 1, sizeof(chunk), f)) > 0) buf.append(chunk, got);
+    const bool bad = std::ferror(f) != 0;
+    std::fclose(f);
+    if (bad) {
+        set_error("cube: read error on '%s'", path);
+        return LUTR_ERR_IO;
+    }
+    return parse_cube(buf.data(), buf.size(), out);
+}
+
+}  // namespace lutr

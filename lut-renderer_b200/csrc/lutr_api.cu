@@ -1,0 +1,593 @@
+// C-ABI implementation (include/lutr.h): contexts, LUT upload, stage set-up, launches, host<->device pipelining.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "lutr_internal.h"
+
+using namespace lutr;
+
+struct lutr_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t l2_bytes = 0, persist_max = 0;
+};
+
+struct lutr_lut {
+    lutr_ctx *ctx = nullptr;
+    int size = 0;
+    float scale[3] = {1.f, 1.f, 1.f};
+    float4 *dev = nullptr;   // size^3 nodes + tail padding
+    size_t dev_bytes = 0;
+};
+
+struct lutr_stage {
+    lutr_ctx *ctx = nullptr;
+    lutr_stage_desc d{};
+    Yuv2RgbK f{};
+    Rgb2YuvK b{};
+    int depth = 8;
+    size_t in_bytes = 0, out_bytes = 0;  // packed frame sizes
+    cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
+    // host pipeline: NBUF device slots of `chunk` frames each
+    static constexpr int NBUF = 3;
+    int chunk = 0;
+    uint8_t *dev_in[NBUF] = {nullptr, nullptr, nullptr}, *dev_out[NBUF] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in[NBUF]{}, ev_done[NBUF]{}, ev_out[NBUF]{};
+    bool ev_ok = false;
+    // tunables
+    int rows_per_cta = 0;  // 0 = auto
+    int band_rows = 0;     // 0 = auto
+    int l2_persist = 1;
+    const lutr_lut *persist_lut = nullptr;
+    std::atomic<int64_t> launches{0};
+};
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return LUTR_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+
+int plane_rows(int fmt, int h, int p) { return (fmt == LUTR_PIX_YUV420P && p > 0) ? h / 2 : h; }
+int plane_row_bytes(int fmt, int w, int p) {
+    const int bps = fmt == LUTR_PIX_YUV422P10LE ? 2 : 1;
+    return (p == 0 ? w : w / 2) * bps;
+}
+size_t frame_bytes(int fmt, int w, int h) {
+    size_t n = 0;
+    for (int p = 0; p < 3; ++p) n += (size_t)plane_rows(fmt, h, p) * plane_row_bytes(fmt, w, p);
+    return n;
+}
+
+void packed_planes(int fmt, int w, int h, uint8_t *base, lutr_planes *pl) {
+    size_t off = 0;
+    for (int p = 0; p < 3; ++p) {
+        pl->data[p] = base + off;
+        pl->stride[p] = plane_row_bytes(fmt, w, p);
+        off += (size_t)plane_rows(fmt, h, p) * pl->stride[p];
+    }
+    pl->frame_step = (int64_t)off;
+}
+
+int upload_lut(lutr_ctx *ctx, const CubeLut &c, lutr_lut **out) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    lutr_lut *l = new (std::nothrow) lutr_lut;
+    if (!l) return LUTR_ERR_NOMEM;
+    l->ctx = ctx;
+    l->size = c.size;
+    std::memcpy(l->scale, c.scale, sizeof(l->scale));
+    const size_t n = (size_t)c.size * c.size * c.size;
+    const size_t pad = (size_t)c.size * c.size + c.size + 2;  // zeroed tail: any "next" offset stays inside the buffer
+    std::vector<float4> host(n + pad, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (size_t i = 0; i < n; ++i) {
+        if (!std::isfinite(c.rgb[3 * i]) || !std::isfinite(c.rgb[3 * i + 1]) || !std::isfinite(c.rgb[3 * i + 2])) {
+            delete l;
+            set_error("lut: non-finite table entry %zu", i);
+            return LUTR_ERR_INVALID_DATA;
+        }
+        host[i] = make_float4(c.rgb[3 * i], c.rgb[3 * i + 1], c.rgb[3 * i + 2], 0.f);
+    }
+    l->dev_bytes = host.size() * sizeof(float4);
+    cudaError_t e = cudaMalloc((void **)&l->dev, l->dev_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(l->dev, host.data(), l->dev_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("lut upload: %s", cudaGetErrorString(e));
+        if (l->dev) cudaFree(l->dev);
+        delete l;
+        return LUTR_ERR_CUDA;
+    }
+    *out = l;
+    return LUTR_OK;
+}
+
+int check_planes(const lutr_stage *s, const lutr_planes *pl, int fmt, int nframes, const char *what) {
+    for (int p = 0; p < 3; ++p) {
+        if (!pl->data[p]) {
+            set_error("%s plane %d is NULL", what, p);
+            return LUTR_ERR_INVALID_ARG;
+        }
+        if (pl->stride[p] < plane_row_bytes(fmt, s->d.width, p)) {
+            set_error("%s stride[%d]=%d is smaller than the row (%d bytes)", what, p, pl->stride[p], plane_row_bytes(fmt, s->d.width, p));
+            return LUTR_ERR_INVALID_ARG;
+        }
+        // vector loads / stores: 16 B for Y rows of 10-bit, 8 B for 8-bit; keep one rule
+        const int need = (p == 0) ? 16 : 8;
+        const int a = fmt == LUTR_PIX_YUV422P10LE ? need : need / 2;
+        if (((uintptr_t)pl->data[p] % a) || (pl->stride[p] % a) || (nframes > 1 && (pl->frame_step % 16))) {
+            set_error("%s plane %d: pointer/stride/frame_step must be %d-byte aligned", what, p, a);
+            return LUTR_ERR_UNSUPPORTED;
+        }
+    }
+    return LUTR_OK;
+}
+
+int set_l2_window(lutr_stage *s, const lutr_lut *lut, cudaStream_t st) {
+    // keep the LUT nodes resident in L2 while frames stream through (frames use no_allocate / streaming accesses)
+    if (!s->l2_persist || s->ctx->persist_max == 0) return LUTR_OK;
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.base_ptr = (void *)lut->dev;
+    v.accessPolicyWindow.num_bytes = lut->dev_bytes < s->ctx->persist_max ? lut->dev_bytes : s->ctx->persist_max;
+    v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+    return LUTR_OK;
+}
+
+int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lutr_planes *out, int nframes, cudaStream_t st) {
+    StageK k{};
+    k.w = s->d.width, k.h = s->d.height, k.nframes = nframes;
+    k.range_pass = (s->d.in_range == LUTR_RANGE_PC && s->d.norm_range == LUTR_RANGE_TV) ? 1 : 0;
+    k.f = s->f, k.b = s->b;
+    const float lut_max = (float)(lut->size - 1);
+    const int maxv = (1 << s->depth) - 1;
+    k.lut.tab = lut->dev;
+    k.lut.n = lut->size, k.lut.n2 = lut->size * lut->size;
+    k.lut.lut_max = lut_max;
+    k.lut.in_scale = 1.0f / maxv;
+    k.lut.sr = lut->scale[0] * lut_max, k.lut.sg = lut->scale[1] * lut_max, k.lut.sb = lut->scale[2] * lut_max;
+    k.lut.out_scale = (float)maxv;
+    for (int p = 0; p < 3; ++p) {
+        k.p.in[p] = (const uint8_t *)in->data[p], k.p.out[p] = (uint8_t *)out->data[p];
+        k.p.in_stride[p] = in->stride[p], k.p.out_stride[p] = out->stride[p];
+    }
+    k.p.in_step = nframes > 1 ? in->frame_step : 0, k.p.out_step = nframes > 1 ? out->frame_step : 0;
+    if (s->persist_lut != lut) {
+        set_l2_window(s, lut, st);
+        s->persist_lut = lut;
+    }
+    int rc;
+    if (s->d.in_fmt == LUTR_PIX_YUV422P10LE) {
+        k.rows_per_cta = s->rows_per_cta > 0 ? s->rows_per_cta : 1;
+        k.bands = 1;
+        rc = launch_yuv422p10(k, s->d.interp, s->d.float_mode, st);
+    } else {
+        // bands per frame: enough CTAs to fill the device a few times over, but bands of >= 16 rows (7 halo rows each)
+        int rows = s->band_rows;
+        if (rows <= 0) {
+            const int target_ctas = s->ctx->sm_count * 8;
+            int bands = (target_ctas + nframes - 1) / nframes;
+            if (bands < 1) bands = 1;
+            rows = (k.h + bands - 1) / bands;
+            if (rows < 32) rows = 32;
+        }
+        rows = (rows + 1) & ~1;
+        if (rows > k.h) rows = k.h;
+        k.rows_per_cta = rows;
+        k.bands = (k.h + rows - 1) / rows;
+        rc = launch_yuv420p8(k, s->d.interp, s->d.float_mode, st);
+    }
+    if (rc != LUTR_OK) {
+        set_error("kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return rc;
+    }
+    s->launches.fetch_add(1, std::memory_order_relaxed);
+    return LUTR_OK;
+}
+
+void free_host_pipeline(lutr_stage *s) {
+    for (int i = 0; i < lutr_stage::NBUF; ++i) {
+        if (s->dev_in[i]) cudaFree(s->dev_in[i]);
+        if (s->dev_out[i]) cudaFree(s->dev_out[i]);
+        s->dev_in[i] = s->dev_out[i] = nullptr;
+    }
+    s->chunk = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lutr_version(void) { return LUTR_VERSION; }
+
+const char *lutr_status_string(int status) {
+    switch (status) {
+        case LUTR_OK: return "ok";
+        case LUTR_ERR_INVALID_ARG: return "invalid argument";
+        case LUTR_ERR_INVALID_DATA: return "invalid data found when processing input";
+        case LUTR_ERR_LUT_SIZE: return "too large or invalid 3D LUT size";
+        case LUTR_ERR_IO: return "i/o error";
+        case LUTR_ERR_NOMEM: return "out of memory";
+        case LUTR_ERR_CUDA: return "CUDA error / no usable sm_100 device";
+        case LUTR_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown status";
+    }
+}
+
+const char *lutr_last_error(void) { return get_error(); }
+
+int lutr_cube_parse(const char *text, size_t len, int32_t *size, float scale[3], float **table) {
+    if (!size || !table) {
+        set_error("lutr_cube_parse: NULL output");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    CubeLut c;
+    int rc = parse_cube(text, len, c);
+    if (rc != LUTR_OK) return rc;
+    float *t = (float *)std::malloc(c.rgb.size() * sizeof(float));
+    if (!t) return LUTR_ERR_NOMEM;
+    std::memcpy(t, c.rgb.data(), c.rgb.size() * sizeof(float));
+    *size = c.size;
+    if (scale) std::memcpy(scale, c.scale, 3 * sizeof(float));
+    *table = t;
+    return LUTR_OK;
+}
+
+int lutr_cube_parse_file(const char *path, int32_t *size, float scale[3], float **table) {
+    if (!size || !table) {
+        set_error("lutr_cube_parse_file: NULL output");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    CubeLut c;
+    int rc = parse_cube_file(path, c);
+    if (rc != LUTR_OK) return rc;
+    float *t = (float *)std::malloc(c.rgb.size() * sizeof(float));
+    if (!t) return LUTR_ERR_NOMEM;
+    std::memcpy(t, c.rgb.data(), c.rgb.size() * sizeof(float));
+    *size = c.size;
+    if (scale) std::memcpy(scale, c.scale, 3 * sizeof(float));
+    *table = t;
+    return LUTR_OK;
+}
+
+void lutr_free(void *p) { std::free(p); }
+
+int lutr_device_count(int32_t *count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        if (count) *count = 0;
+        return LUTR_ERR_CUDA;
+    }
+    if (count) *count = n;
+    return LUTR_OK;
+}
+
+int lutr_ctx_create(int32_t device, lutr_ctx **out) {
+    if (!out) return LUTR_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (this library has no CPU fallback)");
+        return LUTR_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range (0..%d)", device, n - 1);
+        return LUTR_ERR_INVALID_ARG;
+    }
+    cudaDeviceProp prop{};
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major, prop.minor);
+        return LUTR_ERR_CUDA;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    lutr_ctx *c = new (std::nothrow) lutr_ctx;
+    if (!c) return LUTR_ERR_NOMEM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major, c->cc_minor = prop.minor;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    c->persist_max = (size_t)prop.accessPolicyMaxWindowSize;
+    // allow up to 1/4 of L2 to be set aside for persisting lines (the LUT is <= 256^3*16 B, usually 0.6-4.4 MB)
+    size_t want = (size_t)prop.persistingL2CacheMaxSize;
+    if (want > c->l2_bytes / 4) want = c->l2_bytes / 4;
+    if (want) {
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+    }
+    *out = c;
+    return LUTR_OK;
+}
+
+void lutr_ctx_destroy(lutr_ctx *ctx) { delete ctx; }
+
+int lutr_ctx_info(const lutr_ctx *ctx, int32_t *device, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor) {
+    if (!ctx) return LUTR_ERR_INVALID_ARG;
+    if (device) *device = ctx->device;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    return LUTR_OK;
+}
+
+int lutr_host_alloc(lutr_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return LUTR_ERR_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return LUTR_OK;
+}
+
+void lutr_host_free(lutr_ctx *ctx, void *p) {
+    (void)ctx;
+    if (p) cudaFreeHost(p);
+}
+
+int lutr_lut_load_cube(lutr_ctx *ctx, const char *path, lutr_lut **out) {
+    if (!ctx || !out) return LUTR_ERR_INVALID_ARG;
+    *out = nullptr;
+    CubeLut c;
+    int rc = parse_cube_file(path, c);
+    if (rc != LUTR_OK) return rc;
+    return upload_lut(ctx, c, out);
+}
+
+int lutr_lut_load_cube_memory(lutr_ctx *ctx, const char *text, size_t len, lutr_lut **out) {
+    if (!ctx || !out) return LUTR_ERR_INVALID_ARG;
+    *out = nullptr;
+    CubeLut c;
+    int rc = parse_cube(text, len, c);
+    if (rc != LUTR_OK) return rc;
+    return upload_lut(ctx, c, out);
+}
+
+int lutr_lut_from_table(lutr_ctx *ctx, int32_t size, const float *rgb, const float scale[3], lutr_lut **out) {
+    if (!ctx || !out || !rgb) return LUTR_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (size < 2 || size > 256) {
+        set_error("lut: Too large or invalid 3D LUT size (%d)", size);
+        return LUTR_ERR_LUT_SIZE;
+    }
+    CubeLut c;
+    c.size = size;
+    c.rgb.assign(rgb, rgb + (size_t)size * size * size * 3);
+    for (int i = 0; i < 3; ++i) c.scale[i] = scale ? scale[i] : 1.f;
+    return upload_lut(ctx, c, out);
+}
+
+int lutr_lut_size(const lutr_lut *lut) { return lut ? lut->size : LUTR_ERR_INVALID_ARG; }
+
+void lutr_lut_destroy(lutr_lut *lut) {
+    if (!lut) return;
+    if (lut->dev) {
+        cudaSetDevice(lut->ctx->device);
+        cudaFree(lut->dev);
+    }
+    delete lut;
+}
+
+int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **out) {
+    if (!ctx || !desc || !out) return LUTR_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (desc->struct_size != sizeof(lutr_stage_desc)) {
+        set_error("lutr_stage_desc.struct_size=%u, expected %zu", desc->struct_size, sizeof(lutr_stage_desc));
+        return LUTR_ERR_INVALID_ARG;
+    }
+    const lutr_stage_desc &d = *desc;
+    if (d.width <= 0 || d.height <= 0 || d.interp < 0 || d.interp > 2 || d.float_mode < 0 || d.float_mode > 1 ||
+        d.in_matrix < 0 || d.in_matrix > 4 || d.out_matrix < 0 || d.out_matrix > 4 || d.in_range < 0 || d.in_range > 1 ||
+        d.norm_range < 0 || d.norm_range > 1 || d.out_range < 0 || d.out_range > 1) {
+        set_error("stage: bad geometry or enum value");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    if (d.in_fmt != d.out_fmt || (d.in_fmt != LUTR_PIX_YUV420P && d.in_fmt != LUTR_PIX_YUV422P10LE)) {
+        set_error("stage: only yuv420p->yuv420p and yuv422p10le->yuv422p10le are implemented");
+        return LUTR_ERR_UNSUPPORTED;
+    }
+    if (d.out_range != LUTR_RANGE_TV) {
+        set_error("stage: full-range output is not implemented (reference default tags=bt709 gives tv)");
+        return LUTR_ERR_UNSUPPORTED;
+    }
+    if (d.in_range == LUTR_RANGE_TV && d.norm_range != LUTR_RANGE_TV) {
+        set_error("stage: norm_range must equal in_range for a tv source");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    if (d.in_fmt == LUTR_PIX_YUV422P10LE && d.in_range == LUTR_RANGE_PC && d.norm_range == LUTR_RANGE_TV) {
+        // the reference's pc->tv pass always drops to 8-bit yuv4xxp (ffmpeg.py:137-143,233): a 10-bit in/out stage cannot express it
+        set_error("stage: pc->tv normalisation of a 10-bit source re-quantises to 8 bit in the reference; not implemented");
+        return LUTR_ERR_UNSUPPORTED;
+    }
+    // geometry the arithmetic model was pinned for against libswscale (tests/test_oracle_swscale.py)
+    if ((d.width % 8) || d.width < 16 || d.width > 16384) {
+        set_error("stage: width must be a multiple of 8 in [16, 16384]");
+        return LUTR_ERR_UNSUPPORTED;
+    }
+    if (d.in_fmt == LUTR_PIX_YUV420P && ((d.height % 2) || d.height < 12)) {
+        set_error("stage: yuv420p needs an even height >= 12");
+        return LUTR_ERR_UNSUPPORTED;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    lutr_stage *s = new (std::nothrow) lutr_stage;
+    if (!s) return LUTR_ERR_NOMEM;
+    s->ctx = ctx;
+    s->d = d;
+    s->depth = d.in_fmt == LUTR_PIX_YUV422P10LE ? 10 : 8;
+    // YUV->RGB sees the range left by the normalisation pass
+    make_yuv2rgb(d.in_matrix, d.norm_range == LUTR_RANGE_PC, s->f);
+    make_rgb2yuv(d.out_matrix, s->b);
+    s->in_bytes = frame_bytes(d.in_fmt, d.width, d.height);
+    s->out_bytes = frame_bytes(d.out_fmt, d.width, d.height);
+    cudaError_t e = cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < lutr_stage::NBUF && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        set_error("stage: stream/event creation failed: %s", cudaGetErrorString(e));
+        lutr_stage_destroy(s);
+        return LUTR_ERR_CUDA;
+    }
+    s->ev_ok = true;
+    *out = s;
+    return LUTR_OK;
+}
+
+void lutr_stage_destroy(lutr_stage *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    if (s->compute) cudaStreamSynchronize(s->compute);
+    free_host_pipeline(s);
+    if (s->ev_ok)
+        for (int i = 0; i < lutr_stage::NBUF; ++i) {
+            cudaEventDestroy(s->ev_in[i]);
+            cudaEventDestroy(s->ev_done[i]);
+            cudaEventDestroy(s->ev_out[i]);
+        }
+    if (s->compute) cudaStreamDestroy(s->compute);
+    if (s->h2d) cudaStreamDestroy(s->h2d);
+    if (s->d2h) cudaStreamDestroy(s->d2h);
+    delete s;
+}
+
+int lutr_stage_frame_bytes(const lutr_stage *s, size_t *in_bytes, size_t *out_bytes) {
+    if (!s) return LUTR_ERR_INVALID_ARG;
+    if (in_bytes) *in_bytes = s->in_bytes;
+    if (out_bytes) *out_bytes = s->out_bytes;
+    return LUTR_OK;
+}
+
+int lutr_stage_packed_planes(const lutr_stage *s, int32_t which, void *base, lutr_planes *planes) {
+    if (!s || !planes || !base) return LUTR_ERR_INVALID_ARG;
+    packed_planes(which ? s->d.out_fmt : s->d.in_fmt, s->d.width, s->d.height, (uint8_t *)base, planes);
+    return LUTR_OK;
+}
+
+int lutr_stage_run(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lutr_planes *out, int32_t nframes,
+                   void *cuda_stream) {
+    if (!s || !lut || !in || !out || nframes <= 0) {
+        set_error("lutr_stage_run: NULL argument or nframes <= 0");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    if (lut->ctx->device != s->ctx->device) {
+        set_error("lutr_stage_run: LUT lives on device %d, stage on device %d", lut->ctx->device, s->ctx->device);
+        return LUTR_ERR_INVALID_ARG;
+    }
+    int rc = check_planes(s, in, s->d.in_fmt, nframes, "input");
+    if (rc == LUTR_OK) rc = check_planes(s, out, s->d.out_fmt, nframes, "output");
+    if (rc != LUTR_OK) return rc;
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    return enqueue(s, lut, in, out, nframes, cuda_stream ? (cudaStream_t)cuda_stream : s->compute);
+}
+
+int lutr_stage_run_host(lutr_stage *s, const lutr_lut *lut, const void *in_host, void *out_host, int32_t nframes) {
+    if (!s || !lut || !in_host || !out_host || nframes <= 0) {
+        set_error("lutr_stage_run_host: NULL argument or nframes <= 0");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    if (lut->ctx->device != s->ctx->device) {
+        set_error("lutr_stage_run_host: LUT and stage are on different devices");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    // chunk = frames per pipeline slot: ~64 MB of input per slot keeps PCIe busy without hoarding HBM
+    if (s->chunk == 0) {
+        size_t per = s->in_bytes > s->out_bytes ? s->in_bytes : s->out_bytes;
+        int chunk = (int)((64u << 20) / per);
+        if (chunk < 1) chunk = 1;
+        if (chunk > 64) chunk = 64;
+        for (int i = 0; i < lutr_stage::NBUF; ++i) {
+            cudaError_t e = cudaMalloc((void **)&s->dev_in[i], (size_t)chunk * s->in_bytes);
+            if (e == cudaSuccess) e = cudaMalloc((void **)&s->dev_out[i], (size_t)chunk * s->out_bytes);
+            if (e != cudaSuccess) {
+                set_error("stage: staging allocation failed: %s", cudaGetErrorString(e));
+                free_host_pipeline(s);
+                return LUTR_ERR_CUDA;
+            }
+        }
+        s->chunk = chunk;
+    }
+    const uint8_t *src = (const uint8_t *)in_host;
+    uint8_t *dst = (uint8_t *)out_host;
+    int slot = 0;
+    bool used[lutr_stage::NBUF] = {false, false, false};
+    for (int f0 = 0; f0 < nframes; f0 += s->chunk, slot = (slot + 1) % lutr_stage::NBUF) {
+        const int n = nframes - f0 < s->chunk ? nframes - f0 : s->chunk;
+        // slot reuse: its previous D2H must have drained before we overwrite dev_in / dev_out
+        if (used[slot]) {
+            CUDA_TRY(cudaStreamWaitEvent(s->h2d, s->ev_out[slot], 0));
+            CUDA_TRY(cudaStreamWaitEvent(s->compute, s->ev_out[slot], 0));
+        }
+        CUDA_TRY(cudaMemcpyAsync(s->dev_in[slot], src + (size_t)f0 * s->in_bytes, (size_t)n * s->in_bytes, cudaMemcpyHostToDevice, s->h2d));
+        CUDA_TRY(cudaEventRecord(s->ev_in[slot], s->h2d));
+        CUDA_TRY(cudaStreamWaitEvent(s->compute, s->ev_in[slot], 0));
+        lutr_planes pin{}, pout{};
+        packed_planes(s->d.in_fmt, s->d.width, s->d.height, s->dev_in[slot], &pin);
+        packed_planes(s->d.out_fmt, s->d.width, s->d.height, s->dev_out[slot], &pout);
+        int rc = enqueue(s, lut, &pin, &pout, n, s->compute);
+        if (rc != LUTR_OK) return rc;
+        CUDA_TRY(cudaEventRecord(s->ev_done[slot], s->compute));
+        CUDA_TRY(cudaStreamWaitEvent(s->d2h, s->ev_done[slot], 0));
+        CUDA_TRY(cudaMemcpyAsync(dst + (size_t)f0 * s->out_bytes, s->dev_out[slot], (size_t)n * s->out_bytes, cudaMemcpyDeviceToHost, s->d2h));
+        CUDA_TRY(cudaEventRecord(s->ev_out[slot], s->d2h));
+        used[slot] = true;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->d2h));
+    CUDA_TRY(cudaStreamSynchronize(s->compute));
+    return LUTR_OK;
+}
+
+int lutr_stage_sync(lutr_stage *s) {
+    if (!s) return LUTR_ERR_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(s->compute));
+    return LUTR_OK;
+}
+
+int64_t lutr_stage_launch_count(const lutr_stage *s) { return s ? s->launches.load() : 0; }
+
+int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
+    if (!s || !name) return LUTR_ERR_INVALID_ARG;
+    if (!std::strcmp(name, "rows_per_cta")) s->rows_per_cta = value;
+    else if (!std::strcmp(name, "band_rows")) s->band_rows = value;
+    else if (!std::strcmp(name, "l2_persist")) {
+        s->l2_persist = value;
+        s->persist_lut = nullptr;
+    } else {
+        set_error("unknown option '%s'", name);
+        return LUTR_ERR_INVALID_ARG;
+    }
+    return LUTR_OK;
+}
+
+int lutr_tables_yuv2rgb(int32_t matrix, int32_t full_range, int32_t out[7]) {
+    Yuv2RgbK k;
+    if (!out || !make_yuv2rgb(matrix, full_range != 0, k)) return LUTR_ERR_INVALID_ARG;
+    out[0] = k.yC, out[1] = k.yO8, out[2] = k.vr, out[3] = k.ub, out[4] = k.ug, out[5] = k.vg, out[6] = k.yOff10;
+    return LUTR_OK;
+}
+
+int lutr_tables_rgb2yuv(int32_t matrix, int32_t out[9]) {
+    Rgb2YuvK k;
+    if (!out || !make_rgb2yuv(matrix, k)) return LUTR_ERR_INVALID_ARG;
+    out[0] = k.ry, out[1] = k.gy, out[2] = k.by, out[3] = k.ru, out[4] = k.gu, out[5] = k.bu, out[6] = k.rv, out[7] = k.gv, out[8] = k.bv;
+    return LUTR_OK;
+}
+
+}  // extern "C"

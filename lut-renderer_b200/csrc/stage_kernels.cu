@@ -1,0 +1,414 @@
+// Fused colour-stage kernels for sm_100a.
+//
+// One launch = unpack -> (range pass) -> YUV->RGB -> 3D-LUT interpolation -> RGB->YUV -> chroma decimation -> pack,
+// i.e. the whole `scale,format,lut3d,format` chain the reference hands to FFmpeg
+// (reference src/lut_renderer/ffmpeg.py:211-247, 304-310), for a batch of device-resident frames.
+//
+// The arithmetic is integer fixed point (the swscale legs) and float32 without contraction (lut3d); it is
+// defined in DESIGN.md "Arithmetic" and checked bit-for-bit against oracle/ in tests/.  This is an
+// HBM-streaming / L1-gather kernel: no tensor cores on purpose.
+#include <cuda_runtime.h>
+
+#include "lutr_internal.h"
+
+namespace lutr {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clamp_u(int v, int hi) { return __vimin_s32_relu(v, hi); }  // min(max(v,0),hi), 1 instr
+
+__device__ __forceinline__ uint4 ldg_stream16(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream8(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned ldg_stream4(const void *p) {
+    unsigned r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream16(void *p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream8(void *p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream4(void *p, unsigned v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3D LUT (lut3d): float32, evaluation order of FFmpeg's C code; FMA = contracted variant (x86 asm for planar)
+// ---------------------------------------------------------------------------------------------------------------
+template <bool FMA>
+__device__ __forceinline__ float madd(float a, float b, float c) {  // a*b + c
+    if (FMA) return __fmaf_rn(a, b, c);
+    return __fadd_rn(__fmul_rn(a, b), c);
+}
+
+template <bool FMA>
+__device__ __forceinline__ float lerp1(float v0, float v1, float f) {  // v0 + (v1 - v0) * f
+    return madd<FMA>(__fsub_rn(v1, v0), f, v0);
+}
+
+template <bool FMA>
+__device__ __forceinline__ float4 lerp3(float4 a, float4 b, float f) {
+    return make_float4(lerp1<FMA>(a.x, b.x, f), lerp1<FMA>(a.y, b.y, f), lerp1<FMA>(a.z, b.z, f), 0.f);
+}
+
+// int (0..2^depth-1) in, int out.  Body of lut3d's per-pixel loop:
+//   s = clip(src * (1/max) * (scale*lut_max), 0, lut_max); prev = (int)s; next = min(prev+1, n-1); d = s - prev
+//   out = clip((int)(interp(...) * max), 0, max)     (truncation, not rounding)
+template <int INTERP, bool FMA>
+__device__ __forceinline__ void lut3d_px(const LutK &L, int ri, int gi, int bi, int out_max, int &ro, int &go, int &bo) {
+    const float sr = fminf(fmaxf(__fmul_rn(__fmul_rn(__int2float_rn(ri), L.in_scale), L.sr), 0.f), L.lut_max);
+    const float sg = fminf(fmaxf(__fmul_rn(__fmul_rn(__int2float_rn(gi), L.in_scale), L.sg), 0.f), L.lut_max);
+    const float sb = fminf(fmaxf(__fmul_rn(__fmul_rn(__int2float_rn(bi), L.in_scale), L.sb), 0.f), L.lut_max);
+    float4 c;
+    if (INTERP == LUTR_INTERP_NEAREST) {
+        // NEAR(x) = (int)((double)x + .5); x <= 255 so the double sum is exact and float rz after an exact add matches
+        const int nr = __double2int_rz((double)sr + .5), ng = __double2int_rz((double)sg + .5), nb = __double2int_rz((double)sb + .5);
+        c = __ldg(L.tab + (nr * L.n2 + ng * L.n + nb));
+    } else {
+        const int pr = __float2int_rz(sr), pg = __float2int_rz(sg), pb = __float2int_rz(sb);
+        const float dr = __fsub_rn(sr, __int2float_rn(pr)), dg = __fsub_rn(sg, __int2float_rn(pg)), db = __fsub_rn(sb, __int2float_rn(pb));
+        const int base = pr * L.n2 + pg * L.n + pb;
+        // offsets to the "next" node along each axis; 0 when prev is already the last node (next = min(prev+1, n-1))
+        const int oR = pr < L.n - 1 ? L.n2 : 0, oG = pg < L.n - 1 ? L.n : 0, oB = pb < L.n - 1 ? 1 : 0;
+        if (INTERP == LUTR_INTERP_TRILINEAR) {
+            const float4 c000 = __ldg(L.tab + base), c001 = __ldg(L.tab + base + oB);
+            const float4 c010 = __ldg(L.tab + base + oG), c011 = __ldg(L.tab + base + oG + oB);
+            const float4 c100 = __ldg(L.tab + base + oR), c101 = __ldg(L.tab + base + oR + oB);
+            const float4 c110 = __ldg(L.tab + base + oR + oG), c111 = __ldg(L.tab + base + oR + oG + oB);
+            const float4 c00 = lerp3<FMA>(c000, c100, dr), c10 = lerp3<FMA>(c010, c110, dr);
+            const float4 c01 = lerp3<FMA>(c001, c101, dr), c11 = lerp3<FMA>(c011, c111, dr);
+            const float4 c0 = lerp3<FMA>(c00, c10, dg), c1 = lerp3<FMA>(c01, c11, dg);
+            c = lerp3<FMA>(c0, c1, db);
+        } else {
+            // Tetrahedral.  All six branches of the C code have the form
+            //   (1-d1)*c000 + (d1-d2)*c[e1] + (d2-d3)*c[e1+e2] + d3*c111   with d1 >= d2 >= d3 the sorted fractions.
+            // Ties only ever swap two vertices whose weight is exactly 0, so any stable sort gives identical bits
+            // (table entries are finite; the parser guarantees it).  Sort (d, offset) pairs without branches.
+            const bool rg = dr > dg;
+            const float hi = fmaxf(dr, dg), lo = fminf(dr, dg);
+            const int ohi = rg ? oR : oG, olo = rg ? oG : oR;
+            const bool bh = db > hi;
+            const float d1 = fmaxf(hi, db), md = fminf(hi, db);
+            const int o1 = bh ? oB : ohi, om = bh ? ohi : oB;
+            const bool ml = md > lo;
+            const float d2 = fmaxf(md, lo), d3 = fminf(md, lo);
+            const int o2 = ml ? om : olo;
+            const float4 c000 = __ldg(L.tab + base), cA = __ldg(L.tab + base + o1);
+            const float4 cB = __ldg(L.tab + base + o1 + o2), c111 = __ldg(L.tab + base + oR + oG + oB);
+            const float w0 = __fsub_rn(1.f, d1), w1 = __fsub_rn(d1, d2), w2 = __fsub_rn(d2, d3), w3 = d3;
+            c.x = madd<FMA>(w3, c111.x, madd<FMA>(w2, cB.x, madd<FMA>(w1, cA.x, __fmul_rn(w0, c000.x))));
+            c.y = madd<FMA>(w3, c111.y, madd<FMA>(w2, cB.y, madd<FMA>(w1, cA.y, __fmul_rn(w0, c000.y))));
+            c.z = madd<FMA>(w3, c111.z, madd<FMA>(w2, cB.z, madd<FMA>(w1, cA.z, __fmul_rn(w0, c000.z))));
+        }
+    }
+    const float om = L.out_scale;
+    // (int) truncation then clip == clamp in float then truncate (NaN -> 0 either way)
+    ro = __float2int_rz(fminf(fmaxf(__fmul_rn(c.x, om), 0.f), om));
+    go = __float2int_rz(fminf(fmaxf(__fmul_rn(c.y, om), 0.f), om));
+    bo = __float2int_rz(fminf(fmaxf(__fmul_rn(c.z, om), 0.f), om));
+    (void)out_max;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// yuv422p10le -> yuv422p10le   (BASELINE cfg 3 / 4)
+// One CTA owns whole rows; a thread owns 8-pixel groups g = tid, tid + blockDim, ...  (16 B of Y, 8 B of U, 8 B of V).
+// Phase 1 per group: 4-tap chroma upsample + matrix -> gbrp10 -> lut3d -> Y out, per-pixel chroma terms to smem.
+// Phase 2 per group: 8-tap horizontal chroma decimation from smem -> U, V out.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int up4(int a, int b, int c, int d, int t0, int t1, int t2, int t3) {
+    return min((a * t0 + b * t1 + c * t2 + d * t3) >> 9, 32767);
+}
+
+template <int INTERP, bool FMA>
+__global__ void __launch_bounds__(512, 2) k_yuv422p10(const StageK K) {
+    extern __shared__ unsigned s_c14[];  // [2][w]: (u14 | v14 << 16) per luma column, double buffered over rows
+    const int w = K.w, cw = w >> 1, groups = w >> 3;
+    const long total_rows = (long)K.h * K.nframes;
+    const long row0 = (long)blockIdx.x * K.rows_per_cta;
+    const Yuv2RgbK f = K.f;
+    const Rgb2YuvK b = K.b;
+    // constants of the 10-bit yuv2rgb: wrapping 32-bit arithmetic as in the C code
+    const unsigned yA = (unsigned)(128 * f.yC), yK = (unsigned)(-f.yOff10 * f.yC) + (1u << 19);
+
+    for (int rr = 0; rr < K.rows_per_cta; ++rr) {
+        const long grow = row0 + rr;
+        if (grow >= total_rows) break;
+        const int frame = (int)(grow / K.h), y = (int)(grow - (long)frame * K.h);
+        const uint8_t *inY = K.p.in[0] + frame * K.p.in_step + (long)y * K.p.in_stride[0];
+        const uint8_t *inU = K.p.in[1] + frame * K.p.in_step + (long)y * K.p.in_stride[1];
+        const uint8_t *inV = K.p.in[2] + frame * K.p.in_step + (long)y * K.p.in_stride[2];
+        uint8_t *outY = K.p.out[0] + frame * K.p.out_step + (long)y * K.p.out_stride[0];
+        uint8_t *outU = K.p.out[1] + frame * K.p.out_step + (long)y * K.p.out_stride[1];
+        uint8_t *outV = K.p.out[2] + frame * K.p.out_step + (long)y * K.p.out_stride[2];
+        unsigned *sc = s_c14 + (rr & 1) * w;
+
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+            const int x0 = g << 3, i0 = g << 2;
+            const uint4 yv = ldg_stream16(inY + 2 * x0);
+            const uint2 uv = ldg_stream8(inU + 2 * i0), vv = ldg_stream8(inV + 2 * i0);
+            // chroma window e[0..7] = C[i0-2 .. i0+5], clamped to the row
+            int eu[8], ev[8];
+            eu[2] = uv.x & 0xFFFF, eu[3] = uv.x >> 16, eu[4] = uv.y & 0xFFFF, eu[5] = uv.y >> 16;
+            ev[2] = vv.x & 0xFFFF, ev[3] = vv.x >> 16, ev[4] = vv.y & 0xFFFF, ev[5] = vv.y >> 16;
+            if (g > 0) {
+                const unsigned lu = __ldg((const unsigned *)(inU + 2 * (i0 - 2))), lv = __ldg((const unsigned *)(inV + 2 * (i0 - 2)));
+                eu[0] = lu & 0xFFFF, eu[1] = lu >> 16, ev[0] = lv & 0xFFFF, ev[1] = lv >> 16;
+            } else {
+                eu[0] = eu[1] = eu[2], ev[0] = ev[1] = ev[2];
+            }
+            if (g < groups - 1) {
+                const unsigned ru = __ldg((const unsigned *)(inU + 2 * (i0 + 4))), rv = __ldg((const unsigned *)(inV + 2 * (i0 + 4)));
+                eu[6] = ru & 0xFFFF, eu[7] = ru >> 16, ev[6] = rv & 0xFFFF, ev[7] = rv >> 16;
+            } else {
+                eu[6] = eu[7] = eu[5], ev[6] = ev[7] = ev[5];
+            }
+            const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
+            unsigned yo[4];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int Y = (k & 1) ? (int)(yw[k >> 1] >> 16) : (int)(yw[k >> 1] & 0xFFFF);
+                const int j = k >> 1;
+                int cu, cv;
+                if (!(k & 1)) {  // even column 2i: taps on C[i-2..i+1]
+                    cu = up4(eu[j], eu[j + 1], eu[j + 2], eu[j + 3], -461, 3943, 14284, -1382);
+                    cv = up4(ev[j], ev[j + 1], ev[j + 2], ev[j + 3], -461, 3943, 14284, -1382);
+                    if (g == 0 && k == 0) {  // the two left-most even columns use swscale's edge-normalised taps
+                        cu = min((17729 * eu[2] - 1345 * eu[3]) >> 9, 32767);
+                        cv = min((17729 * ev[2] - 1345 * ev[3]) >> 9, 32767);
+                    } else if (g == 0 && k == 2) {
+                        cu = min((3835 * eu[2] + 13894 * eu[3] - 1345 * eu[4]) >> 9, 32767);
+                        cv = min((3835 * ev[2] + 13894 * ev[3] - 1345 * ev[4]) >> 9, 32767);
+                    }
+                } else {  // odd column 2i+1: taps on C[i-1..i+2]
+                    cu = up4(eu[j + 1], eu[j + 2], eu[j + 3], eu[j + 4], -1382, 14284, 3943, -461);
+                    cv = up4(ev[j + 1], ev[j + 2], ev[j + 3], ev[j + 4], -1382, 14284, 3943, -461);
+                }
+                // u17 = ((1<<9) - (128<<19) + c15*4096) >> 10 == 4*c15 - 65536
+                const unsigned u17 = (unsigned)(4 * cu - 65536), v17 = (unsigned)(4 * cv - 65536);
+                const unsigned yy = (unsigned)Y * yA + yK;
+                const int R = (int)(yy + v17 * (unsigned)f.vr);
+                const int G = (int)(yy + v17 * (unsigned)f.vg + u17 * (unsigned)f.ug);
+                const int B = (int)(yy + u17 * (unsigned)f.ub);
+                // av_clip_uintp2(x, 30) >> 20  ==  clamp(x >> 20, 0, 1023)
+                const int r10 = clamp_u(R >> 20, 1023), g10 = clamp_u(G >> 20, 1023), b10 = clamp_u(B >> 20, 1023);
+                int ro, go, bo;
+                lut3d_px<INTERP, FMA>(K.lut, r10, g10, b10, 1023, ro, go, bo);
+                // planar_rgb16_to_y + yuv2plane1_10
+                const int y14 = (b.ry * ro + b.gy * go + b.by * bo + (16 << 17) + (1 << 10)) >> 11;
+                const unsigned yq = (unsigned)clamp_u((min(2 * y14, 32767) + 16) >> 5, 1023);
+                const int u14 = (b.ru * ro + b.gu * go + b.bu * bo + (128 << 17) + (1 << 10)) >> 11;
+                const int v14 = (b.rv * ro + b.gv * go + b.bv * bo + (128 << 17) + (1 << 10)) >> 11;
+                sc[x0 + k] = (unsigned)(u14 & 0xFFFF) | ((unsigned)v14 << 16);
+                if (k & 1) yo[k >> 1] |= yq << 16;
+                else yo[k >> 1] = yq;
+            }
+            stg_stream16(outY + 2 * x0, make_uint4(yo[0], yo[1], yo[2], yo[3]));
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+            const int x0 = g << 3, i0 = g << 2;
+            // c14 window t[0..13] = columns x0-3 .. x0+10, clamped to the row
+            int tu[14], tv[14];
+#pragma unroll
+            for (int k = 0; k < 14; ++k) {
+                int x = x0 - 3 + k;
+                x = max(0, min(x, w - 1));
+                const unsigned pk = sc[x];
+                tu[k] = (int)(short)(pk & 0xFFFF);
+                tv[k] = (int)(pk >> 16);
+            }
+            unsigned uo[2], vo[2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // chroma column i0+j covers luma columns 2i-3 .. 2i+4 = t[2j .. 2j+7]
+                const int su = -230 * (tu[2 * j] + tu[2 * j + 7]) - 692 * (tu[2 * j + 1] + tu[2 * j + 6]) +
+                               1972 * (tu[2 * j + 2] + tu[2 * j + 5]) + 7142 * (tu[2 * j + 3] + tu[2 * j + 4]);
+                const int sv = -230 * (tv[2 * j] + tv[2 * j + 7]) - 692 * (tv[2 * j + 1] + tv[2 * j + 6]) +
+                               1972 * (tv[2 * j + 2] + tv[2 * j + 5]) + 7142 * (tv[2 * j + 3] + tv[2 * j + 4]);
+                const unsigned uq = (unsigned)clamp_u((min(su >> 13, 32767) + 16) >> 5, 1023);
+                const unsigned vq = (unsigned)clamp_u((min(sv >> 13, 32767) + 16) >> 5, 1023);
+                if (j & 1) uo[j >> 1] |= uq << 16, vo[j >> 1] |= vq << 16;
+                else uo[j >> 1] = uq, vo[j >> 1] = vq;
+            }
+            stg_stream8(outU + 2 * i0, make_uint2(uo[0], uo[1]));
+            stg_stream8(outV + 2 * i0, make_uint2(vo[0], vo[1]));
+            (void)cw;
+        }
+        // next row writes the other half of s_c14; the barrier above orders this row's reads before the
+        // row after next overwrites them (every thread passes the next barrier only after its reads here)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// yuv420p (8 bit) -> yuv420p   (BASELINE cfg 1 / 2)
+// A CTA owns one band of luma rows of one frame and walks down it; a thread owns 8-pixel column groups.
+// Nothing crosses threads: YUV->RGB uses replicated chroma, the chroma decimation is 2-px horizontal sum (inside the
+// group) + 8-tap vertical filter over the same columns.  The per-row chroma terms live in a thread-private 8-row
+// ring in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pc2tv_luma8(int v) { return clamp_u(((((v << 7) * 14071 + 33561947) >> 14) + 64) >> 7, 255); }
+__device__ __forceinline__ int pc2tv_chroma8(int v) { return clamp_u(((((v << 7) * 7197 + 16762880) >> 13) + 64) >> 7, 255); }
+
+__device__ __forceinline__ unsigned map4(unsigned p, bool chroma) {
+    unsigned r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int v = (p >> (8 * k)) & 0xFF;
+        r |= (unsigned)(chroma ? pc2tv_chroma8(v) : pc2tv_luma8(v)) << (8 * k);
+    }
+    return r;
+}
+
+template <int INTERP, bool FMA>
+__global__ void __launch_bounds__(512, 2) k_yuv420p8(const StageK K) {
+    extern __shared__ uint4 s_ring[];  // [8][groups]: 4 x (u15 | v15 << 16) per row and group
+    const int w = K.w, h = K.h, groups = w >> 3, ch = h >> 1;
+    const int frame = blockIdx.x / K.bands, band = blockIdx.x - frame * K.bands;
+    const int y_begin = band * K.rows_per_cta;              // first luma row whose outputs this CTA owns (even)
+    const int y_end = min(h, y_begin + K.rows_per_cta);     // one past the last
+    if (y_begin >= h) return;
+    const Yuv2RgbK f = K.f;
+    const Rgb2YuvK b = K.b;
+    const uint8_t *inY = K.p.in[0] + frame * K.p.in_step, *inU = K.p.in[1] + frame * K.p.in_step, *inV = K.p.in[2] + frame * K.p.in_step;
+    uint8_t *outY = K.p.out[0] + frame * K.p.out_step, *outU = K.p.out[1] + frame * K.p.out_step, *outV = K.p.out[2] + frame * K.p.out_step;
+    const int taps[8] = {-58, -172, 492, 1786, 1786, 492, -172, -58};
+
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const int x0 = g << 3, i0 = g << 2;
+        int next_row = max(0, y_begin - 3);  // next luma row to run through the pixel pipeline
+        for (int j = y_begin >> 1; j < (y_end >> 1); ++j) {
+            const int last_needed = min(h - 1, 2 * j + 4);
+            for (; next_row <= last_needed; ++next_row) {
+                const int y = next_row;
+                uint2 yv = ldg_stream8(inY + (long)y * K.p.in_stride[0] + x0);
+                unsigned uv = ldg_stream4(inU + (long)(y >> 1) * K.p.in_stride[1] + i0);
+                unsigned vv = ldg_stream4(inV + (long)(y >> 1) * K.p.in_stride[2] + i0);
+                if (K.range_pass) {
+                    yv.x = map4(yv.x, false), yv.y = map4(yv.y, false);
+                    uv = map4(uv, true), vv = map4(vv, true);
+                }
+                unsigned yo[2] = {0u, 0u};
+                unsigned ring[4];
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {  // pixel pairs sharing one chroma sample
+                    const int u = (int)((uv >> (8 * pr)) & 0xFF) * 8 - 1024, v = (int)((vv >> (8 * pr)) & 0xFF) * 8 - 1024;
+                    const int cr = (v * f.vr) >> 16, cg = ((u * f.ug) >> 16) + ((v * f.vg) >> 16), cb = (u * f.ub) >> 16;
+                    int rs = 0, gs = 0, bs = 0;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int k = 2 * pr + q;
+                        const int Y = (int)(((k < 4 ? yv.x : yv.y) >> (8 * (k & 3))) & 0xFF);
+                        const int yy = ((Y * 8 - f.yO8) * f.yC) >> 16;
+                        const int r8 = clamp_u(yy + cr, 255), g8 = clamp_u(yy + cg, 255), b8 = clamp_u(yy + cb, 255);
+                        int ro, go, bo;
+                        lut3d_px<INTERP, FMA>(K.lut, r8, g8, b8, 255, ro, go, bo);
+                        // rgb24ToY + unit hscale + yuv2plane1_8
+                        const int y14 = (b.ry * ro + b.gy * go + b.by * bo + (32 << 14) + (1 << 8)) >> 9;
+                        const unsigned yq = (unsigned)clamp_u((2 * y14 + 64) >> 7, 255);
+                        yo[k >> 2] |= yq << (8 * (k & 3));
+                        rs += ro, gs += go, bs += bo;
+                    }
+                    // rgb24ToUV_half: sum of the pair, then 15-bit intermediate
+                    const int u14 = (b.ru * rs + b.gu * gs + b.bu * bs + (256 << 15) + (1 << 9)) >> 10;
+                    const int v14 = (b.rv * rs + b.gv * gs + b.bv * bs + (256 << 15) + (1 << 9)) >> 10;
+                    ring[pr] = (unsigned)((2 * u14) & 0xFFFF) | ((unsigned)(2 * v14) << 16);
+                }
+                s_ring[(y & 7) * groups + g] = make_uint4(ring[0], ring[1], ring[2], ring[3]);
+                if (y >= y_begin && y < y_end) stg_stream8(outY + (long)y * K.p.out_stride[0] + x0, make_uint2(yo[0], yo[1]));
+            }
+            // vertical 8-tap decimation for chroma row j over luma rows 2j-3 .. 2j+4 (clamped; taps that land on the
+            // same edge row are summed into one coefficient before the multiply)
+            int au[4], av[4];
+            const bool exact = (j == ch - 1);  // swscale's C vertical scaler handles the last output row: no per-tap truncation
+#pragma unroll
+            for (int c = 0; c < 4; ++c) au[c] = av[c] = exact ? (64 << 12) : 7;
+            int fold = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int row = max(0, min(h - 1, 2 * j - 3 + k));
+                const int nrow = max(0, min(h - 1, 2 * j - 2 + k));
+                fold += taps[k];
+                if (k == 7 || nrow != row) {
+                    const uint4 q = s_ring[(row & 7) * groups + g];
+                    const unsigned qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int cu = (int)(qq[c] & 0xFFFF), cv = (int)(qq[c] >> 16);
+                        if (exact) au[c] += cu * fold, av[c] += cv * fold;
+                        else au[c] += (cu * fold) >> 16, av[c] += (cv * fold) >> 16;
+                    }
+                    fold = 0;
+                }
+            }
+            unsigned uo = 0, vo = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uo |= (unsigned)clamp_u(au[c] >> (exact ? 19 : 3), 255) << (8 * c);
+                vo |= (unsigned)clamp_u(av[c] >> (exact ? 19 : 3), 255) << (8 * c);
+            }
+            stg_stream4(outU + (long)j * K.p.out_stride[1] + i0, uo);
+            stg_stream4(outV + (long)j * K.p.out_stride[2] + i0, vo);
+        }
+    }
+}
+
+template <int INTERP>
+int launch422(const StageK &k, int float_mode, cudaStream_t st) {
+    const int groups = k.w >> 3;
+    int per = (groups + 511) / 512;                   // groups per thread
+    int threads = ((groups + per - 1) / per + 31) / 32 * 32;
+    const long total_rows = (long)k.h * k.nframes;
+    const unsigned grid = (unsigned)((total_rows + k.rows_per_cta - 1) / k.rows_per_cta);
+    const size_t smem = (size_t)2 * k.w * sizeof(unsigned);
+    auto fn = float_mode == LUTR_FLOAT_FMA ? k_yuv422p10<INTERP, true> : k_yuv422p10<INTERP, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fn<<<grid, threads, smem, st>>>(k);
+    return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
+}
+
+template <int INTERP>
+int launch420(const StageK &k, int float_mode, cudaStream_t st) {
+    const int groups = k.w >> 3;
+    int per = (groups + 511) / 512;
+    int threads = ((groups + per - 1) / per + 31) / 32 * 32;
+    const unsigned grid = (unsigned)(k.bands * k.nframes);
+    const size_t smem = (size_t)8 * groups * sizeof(uint4);
+    auto fn = float_mode == LUTR_FLOAT_FMA ? k_yuv420p8<INTERP, true> : k_yuv420p8<INTERP, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fn<<<grid, threads, smem, st>>>(k);
+    return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
+}
+
+}  // namespace
+
+int launch_yuv422p10(const StageK &k, int interp, int float_mode, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (interp) {
+        case LUTR_INTERP_NEAREST: return launch422<LUTR_INTERP_NEAREST>(k, float_mode, st);
+        case LUTR_INTERP_TRILINEAR: return launch422<LUTR_INTERP_TRILINEAR>(k, float_mode, st);
+        default: return launch422<LUTR_INTERP_TETRAHEDRAL>(k, float_mode, st);
+    }
+}
+
+int launch_yuv420p8(const StageK &k, int interp, int float_mode, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (interp) {
+        case LUTR_INTERP_NEAREST: return launch420<LUTR_INTERP_NEAREST>(k, float_mode, st);
+        case LUTR_INTERP_TRILINEAR: return launch420<LUTR_INTERP_TRILINEAR>(k, float_mode, st);
+        default: return launch420<LUTR_INTERP_TETRAHEDRAL>(k, float_mode, st);
+    }
+}
+
+}  // namespace lutr

@@ -1,0 +1,181 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- ctypes loader for oracle/liblutr_oracle.so (lutr_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liblutr_oracle.so")
+
+MATRIX_ID = {"bt709": 0, "bt601": 1, "smpte170m": 1, "bt470bg": 1, "default": 1, "bt2020nc": 2, "bt2020c": 2,
+             "bt2020": 2, "fcc": 3, "smpte240m": 4}
+INTERP_ID = {"nearest": 0, "trilinear": 1, "tetrahedral": 2}
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "lutr_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = ctypes.CDLL(_SO)
+        L.orc_cube_parse_path.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.orc_cube_parse_memory.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        L.orc_lut_free.argtypes = [ctypes.c_void_p]
+        L.orc_lut_free.restype = None
+        L.orc_lut_size.argtypes = [ctypes.c_void_p]
+        L.orc_lut_data.argtypes = [ctypes.c_void_p]
+        L.orc_lut_data.restype = ctypes.POINTER(ctypes.c_float)
+        L.orc_lut_scale.argtypes = [ctypes.c_void_p]
+        L.orc_lut_scale.restype = ctypes.POINTER(ctypes.c_float)
+        L.orc_lut_from_table.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_lut_from_table.restype = ctypes.c_void_p
+        L.orc_inv_table.restype = ctypes.POINTER(ctypes.c_int32)
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class OracleLut:
+    """A parsed 3D LUT (in-memory order [r][g][b], float32 triplets) -- restates vf_lut3d's LUT3DContext."""
+
+    def __init__(self, handle):
+        self._h = ctypes.c_void_p(handle)
+        L = lib()
+        self.size = L.orc_lut_size(self._h)
+        n = self.size ** 3 * 3
+        self.table = np.ctypeslib.as_array(L.orc_lut_data(self._h), shape=(n,)).reshape(
+            self.size, self.size, self.size, 3).copy()
+        self.scale = np.ctypeslib.as_array(L.orc_lut_scale(self._h), shape=(3,)).copy()
+
+    @classmethod
+    def from_path(cls, path):
+        h = ctypes.c_void_p()
+        r = lib().orc_cube_parse_path(os.fsencode(str(path)), ctypes.byref(h))
+        if r != 0:
+            raise ValueError(f"cube parse failed: {r}")
+        return cls(h.value)
+
+    @classmethod
+    def from_text(cls, text):
+        data = text if isinstance(text, bytes) else text.encode()
+        h = ctypes.c_void_p()
+        r = lib().orc_cube_parse_memory(data, len(data), ctypes.byref(h))
+        if r != 0:
+            raise ValueError(f"cube parse failed: {r}")
+        return cls(h.value)
+
+    @classmethod
+    def from_table(cls, table, scale=(1.0, 1.0, 1.0)):
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        s = np.asarray(scale, dtype=np.float32)
+        return cls(lib().orc_lut_from_table(t.shape[0], _p(t), _p(s)))
+
+    def __del__(self):
+        try:
+            lib().orc_lut_free(self._h)
+        except Exception:
+            pass
+
+
+def yuv2rgb_coeffs(matrix, full_range):
+    out = (ctypes.c_int32 * 7)()
+    lib().orc_yuv2rgb_setup(MATRIX_ID[matrix], int(full_range), out)
+    return dict(zip(("yC", "yO8", "vr", "ub", "ug", "vg", "yOff10"), list(out)))
+
+
+def rgb2yuv_coeffs(matrix):
+    out = (ctypes.c_int32 * 9)()
+    lib().orc_rgb2yuv_setup(MATRIX_ID[matrix], out)
+    return list(out)
+
+
+def range_tables():
+    tl, tc = np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+    lib().orc_range_pc_to_tv_tables(_p(tl), _p(tc))
+    return tl, tc
+
+
+def yuv420p_to_rgb24(Y, U, V, matrix="bt709", full_range=False):
+    h, w = Y.shape
+    rgb = np.empty((h, 3 * w), np.uint8)
+    lib().orc_yuv420p_to_rgb24(_p(Y), Y.strides[0], _p(U), _p(V), U.strides[0], _p(rgb), rgb.strides[0], w, h,
+                               MATRIX_ID[matrix], int(full_range))
+    return rgb
+
+
+def rgb24_to_yuv420p(rgb, matrix="bt709"):
+    h, w = rgb.shape[0], rgb.shape[1] // 3
+    Y, U, V = np.empty((h, w), np.uint8), np.empty((h // 2, w // 2), np.uint8), np.empty((h // 2, w // 2), np.uint8)
+    lib().orc_rgb24_to_yuv420p(_p(rgb), rgb.strides[0], _p(Y), w, _p(U), _p(V), w // 2, w, h, MATRIX_ID[matrix])
+    return Y, U, V
+
+
+def yuv422p10_to_gbrp10(Y, U, V, matrix="bt709", full_range=False):
+    h, w = Y.shape
+    R, G, B = (np.empty((h, w), np.uint16) for _ in range(3))
+    lib().orc_yuv422p10_to_gbrp10(_p(Y), w, _p(U), _p(V), w // 2, _p(R), _p(G), _p(B), w, w, h, MATRIX_ID[matrix],
+                                  int(full_range))
+    return R, G, B
+
+
+def gbrp10_to_yuv422p10(R, G, B, matrix="bt709"):
+    h, w = R.shape
+    Y, U, V = np.empty((h, w), np.uint16), np.empty((h, w // 2), np.uint16), np.empty((h, w // 2), np.uint16)
+    lib().orc_gbrp10_to_yuv422p10(_p(R), _p(G), _p(B), w, _p(Y), w, _p(U), _p(V), w // 2, w, h, MATRIX_ID[matrix])
+    return Y, U, V
+
+
+def lut3d_rgb24(lut: OracleLut, rgb, interp="tetrahedral"):
+    h, w = rgb.shape[0], rgb.shape[1] // 3
+    out = np.empty_like(rgb)
+    lib().orc_lut3d_rgb24(lut._h, INTERP_ID[interp], _p(rgb), rgb.strides[0], _p(out), out.strides[0], w, h)
+    return out
+
+
+def lut3d_planar16(lut: OracleLut, R, G, B, depth=10, interp="tetrahedral"):
+    h, w = R.shape
+    Ro, Go, Bo = (np.empty((h, w), np.uint16) for _ in range(3))
+    lib().orc_lut3d_planar16(lut._h, INTERP_ID[interp], depth, _p(R), _p(G), _p(B), w, _p(Ro), _p(Go), _p(Bo), w, w, h)
+    return Ro, Go, Bo
+
+
+def stage_yuv422p10(lut, Y, U, V, interp="tetrahedral", in_matrix="bt709", in_full_range=False, out_matrix="bt709"):
+    """cfg 3/4 chain on one frame; planes are C-contiguous uint16 (h,w),(h,w/2),(h,w/2)."""
+    h, w = Y.shape
+    Yo, Uo, Vo = np.empty_like(Y), np.empty_like(U), np.empty_like(V)
+    r = lib().orc_stage_yuv422p10(lut._h, INTERP_ID[interp], MATRIX_ID[in_matrix], int(in_full_range),
+                                  MATRIX_ID[out_matrix], _p(Y), _p(U), _p(V), _p(Yo), _p(Uo), _p(Vo), w, h)
+    if r:
+        raise RuntimeError(f"orc_stage_yuv422p10: {r}")
+    return Yo, Uo, Vo
+
+
+def stage_yuv420p(lut, Y, U, V, interp="tetrahedral", range_pass=False, in_matrix="bt709", in_full_range=False,
+                  out_matrix="bt709"):
+    """cfg 1/2 chain on one frame; planes are C-contiguous uint8 (h,w),(h/2,w/2),(h/2,w/2)."""
+    h, w = Y.shape
+    Yo, Uo, Vo = np.empty_like(Y), np.empty_like(U), np.empty_like(V)
+    r = lib().orc_stage_yuv420p(lut._h, INTERP_ID[interp], int(range_pass), MATRIX_ID[in_matrix], int(in_full_range),
+                                MATRIX_ID[out_matrix], _p(Y), _p(U), _p(V), _p(Yo), _p(Uo), _p(Vo), w, h)
+    if r:
+        raise RuntimeError(f"orc_stage_yuv420p: {r}")
+    return Yo, Uo, Vo
