@@ -234,10 +234,12 @@ def main():
     # this rank's contiguous frame range of the (world * F)-frame clip, resident in HBM
     src, base_frames = device_frames(cfg, args.content, F, device, rank)
     dst = torch.empty(F * stage.out_frame_bytes, dtype=torch.uint8, device=device)
-    stream = torch.cuda.current_stream().cuda_stream
+    # launch on a torch-visible stream so the CUDA events below bracket the kernels
+    tstream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(tstream)
 
     def step():
-        stage.run(lut, src, dst, F, stream=stream)
+        stage.run(lut, src, dst, F, stream=tstream)
 
     def barrier():
         torch.cuda.synchronize()

@@ -122,11 +122,11 @@ int check_planes(const lutr_stage *s, const lutr_planes *pl, int fmt, int nframe
             set_error("%s stride[%d]=%d is smaller than the row (%d bytes)", what, p, pl->stride[p], plane_row_bytes(fmt, s->d.width, p));
             return LUTR_ERR_INVALID_ARG;
         }
-        // vector loads / stores: 16 B for Y rows of 10-bit, 8 B for 8-bit; keep one rule
-        const int need = (p == 0) ? 16 : 8;
-        const int a = fmt == LUTR_PIX_YUV422P10LE ? need : need / 2;
-        if (((uintptr_t)pl->data[p] % a) || (pl->stride[p] % a) || (nframes > 1 && (pl->frame_step % 16))) {
-            set_error("%s plane %d: pointer/stride/frame_step must be %d-byte aligned", what, p, a);
+        // vector accesses: one 8-pixel group of Y (16 B at 10 bit, 8 B at 8 bit), half of that for a chroma group
+        const int ya = fmt == LUTR_PIX_YUV422P10LE ? 16 : 8;
+        const int a = p == 0 ? ya : ya / 2;
+        if (((uintptr_t)pl->data[p] % a) || (pl->stride[p] % a) || (nframes > 1 && (pl->frame_step % ya))) {
+            set_error("%s plane %d: pointer and stride must be %d-byte aligned, frame_step %d-byte aligned", what, p, a, ya);
             return LUTR_ERR_UNSUPPORTED;
         }
     }

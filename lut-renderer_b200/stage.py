@@ -112,6 +112,14 @@ class PinnedBuffer:
             self._p = None
 
 
+def _stream_arg(stream):
+    """None -> the stage's own stream; a cudaStream_t handle otherwise (0 = the legacy default stream, cudaStreamLegacy)."""
+    if stream is None:
+        return c_void_p(None)
+    handle = int(getattr(stream, "cuda_stream", stream))
+    return c_void_p(handle if handle else 1)
+
+
 def _address(buf) -> int:
     if isinstance(buf, int):
         return buf
@@ -158,21 +166,21 @@ class ColourStage:
                    plan.in_matrix, plan.out_matrix, plan.out_range, plan.interp, float_mode, device)
 
     # -- device-resident frames ------------------------------------------------------------------------------
-    def run(self, lut: DeviceLut, src, dst, nframes: int = 1, stream: int = 0) -> None:
+    def run(self, lut: DeviceLut, src, dst, nframes: int = 1, stream=None) -> None:
         """Enqueue the fused kernel on tightly packed device frames (src/dst: tensors or addresses). Asynchronous."""
         pin, pout = N.Planes(), N.Planes()
         N.check(N.lib().lutr_stage_packed_planes(self._h, 0, _address(src), byref(pin)))
         N.check(N.lib().lutr_stage_packed_planes(self._h, 1, _address(dst), byref(pout)))
-        N.check(N.lib().lutr_stage_run(self._h, lut._h, byref(pin), byref(pout), int(nframes), c_void_p(stream or None)))
+        N.check(N.lib().lutr_stage_run(self._h, lut._h, byref(pin), byref(pout), int(nframes), _stream_arg(stream)))
 
     def run_planes(self, lut: DeviceLut, in_planes, in_strides, out_planes, out_strides, nframes: int = 1,
-                   in_frame_step: int = 0, out_frame_step: int = 0, stream: int = 0) -> None:
+                   in_frame_step: int = 0, out_frame_step: int = 0, stream=None) -> None:
         pin, pout = N.Planes(), N.Planes()
         for i in range(3):
             pin.data[i], pin.stride[i] = _address(in_planes[i]), int(in_strides[i])
             pout.data[i], pout.stride[i] = _address(out_planes[i]), int(out_strides[i])
         pin.frame_step, pout.frame_step = int(in_frame_step), int(out_frame_step)
-        N.check(N.lib().lutr_stage_run(self._h, lut._h, byref(pin), byref(pout), int(nframes), c_void_p(stream or None)))
+        N.check(N.lib().lutr_stage_run(self._h, lut._h, byref(pin), byref(pout), int(nframes), _stream_arg(stream)))
 
     # -- host frames (the raw-pipe path) ---------------------------------------------------------------------
     def run_host(self, lut: DeviceLut, src, dst, nframes: int = 1) -> None:

@@ -37,8 +37,8 @@ def gpu_stage(pix_fmt, w, h, frames, table, scale=(1.0, 1.0, 1.0), device=0, opt
     n = len(frames)
     src = torch.from_numpy(np.concatenate(frames)).to(f"cuda:{device}")
     dst = torch.zeros(n * st.out_frame_bytes, dtype=torch.uint8, device=f"cuda:{device}")
-    st.run(lut, src, dst, n)
-    st.sync()
+    st.run(lut, src, dst, n, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
     out = dst.cpu().numpy()
     st.close()
     lut.close()

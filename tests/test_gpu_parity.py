@@ -182,8 +182,9 @@ def test_strided_planes_and_frame_step():
                 host[o:o + rows.shape[1]] = rows[r]
     src.copy_(torch.from_numpy(host))
     st.run_planes(lut, [src.data_ptr() + o for o in offs], (ystride, cstride, cstride),
-                  [dst.data_ptr() + o for o in offs], (ystride, cstride, cstride), n, step, step)
-    st.sync()
+                  [dst.data_ptr() + o for o in offs], (ystride, cstride, cstride), n, step, step,
+                  stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
     out = dst.cpu().numpy()
     L = oracle_lut(table)
     for i, f in enumerate(frames):
@@ -232,8 +233,8 @@ def test_cube_file_to_pixels(tmp_path):
     f = synth.natural_frame("yuv422p10le", w, h, t=2)
     src = torch.from_numpy(f).cuda()
     dst = torch.zeros(st.out_frame_bytes, dtype=torch.uint8, device="cuda")
-    st.run(lut, src, dst, 1)
-    st.sync()
+    st.run(lut, src, dst, 1, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
     exp = oracle_stage("yuv422p10le", w, h, f, O.OracleLut.from_path(path))
     assert_bit_exact("yuv422p10le", w, h, dst.cpu().numpy(), exp, "cube file path")
     st.close()
