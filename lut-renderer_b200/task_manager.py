@@ -1,0 +1,269 @@
+"""Runner of one task: decode -> raw pipe -> GPU colour stage -> raw pipe -> encode.
+
+Replaces ``TaskRunner._run_stage`` of the reference (reference src/lut_renderer/task_manager.py:29-216), which blocks on a
+single ffmpeg process whose filter graph contains ``lut3d``.  Signals become plain callbacks (no Qt here); status
+strings, progress split over stages, cancellation and clean-up keep the reference's behaviour:
+
+* ``status``: "running" / "completed" / "canceled" / "failed: exit N" / "failed: <exception text>"
+* progress: 0..100, pro mode splits 50/50 over its two stages (task_manager.py:86-91)
+* cancel(): cooperative flag + terminate() of the child processes (task_manager.py:38-44,180-183)
+* intermediates flagged ``cleanup_on_success`` are deleted after a successful run (task_manager.py:117-122)
+
+Stages without a LUT (pro mode stage 2) still run as the reference's single ffmpeg command.
+"""
+from __future__ import annotations
+
+import shlex
+import subprocess
+import threading
+import time
+from typing import Callable, List, Optional
+
+from .ffmpeg import CommandStage, build_command, build_gpu_stage, build_pipeline
+from .media_info import VideoInfo, probe_video
+from .models import Task, TaskStatus
+
+
+class TaskCallbacks:
+    """Default no-op sinks; the GUI connects its own (these stand in for the reference's Qt signals)."""
+
+    def progress(self, task_id: str, percent: int) -> None: ...
+    def status(self, task_id: str, text: str) -> None: ...
+    def finished(self, task_id: str, status: str) -> None: ...
+    def log(self, task_id: str, message: str) -> None: ...
+
+
+def _read_exact(pipe, view) -> int:
+    """Fill ``view`` (a writable memoryview) from ``pipe``; returns bytes read (short only at EOF)."""
+    got = 0
+    while got < len(view):
+        n = pipe.readinto(view[got:])
+        if not n:
+            break
+        got += n
+    return got
+
+
+class TaskRunner:
+    def __init__(self, task: Task, ffmpeg_bin: str = "ffmpeg", device: int = 0, callbacks: Optional[TaskCallbacks] = None,
+                 frames_per_batch: int = 8, popen: Callable = subprocess.Popen, probe: Callable = probe_video):
+        self.task, self.ffmpeg_bin, self.device = task, ffmpeg_bin, device
+        self.signals = callbacks or TaskCallbacks()
+        self.frames_per_batch = max(1, frames_per_batch)
+        self._popen, self._probe = popen, probe
+        self._procs: List = []
+        self._cancelled = False
+        self._lock = threading.Lock()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def cancel(self) -> None:
+        self._cancelled = True
+        with self._lock:
+            procs = list(self._procs)
+        for p in procs:
+            try:
+                if p.poll() is None:
+                    p.terminate()
+            except Exception:
+                pass
+
+    def _log(self, message: str) -> None:
+        self.signals.log(self.task.task_id, message)
+
+    def run(self) -> None:
+        tid = self.task.task_id
+        self.signals.status(tid, TaskStatus.RUNNING.value)
+        self._log("开始")
+        self.task.started_at = time.time()
+        try:
+            stages = build_pipeline(self.task, ffmpeg_bin=self.ffmpeg_bin)
+            if not stages:
+                raise RuntimeError("No ffmpeg stages built.")
+            for index, stage in enumerate(stages):
+                if self._cancelled:
+                    break
+                self._log(f"阶段 {index + 1}/{len(stages)}: {stage.name}")
+                info = self.task.source_info
+                if stage.probe_source:
+                    try:
+                        info = self._probe(stage.source_path)
+                    except Exception as exc:
+                        info = None
+                        self._log(f"提示: 阶段输入探测失败（将按未知处理）: {exc}")
+                span = 100 if len(stages) == 1 else 50
+                base = 0 if index == 0 else 100 - span
+                final = index == len(stages) - 1
+                ok = self._run_stage(stage, info, base, span, final)
+                if ok is None:
+                    self.signals.status(tid, TaskStatus.CANCELED.value)
+                    self._log("已取消")
+                    self.signals.finished(tid, TaskStatus.CANCELED.value)
+                    return
+                if not ok:
+                    code = self._last_returncode
+                    self.signals.status(tid, f"{TaskStatus.FAILED.value}: exit {code}")
+                    self._log(f"失败：退出码 {code}")
+                    self.signals.finished(tid, TaskStatus.FAILED.value)
+                    return
+            for stage in stages:
+                if stage.cleanup_on_success and stage.output_path.exists():
+                    try:
+                        stage.output_path.unlink()
+                    except Exception:
+                        pass
+            self.signals.progress(tid, 100)
+            self.signals.status(tid, TaskStatus.COMPLETED.value)
+            self._log("完成")
+            self.signals.finished(tid, TaskStatus.COMPLETED.value)
+        except Exception as exc:
+            self.signals.status(tid, f"{TaskStatus.FAILED.value}: {exc}")
+            self._log(f"失败：{exc}")
+            self.signals.finished(tid, TaskStatus.FAILED.value)
+
+    # ------------------------------------------------------------------------------------------------------------
+    _last_returncode = -1
+
+    def _spawn(self, cmd, **kw):
+        p = self._popen(cmd, **kw)
+        with self._lock:
+            self._procs.append(p)
+        return p
+
+    def _run_stage(self, stage: CommandStage, info: Optional[VideoInfo], base: int, span: int, final: bool) -> Optional[bool]:
+        if not stage.lut_path:
+            return self._run_plain(stage, info, base, span, final)
+        gpu = build_gpu_stage(stage, info, self.ffmpeg_bin)
+        for note in stage.notes:
+            self._log(note)
+        self._log(f"解码: {shlex.join(gpu.decode_cmd)}")
+        self._log(f"编码: {shlex.join(gpu.encode_cmd)}")
+        from .stage import ColourStage  # deferred: loads liblutr.so, fails loudly when it is missing
+        colour = ColourStage.from_plan(gpu.plan, device=self.device)
+        lut = colour.ctx.lut_from_cube(gpu.plan.lut_path)
+        nb = self.frames_per_batch
+        pin_in = colour.ctx.pinned_buffer(nb * colour.in_frame_bytes)
+        pin_out = colour.ctx.pinned_buffer(nb * colour.out_frame_bytes)
+        total = int(round(info.duration * info.fps)) if info and info.duration and info.fps else 0
+        dec = self._spawn(gpu.decode_cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, bufsize=0)
+        enc = self._spawn(gpu.encode_cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, bufsize=0)
+        done, last = 0, -1
+        try:
+            src_view, dst_view = memoryview(pin_in.array), memoryview(pin_out.array)
+            while not self._cancelled:
+                got = _read_exact(dec.stdout, src_view)
+                n = got // colour.in_frame_bytes
+                if n == 0:
+                    break
+                colour.run_host(lut, pin_in, pin_out, n)
+                enc.stdin.write(dst_view[:n * colour.out_frame_bytes])
+                done += n
+                if total:
+                    pct = min(int(done / total * span), span - (0 if final else 1))
+                    prog = min(base + pct, 100 if final else 99)
+                    if prog != last:
+                        last = prog
+                        self.signals.progress(self.task.task_id, prog)
+                if got < len(src_view):
+                    break
+        finally:
+            try:
+                enc.stdin.close()
+            except Exception:
+                pass
+            if self._cancelled:
+                for p in (dec, enc):
+                    if p.poll() is None:
+                        p.kill()
+            rc_dec, rc_enc = dec.wait(), enc.wait()
+            pin_in.close()
+            pin_out.close()
+            colour.close()
+        if self._cancelled:
+            return None
+        self._last_returncode = rc_enc or rc_dec
+        if rc_dec == 0 and rc_enc == 0:
+            if not final:
+                self.signals.progress(self.task.task_id, base + span)
+            return True
+        return False
+
+    def _run_plain(self, stage: CommandStage, info: Optional[VideoInfo], base: int, span: int, final: bool) -> Optional[bool]:
+        """A stage without LUT: the reference's own single ffmpeg process, progress parsed from its log."""
+        import re
+        cmd = build_command(stage.source_path, stage.output_path, stage.params, None, self.ffmpeg_bin, info, stage.notes)
+        for note in stage.notes:
+            self._log(note)
+        self._log(f"命令: {shlex.join(cmd)}")
+        dur_re = re.compile(r"Duration: (\d+):(\d+):(\d+(?:\.\d+)?)")
+        time_re = re.compile(r"time=(\d+):(\d+):(\d+(?:\.\d+)?)")
+        secs = lambda m: int(m.group(1)) * 3600 + int(m.group(2)) * 60 + float(m.group(3))  # noqa: E731
+        proc = self._spawn(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, bufsize=1)
+        duration, last = None, -1
+        for line in proc.stdout:
+            if self._cancelled:
+                break
+            if line.strip():
+                self._log(line.strip())
+            if duration is None:
+                m = dur_re.search(line)
+                if m:
+                    duration = secs(m)
+                    continue
+            m = time_re.search(line)
+            if m and duration:
+                pct = int(secs(m) / duration * span)
+                if not final:
+                    pct = min(pct, max(0, span - 1))
+                prog = min(base + pct, 100 if final else 99)
+                if prog != last:
+                    last = prog
+                    self.signals.progress(self.task.task_id, prog)
+        if self._cancelled:
+            if proc.poll() is None:
+                proc.kill()
+            return None
+        self._last_returncode = proc.wait()
+        if self._last_returncode == 0:
+            if not final:
+                self.signals.progress(self.task.task_id, base + span)
+            return True
+        return False
+
+
+class TaskManager:
+    """Queue + bounded concurrency (reference task_manager.py:219-315: QThreadPool with 1-16 runners); tasks are dealt to
+    the visible GPUs round-robin so concurrent runners do not share a device unless there are more runners than GPUs."""
+
+    def __init__(self, ffmpeg_bin: str = "ffmpeg", max_concurrency: int = 2, devices: Optional[List[int]] = None,
+                 callbacks: Optional[TaskCallbacks] = None):
+        self.ffmpeg_bin, self.max_concurrency = ffmpeg_bin, max(1, min(16, max_concurrency))
+        self.devices = devices or [0]
+        self.callbacks = callbacks or TaskCallbacks()
+        self.tasks: List[Task] = []
+        self._runners = {}
+
+    def add_tasks(self, tasks: List[Task]) -> None:
+        self.tasks.extend(tasks)
+
+    def start_all(self) -> None:
+        pending = [t for t in self.tasks if t.status == TaskStatus.PENDING]
+        sem = threading.Semaphore(self.max_concurrency)
+        threads = []
+
+        def work(task: Task, device: int):
+            with sem:
+                runner = TaskRunner(task, self.ffmpeg_bin, device, self.callbacks)
+                self._runners[task.task_id] = runner
+                runner.run()
+
+        for i, t in enumerate(pending):
+            th = threading.Thread(target=work, args=(t, self.devices[i % len(self.devices)]), daemon=True)
+            th.start()
+            threads.append(th)
+        for th in threads:
+            th.join()
+
+    def cancel_task(self, task_id: str) -> None:
+        r = self._runners.get(task_id)
+        if r:
+            r.cancel()

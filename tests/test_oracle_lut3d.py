@@ -1,0 +1,88 @@
+"""Known-answer tests for the oracle's vf_lut3d restatement ("parity unpinned": libavfilter is absent, so these pin the
+DEFINED semantics -- SURVEY.md App. C -- with hand-computed values)."""
+import numpy as np
+import pytest
+
+from lut_renderer_b200 import synth
+from oracle import oracle as O
+
+
+def _px(lut, r, g, b, depth=10, interp="tetrahedral"):
+    a = lambda v: np.full((1, 1), v, np.uint16)  # noqa: E731
+    R, G, B = O.lut3d_planar16(lut, a(r), a(g), a(b), depth, interp)
+    return int(R[0, 0]), int(G[0, 0]), int(B[0, 0])
+
+
+def test_identity_lut_is_not_bit_identity_because_of_truncation():
+    lut = O.OracleLut.from_table(synth.identity_lut(33).astype(np.float32))
+    vals = np.arange(1024, dtype=np.uint16).reshape(1, -1)
+    R, G, B = O.lut3d_planar16(lut, vals, vals, vals, 10, "tetrahedral")
+    d = vals.astype(int) - R.astype(int)
+    assert d.min() >= 0 and d.max() == 1 and 0 < (d != 0).mean() < 0.2   # truncating store: never above, sometimes one below
+    assert (R == G).all() and (G == B).all()
+    assert _px(lut, 0, 0, 0) == (0, 0, 0) and _px(lut, 1023, 1023, 1023) == (1023, 1023, 1023)
+
+
+def test_lut_memory_order_is_r_g_b_and_file_order_is_red_fastest():
+    n = 3
+    t = np.zeros((n, n, n, 3), np.float32)
+    t[2, 0, 0] = (1.0, 0.25, 0.5)     # node r=2, g=0, b=0
+    lut = O.OracleLut.from_text(synth.cube_text(t))
+    assert np.array_equal(lut.table, t)
+    assert _px(lut, 1023, 0, 0, interp="nearest") == (1023, 255, 511)   # 0.25*1023 = 255.75 -> 255, 0.5*1023 = 511.5 -> 511
+    assert _px(lut, 0, 1023, 0, interp="nearest") == (0, 0, 0)
+
+
+def test_tetrahedral_hand_computed():
+    # 2-point LUT = the unit cube corners; tetrahedral on f(r,g,b) = corner values
+    t = np.zeros((2, 2, 2, 3), np.float32)
+    for r in range(2):
+        for g in range(2):
+            for b in range(2):
+                t[r, g, b] = (0.1 * r + 0.2 * g + 0.4 * b, float(r and g), float(r or b))
+    lut = O.OracleLut.from_table(t)
+    f32 = np.float32
+    x = lambda v: f32(v) * f32(1.0 / 1023)   # noqa: E731
+    dr, dg, db = x(700), x(300), x(500)      # dr > db > dg -> vertices c000, c100, c101, c111
+    w = [f32(1) - dr, dr - db, db - dg, dg]
+    exp = []
+    for ch in range(3):
+        acc = f32(w[0] * t[0, 0, 0, ch])
+        acc = f32(acc + f32(w[1] * t[1, 0, 0, ch]))
+        acc = f32(acc + f32(w[2] * t[1, 0, 1, ch]))
+        acc = f32(acc + f32(w[3] * t[1, 1, 1, ch]))
+        exp.append(int(min(max(int(f32(acc * f32(1023.0))), 0), 1023)))
+    assert _px(lut, 700, 300, 500) == tuple(exp)
+
+
+def test_trilinear_vs_tetrahedral_agree_on_axes_and_differ_off_axis():
+    lut = O.OracleLut.from_table(synth.look_lut(17).astype(np.float32))
+    assert _px(lut, 512, 0, 0, interp="trilinear") == _px(lut, 512, 0, 0, interp="tetrahedral")
+    rng = np.random.default_rng(0)
+    R, G, B = (rng.integers(0, 1024, (8, 64), dtype=np.uint16) for _ in range(3))
+    a = O.lut3d_planar16(lut, R, G, B, 10, "trilinear")
+    b = O.lut3d_planar16(lut, R, G, B, 10, "tetrahedral")
+    assert any((x != y).any() for x, y in zip(a, b))
+    assert max(int(np.abs(x.astype(int) - y.astype(int)).max()) for x, y in zip(a, b)) < 40
+
+
+def test_out_of_range_lut_values_clip_and_domain_scale():
+    t = np.full((2, 2, 2, 3), -0.5, np.float32)
+    t[1, 1, 1] = 2.0
+    lut = O.OracleLut.from_table(t)
+    assert _px(lut, 0, 0, 0) == (0, 0, 0) and _px(lut, 1023, 1023, 1023) == (1023, 1023, 1023)
+    # DOMAIN_MAX 2 -> scale 0.5: full-scale input only reaches the middle of the table
+    ident = synth.identity_lut(3).astype(np.float32)
+    half = O.OracleLut.from_text(synth.cube_text(ident, domain=((0, 0, 0), (2, 2, 2))))
+    assert list(half.scale) == [0.5, 0.5, 0.5]
+    assert _px(half, 1023, 1023, 1023)[0] in (510, 511)
+    # DOMAIN_MAX 0.5 -> 1/(max-min) = 2 is clipped to 1
+    assert list(O.OracleLut.from_text(synth.cube_text(ident, domain=((0, 0, 0), (.5, .5, .5)))).scale) == [1.0, 1.0, 1.0]
+
+
+def test_8bit_packed_path():
+    lut = O.OracleLut.from_table(synth.identity_lut(33).astype(np.float32))
+    rgb = np.arange(256, dtype=np.uint8).repeat(3).reshape(1, -1)
+    out = O.lut3d_rgb24(lut, rgb, "tetrahedral")
+    d = rgb.astype(int) - out.astype(int)
+    assert d.min() >= 0 and d.max() <= 1

@@ -1,0 +1,106 @@
+"""Pins the oracle's integer models of the swscale legs against the REAL libswscale 9.1.100 (FFmpeg 8.0.1) that
+ships in this image -- the library the reference's `scale` / `format` filters run (ffmpeg.py:225-235, 309-310).
+Bit-exact on random full-code-range frames, known answers from SURVEY.md App. B.6."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import swscale_real as S
+
+pytestmark = pytest.mark.skipif(not S.available(), reason="bundled libswscale not loadable")
+
+
+def test_versions_and_coefficient_tables():
+    v = S.versions()
+    assert v["libswscale"].startswith("9."), v       # a different FFmpeg would need re-pinning
+    for name, mid in (("bt709", 0), ("bt601", 1), ("bt2020", 2), ("fcc", 3), ("smpte240m", 4)):
+        assert S.coefficients(name) == [int(O.lib().orc_inv_table(mid)[i]) for i in range(4)]
+    assert O.rgb2yuv_coeffs("bt709") == [5983, 20127, 2032, -3298, -11094, 14392, 14392, -13073, -1320]
+    assert O.rgb2yuv_coeffs("bt2020") == [7393, 19080, 1669, -4019, -10373, 14392, 14392, -13235, -1158]
+    assert O.rgb2yuv_coeffs("bt601") == [8414, 16519, 3208, -4865, -9528, 14392, 14392, -12061, -2332]
+    t = O.yuv2rgb_coeffs("bt709", False)
+    assert (t["yC"], t["vr"], t["ub"], t["ug"], t["vg"]) == (9539, 14686, 17305, -1747, -4366)
+
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (64, 16), (34, 12), (1000, 18)])
+@pytest.mark.parametrize("matrix", ["bt709", "bt601", "bt2020"])
+def test_yuv420p_legs_match_libswscale(w, h, matrix):
+    rng = np.random.default_rng(w * 31 + h)
+    for full in (0, 1):
+        Y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        U = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+        V = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+        ref = S.SwsConverter(w, h, "yuv420p", "rgb24", src_range=full, src_matrix=matrix, dst_matrix=matrix).convert(
+            [Y, U, V], S.alloc_planes("rgb24", w, h))[0]
+        assert np.array_equal(O.yuv420p_to_rgb24(Y, U, V, matrix, full), ref)
+    rgb = rng.integers(0, 256, (h, 3 * w), dtype=np.uint8)
+    ref = S.SwsConverter(w, h, "rgb24", "yuv420p", src_matrix=matrix, dst_matrix=matrix).convert([rgb], S.alloc_planes("yuv420p", w, h))
+    for a, b in zip(O.rgb24_to_yuv420p(rgb, matrix), ref):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("w,h", [(3840, 16), (1920, 8), (16, 2), (22, 3), (7680, 2)])
+@pytest.mark.parametrize("matrix", ["bt709", "bt601", "bt2020"])
+def test_yuv422p10_legs_match_libswscale(w, h, matrix):
+    rng = np.random.default_rng(w * 17 + h)
+    for full in (0, 1):
+        Y = rng.integers(0, 1024, (h, w), dtype=np.uint16)
+        U = rng.integers(0, 1024, (h, w // 2), dtype=np.uint16)
+        V = rng.integers(0, 1024, (h, w // 2), dtype=np.uint16)
+        g, b, r = S.SwsConverter(w, h, "yuv422p10le", "gbrp10le", src_range=full, src_matrix=matrix, dst_matrix=matrix).convert(
+            [Y, U, V], S.alloc_planes("gbrp10le", w, h))
+        R, G, B = O.yuv422p10_to_gbrp10(Y, U, V, matrix, full)
+        assert np.array_equal(R, r) and np.array_equal(G, g) and np.array_equal(B, b)
+    R, G, B = (rng.integers(0, 1024, (h, w), dtype=np.uint16) for _ in range(3))
+    ref = S.SwsConverter(w, h, "gbrp10le", "yuv422p10le", src_matrix=matrix, dst_matrix=matrix).convert(
+        [G, B, R], S.alloc_planes("yuv422p10le", w, h))
+    for a, b in zip(O.gbrp10_to_yuv422p10(R, G, B, matrix), ref):
+        assert np.array_equal(a, b)
+
+
+def test_range_pass_tables_match_libswscale():
+    tl, tc = O.range_tables()
+    w, h = 256, 12
+    for fmt in ("yuv420p", "yuv422p", "yuv444p"):
+        conv = S.SwsConverter(w, h, fmt, fmt, src_range=1, dst_range=0)
+        src = S.alloc_planes(fmt, w, h)
+        for p in src:
+            p[:] = np.resize(np.arange(256, dtype=np.uint8), p.shape[1])[None, :]
+        dst = conv.convert(src, S.alloc_planes(fmt, w, h))
+        assert np.array_equal(dst[0], tl[src[0]])
+        assert np.array_equal(dst[1], tc[src[1]]) and np.array_equal(dst[2], tc[src[2]])
+    assert (tl[0], tl[128], tl[255], tc[0], tc[128], tc[254], tc[255]) == (16, 126, 235, 16, 128, 239, 240)
+
+
+def test_known_answers_b6():
+    w, h = 64, 12
+    conv = S.SwsConverter(w, h, "yuv422p10le", "gbrp10le")
+    for y, exp in ((64, 0), (65, 1), (512, 522), (940, 1020), (941, 1021), (1023, 1023)):
+        planes = [np.full((h, w), y, np.uint16), np.full((h, w // 2), 512, np.uint16), np.full((h, w // 2), 512, np.uint16)]
+        g, b, r = conv.convert(planes, S.alloc_planes("gbrp10le", w, h))
+        R, G, B = O.yuv422p10_to_gbrp10(*planes)
+        assert int(r[3, 9]) == int(R[3, 9]) == exp
+    for v, exp in ((0, (64, 512, 512)), (512, (504, 512, 512)), (1023, (943, 512, 512))):
+        R = np.full((h, w), v, np.uint16)
+        Y, U, V = O.gbrp10_to_yuv422p10(R, R, R)
+        assert (int(Y[2, 5]), int(U[2, 5]), int(V[2, 5])) == exp
+    rgb = np.full((h, 3 * w), 128, np.uint8)
+    Y, U, V = O.rgb24_to_yuv420p(rgb)
+    assert (int(Y[4, 4]), int(U[2, 2]), int(V[2, 2])) == (126, 128, 128)
+    rgb = np.tile(np.array([200, 30, 77], np.uint8), (h, w)).reshape(h, 3 * w)
+    Y, U, V = O.rgb24_to_yuv420p(rgb)
+    assert int(U[2, 3]) == 131 and int(U[0, 3]) == 132 and int(U[h // 2 - 1, 3]) == 132   # edge-folded taps / C scaler
+
+
+def test_composite_with_real_swscale_legs_equals_oracle_composite():
+    """The full chain with REAL libswscale around the lut3d restatement == the all-oracle chain (what the GPU is held to)."""
+    from lut_renderer_b200 import synth
+    from oracle import cpu_baseline as C
+    for fmt, w, h, n in (("yuv422p10le", 640, 48, 33), ("yuv420p", 320, 36, 17)):
+        lut = O.OracleLut.from_table(synth.look_lut(n).astype(np.float32))
+        for frame in (synth.natural_frame(fmt, w, h, 2), synth.noise_frame(fmt, w, h, 4)):
+            planes = [np.ascontiguousarray(p) for p in synth.split_planes(frame, fmt, w, h)]
+            a = C.CpuStage(fmt, w, h, lut, use_swscale=True).run(planes)
+            b = C.CpuStage(fmt, w, h, lut, use_swscale=False).run(planes)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
