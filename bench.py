@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=0)
     ap.add_argument("--rows-per-cta", type=int, default=0)
     ap.add_argument("--band-rows", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="stage tunable name=value (see lutr_stage_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -229,6 +230,9 @@ def main():
         stage.set_option("rows_per_cta", args.rows_per_cta)
     if args.band_rows:
         stage.set_option("band_rows", args.band_rows)
+    for kv in args.opt:
+        name, _, value = kv.partition("=")
+        stage.set_option(name, int(value))
     table = make_lut_table(cfg["lut"])
     lut = stage.ctx.lut_from_table(table)
     # this rank's contiguous frame range of the (world * F)-frame clip, resident in HBM
@@ -338,7 +342,7 @@ def main():
             "ms_per_step": round(per_launch_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u16+f32" if cfg["pix_fmt"] == "yuv422p10le" else "u8+f32", "data": "synthetic",
             "gpix_per_s": round(fps * mpix / 1e3, 3),
-            "config": {"workload": cfg["desc"], "content": args.content, "frames_per_step": F, "float_mode": args.float_mode,
+            "config": {"workload": cfg["desc"], "content": args.content, "frames_per_step": F, "float_mode": args.float_mode, "options": args.opt,
                        "l2": f"inputs larger than L2 ({F * bytes_per_frame / 2 / 1e6:.0f} MB read + same written per step)",
                        "sharding": "contiguous frame range per GPU, no collective", "parity_spot_check": parity},
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1),

@@ -149,7 +149,8 @@ LUTR_API int lutr_stage_run_host(lutr_stage *stage, const lutr_lut *lut, const v
 LUTR_API int lutr_stage_sync(lutr_stage *stage);
 /* number of kernel launches this stage has enqueued so far (bench.py's gpu_launches) */
 LUTR_API int64_t lutr_stage_launch_count(const lutr_stage *stage);
-/* run-time tunables, for benchmarking: "rows_per_cta", "band_rows", "l2_persist" (0/1) */
+/* run-time tunables, for benchmarking: "rows_per_cta", "band_rows", "l2_persist" (0/1), "fast_path" (0/1),
+ * "grid_ctas" (persistent grid of the fast kernels) */
 LUTR_API int lutr_stage_set_option(lutr_stage *stage, const char *name, int32_t value);
 
 /* ---- coefficient tables (exposed so the parity tests can pin them against libswscale) --------------- */

@@ -25,6 +25,14 @@ struct lutr_lut {
     float scale[3] = {1.f, 1.f, 1.f};
     float4 *dev = nullptr;   // size^3 nodes + tail padding
     size_t dev_bytes = 0;
+    bool needs_clamp = false;  // some entry lies outside [0,1]: the truncating store needs its clip
+};
+
+// device copy of one index table; depends on (bit depth, LUT size, domain scale) only, never overwritten once built
+struct IdxTable {
+    int depth = 0, n = 0;
+    float scale = 0.f;
+    IdxEntry *dev = nullptr;
 };
 
 struct lutr_stage {
@@ -46,6 +54,11 @@ struct lutr_stage {
     int band_rows = 0;     // 0 = auto
     int l2_persist = 1;
     const lutr_lut *persist_lut = nullptr;
+    std::vector<IdxTable> idx_tables;
+    int use_fast = 1;      // 0 forces the generic kernels (testing)
+    int grid_ctas = 0;     // 0 = min_blocks CTAs per SM
+    int idx_mode = 1;      // 0 = shared-memory index table, 1 = arithmetic index
+    int min_blocks = 3;    // occupancy variant of the fast kernels
     std::atomic<int64_t> launches{0};
 };
 
@@ -98,6 +111,8 @@ int upload_lut(lutr_ctx *ctx, const CubeLut &c, lutr_lut **out) {
             return LUTR_ERR_INVALID_DATA;
         }
         host[i] = make_float4(c.rgb[3 * i], c.rgb[3 * i + 1], c.rgb[3 * i + 2], 0.f);
+        for (int ch = 0; ch < 3; ++ch)
+            if (c.rgb[3 * i + ch] < 0.f || c.rgb[3 * i + ch] > 1.f) l->needs_clamp = true;
     }
     l->dev_bytes = host.size() * sizeof(float4);
     cudaError_t e = cudaMalloc((void **)&l->dev, l->dev_bytes);
@@ -146,6 +161,38 @@ int set_l2_window(lutr_stage *s, const lutr_lut *lut, cudaStream_t st) {
     return LUTR_OK;
 }
 
+// The fast kernels need one domain scale for all channels and luma rows whose 15-bit sum cannot saturate.
+bool fast_path_ok(const lutr_stage *s, const lutr_lut *lut) {
+    if (!s->use_fast || s->d.interp == LUTR_INTERP_NEAREST) return false;
+    if (lut->scale[0] != lut->scale[1] || lut->scale[0] != lut->scale[2]) return false;
+    const int maxv = (1 << s->depth) - 1;
+    const long ysum = (long)(s->b.ry + s->b.gy + s->b.by) * maxv;
+    if (s->b.ry < 0 || s->b.gy < 0 || s->b.by < 0) return false;
+    // 10 bit: y14 = (sum + (16<<17) + (1<<10)) >> 11 must keep 2*y14 <= 32767;  8 bit: (sum + (32<<14) + (1<<8)) >> 9 likewise
+    const long y14 = s->depth == 10 ? (ysum + (16 << 17) + (1 << 10)) >> 11 : (ysum + (32 << 14) + (1 << 8)) >> 9;
+    return 2 * y14 <= 32767;
+}
+
+int get_index_table(lutr_stage *s, const lutr_lut *lut, cudaStream_t st, const IdxEntry **out) {
+    for (const IdxTable &t : s->idx_tables)
+        if (t.depth == s->depth && t.n == lut->size && t.scale == lut->scale[0]) {
+            *out = t.dev;
+            return LUTR_OK;
+        }
+    const int entries = s->depth == 10 ? kIdxEntries10 : kIdxEntries8;
+    std::vector<IdxEntry> host(entries);
+    const float lut_max = (float)(lut->size - 1);
+    build_index_table(s->depth, entries, lut->scale[0] * lut_max, lut_max, host.data());
+    IdxTable t;
+    t.depth = s->depth, t.n = lut->size, t.scale = lut->scale[0];
+    CUDA_TRY(cudaMalloc((void **)&t.dev, entries * sizeof(IdxEntry)));
+    // pageable source: the runtime stages it before returning, so `host` may go out of scope
+    CUDA_TRY(cudaMemcpyAsync(t.dev, host.data(), entries * sizeof(IdxEntry), cudaMemcpyHostToDevice, st));
+    s->idx_tables.push_back(t);
+    *out = t.dev;
+    return LUTR_OK;
+}
+
 int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lutr_planes *out, int nframes, cudaStream_t st) {
     StageK k{};
     k.w = s->d.width, k.h = s->d.height, k.nframes = nframes;
@@ -169,6 +216,44 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         s->persist_lut = lut;
     }
     int rc;
+    k.idx_tab = nullptr;
+    k.idx_mode = -1;
+    k.min_blocks = s->min_blocks;
+    k.clamp_out = lut->needs_clamp ? 1 : 0;
+    k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : s->min_blocks * s->ctx->sm_count;
+    if (fast_path_ok(s, lut)) {
+        k.idx_mode = s->idx_mode;
+        if (s->idx_mode == 0) {
+            rc = get_index_table(s, lut, st, &k.idx_tab);
+            if (rc != LUTR_OK) return rc;
+        }
+        const uint32_t magic = 0x4B000000u;  // bits of 8388608.0f: bias of the truncated LUT outputs
+        FastK &fk = k.fk;
+        const uint32_t yK = (uint32_t)(-s->f.yOff10 * s->f.yC) + (1u << 19);
+        fk.yA = (uint32_t)(128 * s->f.yC);
+        fk.vr4 = (uint32_t)(4 * s->f.vr), fk.vg4 = (uint32_t)(4 * s->f.vg), fk.ug4 = (uint32_t)(4 * s->f.ug), fk.ub4 = (uint32_t)(4 * s->f.ub);
+        fk.kR = yK - 65536u * (uint32_t)s->f.vr;
+        fk.kG = yK - 65536u * (uint32_t)s->f.vg - 65536u * (uint32_t)s->f.ug;
+        fk.kB = yK - 65536u * (uint32_t)s->f.ub;
+        if (s->depth == 10) {
+            fk.kY = (uint32_t)((16 << 17) + (1 << 10) + (8 << 11)) - magic * (uint32_t)(s->b.ry + s->b.gy + s->b.by);
+            fk.kU = (uint32_t)((128 << 17) + (1 << 10)) - magic * (uint32_t)(s->b.ru + s->b.gu + s->b.bu);
+            fk.kV = (uint32_t)((128 << 17) + (1 << 10)) - magic * (uint32_t)(s->b.rv + s->b.gv + s->b.bv);
+        } else {
+            fk.kY = (uint32_t)((32 << 14) + (1 << 8) + (32 << 9)) - magic * (uint32_t)(s->b.ry + s->b.gy + s->b.by);
+            fk.kU = (uint32_t)((256 << 15) + (1 << 9)) - 2u * magic * (uint32_t)(s->b.ru + s->b.gu + s->b.bu);
+            fk.kV = (uint32_t)((256 << 15) + (1 << 9)) - 2u * magic * (uint32_t)(s->b.rv + s->b.gv + s->b.bv);
+        }
+        fk.n2b = k.lut.n2 * 16, fk.nb = k.lut.n * 16, fk.totalb = fk.n2b + fk.nb + 16;
+        // arithmetic index: fold a power-of-two LUT scale into the input scale (exact: scaling by 2^k commutes with rounding)
+        int exp2 = 0;
+        const float sr = k.lut.sr;
+        fk.idx_fold = (sr > 0.f && std::frexp(sr, &exp2) == 0.5f) ? 1 : 0;
+        fk.idx_mul = fk.idx_fold ? k.lut.in_scale * sr : k.lut.in_scale;
+        fk.idx_sr = fk.idx_fold ? 1.f : sr;
+        fk.idx_add = -(fk.idx_mul * 8388608.f);
+        fk.maxv = maxv;
+    }
     if (s->d.in_fmt == LUTR_PIX_YUV422P10LE) {
         k.rows_per_cta = s->rows_per_cta > 0 ? s->rows_per_cta : 1;
         k.bands = 1;
@@ -195,6 +280,12 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     }
     s->launches.fetch_add(1, std::memory_order_relaxed);
     return LUTR_OK;
+}
+
+void free_index_tables(lutr_stage *s) {
+    for (IdxTable &t : s->idx_tables)
+        if (t.dev) cudaFree(t.dev);
+    s->idx_tables.clear();
 }
 
 void free_host_pipeline(lutr_stage *s) {
@@ -454,6 +545,7 @@ void lutr_stage_destroy(lutr_stage *s) {
     cudaSetDevice(s->ctx->device);
     if (s->compute) cudaStreamSynchronize(s->compute);
     free_host_pipeline(s);
+    free_index_tables(s);
     if (s->ev_ok)
         for (int i = 0; i < lutr_stage::NBUF; ++i) {
             cudaEventDestroy(s->ev_in[i]);
@@ -566,6 +658,10 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     if (!s || !name) return LUTR_ERR_INVALID_ARG;
     if (!std::strcmp(name, "rows_per_cta")) s->rows_per_cta = value;
     else if (!std::strcmp(name, "band_rows")) s->band_rows = value;
+    else if (!std::strcmp(name, "fast_path")) s->use_fast = value;
+    else if (!std::strcmp(name, "grid_ctas")) s->grid_ctas = value;
+    else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value ? 1 : 0;
+    else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value == 4 ? 4 : 3;
     else if (!std::strcmp(name, "l2_persist")) {
         s->l2_persist = value;
         s->persist_lut = nullptr;

@@ -46,11 +46,33 @@ struct LutK {
     float out_scale;    // (float)(2^depth - 1)
 };
 
+// Per-channel index table of the fast kernels: entry i (a 12-bit / 11-bit two's-complement code value, so that the
+// clamp of the YUV->RGB result is part of the lookup) -> {prev node index, fraction d} exactly as lut3d computes them.
+struct IdxEntry {
+    int32_t prev;
+    float d;
+};
+constexpr int kIdxEntries10 = 4096;  // (R >> 20) & 0xFFF for the 10-bit path
+constexpr int kIdxEntries8 = 2048;   // (yy + c) & 0x7FF for the 8-bit path
+
 struct PlaneSet {
     const uint8_t *in[3];
     uint8_t *out[3];
     int32_t in_stride[3], out_stride[3];  // bytes
     int64_t in_step, out_step;            // bytes between frames
+};
+
+// Constants of the fast kernels, derived on the host so they sit in the constant bank instead of registers.
+struct FastK {
+    uint32_t yA;                  // 128 * yC (10 bit)
+    uint32_t vr4, vg4, ug4, ub4;  // 4 * chroma gains (u17 = 4*c15 - 65536 folded in)
+    uint32_t kR, kG, kB;          // luma offset, rounding and the -65536*gain terms
+    uint32_t kY, kU, kV;          // rounding/offset constants of RGB->YUV with the 0x4B000000 bias folded in
+    int32_t n2b, nb, totalb;      // byte steps of the LUT axes: n*n*16, n*16, sum + 16
+    // arithmetic index path: s = min(fl(fl(x*in_scale) * sr), lut_max) computed as fma(2^23+x, idx_mul, idx_add) [* idx_sr]
+    float idx_mul, idx_add, idx_sr;
+    int32_t idx_fold;             // 1: sr is a power of two and was folded into idx_mul (no second multiply)
+    int32_t maxv;                 // 2^depth - 1
 };
 
 struct StageK {
@@ -63,7 +85,16 @@ struct StageK {
     Rgb2YuvK b;
     LutK lut;
     PlaneSet p;
+    FastK fk;
+    const IdxEntry *idx_tab;  // device copy of the index table (fast kernels), nullptr -> generic kernels
+    int32_t clamp_out;        // 1: LUT entries leave [0,1], the store needs its clip
+    int32_t grid_ctas;        // persistent grid size of the fast kernels
+    int32_t idx_mode;         // 0: shared-memory index table, 1: arithmetic index (no table)
+    int32_t min_blocks;       // occupancy variant of the fast kernel (3 or 4 CTAs of 256 threads per SM)
 };
+
+// host-side construction of the index table (colour_tables.cpp): same float operations as lut3d's per-pixel prologue
+void build_index_table(int depth, int entries, float scale_times_lutmax, float lut_max, IdxEntry *out);
 
 // launchers (stage_kernels.cu); `stream` is a cudaStream_t
 int launch_yuv422p10(const StageK &k, int interp, int float_mode, void *stream);

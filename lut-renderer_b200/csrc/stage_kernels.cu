@@ -251,6 +251,224 @@ __global__ void __launch_bounds__(512, 2) k_yuv422p10(const StageK K) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path building blocks (used when all three channels share one domain scale and interp != nearest).
+//
+//  * index table in shared memory: code value (with the YUV->RGB clip folded into the index) -> {prev, d}; the entries are
+//    computed on the host with lut3d's own float operations, so the lookup is exact by construction and replaces
+//    I2F, 2 FMUL, 2 FMNMX, F2I, I2F, FADD per channel by one LDS.64.
+//  * "next" nodes are NOT clamped: prev == n-1 only happens with d == 0, and every vertex that uses the step of a channel
+//    with d == 0 has weight exactly 0 (tetrahedral: it is the smallest fraction; trilinear: lerp factor 0), so the
+//    out-of-cell node only needs to be finite and inside the (zero-padded) buffer.  x + 0*finite == x bit for bit.
+//  * fractions are non-negative floats, so they sort as integers: max3 / min3 / xor-median, no float compares.
+//  * truncating store: float -> int by adding 2^23 with round-toward-zero; the integer stays biased by 0x4B000000 and the
+//    bias is folded into the constants of the following integer matrix (wrapping 32-bit arithmetic).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr unsigned kMagicBits = 0x4B000000u;  // bits of 8388608.0f
+
+__device__ __forceinline__ float4 ldg_node(const char *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// Exact lut3d prologue for one channel without I2F/F2I: x in [0, maxv] -> (prev biased by 0x4B000000, d).
+//   fl(x * c) = fma(2^23 + x, c, -2^23 * c)   (the product is exact in the fma, one rounding like the plain multiply)
+//   floor(s)  = (s + 2^23 rounded toward zero) - 2^23
+template <int IDX>
+__device__ __forceinline__ void idx_arith(int x, const FastK &fk, float lut_max, unsigned &prev_biased, unsigned &dbits) {
+    const float m = __uint_as_float((unsigned)x | kMagicBits);
+    float s = __fmaf_rn(m, fk.idx_mul, fk.idx_add);
+    if (IDX == 2) s = __fmul_rn(s, fk.idx_sr);
+    s = fminf(s, lut_max);
+    const float t = __fadd_rz(s, 8388608.f);
+    prev_biased = __float_as_uint(t);
+    dbits = __float_as_uint(__fsub_rn(s, __fsub_rn(t, 8388608.f)));
+}
+
+// pr/pg/pb: prev node indices (biased by `bias` each, folded out through kbase); dr/dg/db: fraction bits.
+template <int INTERP, bool FMA, bool CLAMP>
+__device__ __forceinline__ void lut3d_fast(const char *tab, int n, int n2, unsigned kbase, int n2b, int nb, int total, float out_scale,
+                                           unsigned pr, unsigned pg, unsigned pb, unsigned dr_, unsigned dg_, unsigned db_,
+                                           unsigned &rb, unsigned &gb, unsigned &bb) {
+    const unsigned base = pr * (unsigned)n2 + (pg * (unsigned)n + kbase) + pb;
+    const char *p000 = tab + (size_t)base * 16u;
+    float4 c;
+    if (INTERP == LUTR_INTERP_TRILINEAR) {
+        const float dr = __uint_as_float(dr_), dg = __uint_as_float(dg_), db = __uint_as_float(db_);
+        const float4 c000 = ldg_node(p000), c001 = ldg_node(p000 + 16);
+        const float4 c010 = ldg_node(p000 + nb), c011 = ldg_node(p000 + nb + 16);
+        const float4 c100 = ldg_node(p000 + n2b), c101 = ldg_node(p000 + n2b + 16);
+        const float4 c110 = ldg_node(p000 + n2b + nb), c111 = ldg_node(p000 + n2b + nb + 16);
+        const float4 c00 = lerp3<FMA>(c000, c100, dr), c10 = lerp3<FMA>(c010, c110, dr);
+        const float4 c01 = lerp3<FMA>(c001, c101, dr), c11 = lerp3<FMA>(c011, c111, dr);
+        const float4 c0 = lerp3<FMA>(c00, c10, dg), c1 = lerp3<FMA>(c01, c11, dg);
+        c = lerp3<FMA>(c0, c1, db);
+    } else {
+        const int ar = (int)dr_, ag = (int)dg_, ab = (int)db_;
+        const int mx = __vimax3_s32(ar, ag, ab), mn = __vimin3_s32(ar, ag, ab);
+        const int md = ar ^ ag ^ ab ^ mx ^ mn;
+        // step of the largest fraction first, of the smallest last (tie order is irrelevant: tied steps carry weight 0)
+        const int o1 = (ar == mx) ? n2b : ((ag == mx) ? nb : 16);
+        const int o3 = (ab == mn) ? 16 : ((ag == mn) ? nb : n2b);
+        const float4 c000 = ldg_node(p000), cA = ldg_node(p000 + o1), cB = ldg_node(p000 + (total - o3)), c111 = ldg_node(p000 + total);
+        const float d1 = __int_as_float(mx), d2 = __int_as_float(md), d3 = __int_as_float(mn);
+        const float w0 = __fsub_rn(1.f, d1), w1 = __fsub_rn(d1, d2), w2 = __fsub_rn(d2, d3), w3 = d3;
+        c.x = madd<FMA>(w3, c111.x, madd<FMA>(w2, cB.x, madd<FMA>(w1, cA.x, __fmul_rn(w0, c000.x))));
+        c.y = madd<FMA>(w3, c111.y, madd<FMA>(w2, cB.y, madd<FMA>(w1, cA.y, __fmul_rn(w0, c000.y))));
+        c.z = madd<FMA>(w3, c111.z, madd<FMA>(w2, cB.z, madd<FMA>(w1, cA.z, __fmul_rn(w0, c000.z))));
+    }
+    float fr = __fmul_rn(c.x, out_scale), fg = __fmul_rn(c.y, out_scale), fb = __fmul_rn(c.z, out_scale);
+    if (CLAMP) {
+        fr = fminf(fmaxf(fr, 0.f), out_scale), fg = fminf(fmaxf(fg, 0.f), out_scale), fb = fminf(fmaxf(fb, 0.f), out_scale);
+    }
+    rb = __float_as_uint(__fadd_rz(fr, 8388608.f));
+    gb = __float_as_uint(__fadd_rz(fg, 8388608.f));
+    bb = __float_as_uint(__fadd_rz(fb, 8388608.f));
+}
+
+// yuv422p10le -> yuv422p10le, fast path.  Persistent CTAs: CTA b owns rows b, b + gridDim.x, ... of the (frame, row) space.
+// A thread owns 4-pixel groups (8 B of Y, one 32-bit word = 2 samples of U and of V); the chroma words of the two
+// neighbouring groups come from the adjacent lanes by warp shuffle (warp-edge lanes fetch them from L1/L2).
+// IDX: 0 = index table in shared memory, 1 = arithmetic with the LUT scale folded (power of two), 2 = arithmetic, general
+template <int INTERP, bool FMA, bool CLAMP, int IDX, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_yuv422p10_fast(const StageK K) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2 *s_idx = reinterpret_cast<uint2 *>(smem_raw);                                                       // [4096] {prev, d} (IDX == 0)
+    unsigned *s_c14 = reinterpret_cast<unsigned *>(smem_raw + (IDX == 0 ? kIdxEntries10 * sizeof(uint2) : 0));  // [2][w + 8], 4 pad each side
+    const int w = K.w, groups = w >> 2, pitch = w + 8;
+    if (IDX == 0) {
+        for (int i = threadIdx.x; i < kIdxEntries10 / 2; i += blockDim.x)
+            reinterpret_cast<uint4 *>(s_idx)[i] = __ldg(reinterpret_cast<const uint4 *>(K.idx_tab) + i);
+        __syncthreads();
+    }
+
+    const Rgb2YuvK b = K.b;
+    const FastK fk = K.fk;
+    const char *tab = reinterpret_cast<const char *>(K.lut.tab);
+    const int n = K.lut.n, n2 = K.lut.n2;
+    const float out_scale = K.lut.out_scale, lut_max = K.lut.lut_max;
+    const unsigned kbase = IDX == 0 ? 0u : 0u - kMagicBits * (unsigned)(n2 + n + 1);
+    const long total_rows = (long)K.h * K.nframes;
+    const int lane = threadIdx.x & 31;
+    const int gloop = (groups + 31) & ~31;  // whole warps enter the loop so the shuffles are convergent
+    int parity = 0;
+
+    for (long grow = blockIdx.x; grow < total_rows; grow += gridDim.x, parity ^= 1) {
+        const int frame = (int)(grow / K.h), y = (int)(grow - (long)frame * K.h);
+        const uint8_t *inY = K.p.in[0] + frame * K.p.in_step + (long)y * K.p.in_stride[0];
+        const uint8_t *inU = K.p.in[1] + frame * K.p.in_step + (long)y * K.p.in_stride[1];
+        const uint8_t *inV = K.p.in[2] + frame * K.p.in_step + (long)y * K.p.in_stride[2];
+        uint8_t *outY = K.p.out[0] + frame * K.p.out_step + (long)y * K.p.out_stride[0];
+        uint8_t *outU = K.p.out[1] + frame * K.p.out_step + (long)y * K.p.out_stride[1];
+        uint8_t *outV = K.p.out[2] + frame * K.p.out_step + (long)y * K.p.out_stride[2];
+        unsigned *sc = s_c14 + parity * pitch + 4;  // sc[x] for x in [-4, w+4)
+
+        for (int gi = threadIdx.x; gi < gloop; gi += blockDim.x) {
+            const bool valid = gi < groups;
+            const int g = valid ? gi : groups - 1;
+            const int x0 = g << 2;
+            const uint2 yv = ldg_stream8(inY + 2 * x0);
+            const unsigned uw = ldg_stream4(inU + x0), vw = ldg_stream4(inV + x0);   // samples 2g, 2g+1
+            unsigned ul = __shfl_up_sync(0xFFFFFFFFu, uw, 1), vl = __shfl_up_sync(0xFFFFFFFFu, vw, 1);
+            unsigned ur = __shfl_down_sync(0xFFFFFFFFu, uw, 1), vr = __shfl_down_sync(0xFFFFFFFFu, vw, 1);
+            if (g == 0) {  // clamp at the left edge of the row: C[-2] = C[-1] = C[0]
+                ul = (uw & 0xFFFFu) * 0x10001u, vl = (vw & 0xFFFFu) * 0x10001u;
+            } else if (lane == 0) {
+                ul = __ldg((const unsigned *)(inU + x0 - 4)), vl = __ldg((const unsigned *)(inV + x0 - 4));
+            }
+            if (g == groups - 1) {
+                ur = (uw >> 16) * 0x10001u, vr = (vw >> 16) * 0x10001u;
+            } else if (lane == 31) {
+                ur = __ldg((const unsigned *)(inU + x0 + 4)), vr = __ldg((const unsigned *)(inV + x0 + 4));
+            }
+            // chroma window e[0..5] = C[i0-2 .. i0+3]
+            const int eu[6] = {(int)(ul & 0xFFFF), (int)(ul >> 16), (int)(uw & 0xFFFF), (int)(uw >> 16), (int)(ur & 0xFFFF), (int)(ur >> 16)};
+            const int ev[6] = {(int)(vl & 0xFFFF), (int)(vl >> 16), (int)(vw & 0xFFFF), (int)(vw >> 16), (int)(vr & 0xFFFF), (int)(vr >> 16)};
+            unsigned yo[2], pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned yw = k < 2 ? yv.x : yv.y;
+                const unsigned Y = (k & 1) ? (yw >> 16) : (yw & 0xFFFF);
+                const int j = k >> 1;
+                int cu, cv;
+                if (!(k & 1)) {  // even column 2i: taps on C[i-2 .. i+1]
+                    cu = up4(eu[j], eu[j + 1], eu[j + 2], eu[j + 3], -461, 3943, 14284, -1382);
+                    cv = up4(ev[j], ev[j + 1], ev[j + 2], ev[j + 3], -461, 3943, 14284, -1382);
+                    if (g == 0) {  // the two left-most even columns use swscale's edge-normalised taps
+                        if (k == 0) {
+                            cu = min((17729 * eu[2] - 1345 * eu[3]) >> 9, 32767);
+                            cv = min((17729 * ev[2] - 1345 * ev[3]) >> 9, 32767);
+                        } else {
+                            cu = min((3835 * eu[2] + 13894 * eu[3] - 1345 * eu[4]) >> 9, 32767);
+                            cv = min((3835 * ev[2] + 13894 * ev[3] - 1345 * ev[4]) >> 9, 32767);
+                        }
+                    }
+                } else {  // odd column 2i+1: taps on C[i-1 .. i+2]
+                    cu = up4(eu[j + 1], eu[j + 2], eu[j + 3], eu[j + 4], -1382, 14284, 3943, -461);
+                    cv = up4(ev[j + 1], ev[j + 2], ev[j + 3], ev[j + 4], -1382, 14284, 3943, -461);
+                }
+                const unsigned yy = Y * fk.yA;
+                const int R = (int)(yy + (unsigned)cv * fk.vr4 + fk.kR);
+                const int G = (int)(yy + (unsigned)cv * fk.vg4 + (unsigned)cu * fk.ug4 + fk.kG);
+                const int B = (int)(yy + (unsigned)cu * fk.ub4 + fk.kB);
+                uint2 er, eg, eb;
+                if (IDX == 0) {
+                    // table index = 12-bit two's-complement code of (x >> 20): the clip to [0,1023] is part of the table
+                    er = *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(s_idx) + ((unsigned)(R >> 17) & 0x7FF8u));
+                    eg = *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(s_idx) + ((unsigned)(G >> 17) & 0x7FF8u));
+                    eb = *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(s_idx) + ((unsigned)(B >> 17) & 0x7FF8u));
+                } else {
+                    // av_clip_uintp2(x, 30) >> 20 == clamp(x >> 20, 0, 1023)
+                    idx_arith<IDX>(clamp_u(R >> 20, 1023), fk, lut_max, er.x, er.y);
+                    idx_arith<IDX>(clamp_u(G >> 20, 1023), fk, lut_max, eg.x, eg.y);
+                    idx_arith<IDX>(clamp_u(B >> 20, 1023), fk, lut_max, eb.x, eb.y);
+                }
+                unsigned rb, gb, bb;
+                lut3d_fast<INTERP, FMA, CLAMP>(tab, n, n2, kbase, fk.n2b, fk.nb, fk.totalb, out_scale, er.x, eg.x, eb.x, er.y, eg.y, eb.y,
+                                               rb, gb, bb);
+                // Y: clip10((min(2*y14, 32767) + 16) >> 5) with y14 = S >> 11  ==  (S + (8 << 11)) >> 15 (the min and the clip
+                // never bind: S < 2^25 for 10-bit RGB with any of the luma rows; checked on the host)
+                const unsigned yq = (unsigned)((int)((unsigned)b.ry * rb + (unsigned)b.gy * gb + (unsigned)b.by * bb + fk.kY) >> 15);
+                const unsigned u14 = (unsigned)((int)((unsigned)b.ru * rb + (unsigned)b.gu * gb + (unsigned)b.bu * bb + fk.kU) >> 11);
+                const unsigned v14 = (unsigned)((int)((unsigned)b.rv * rb + (unsigned)b.gv * gb + (unsigned)b.bv * bb + fk.kV) >> 11);
+                pk[k] = (v14 << 16) + u14;
+                if (k & 1) yo[k >> 1] |= yq << 16;
+                else yo[k >> 1] = yq;
+            }
+            if (valid) {
+                *reinterpret_cast<uint4 *>(sc + x0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (g == 0) *reinterpret_cast<uint4 *>(sc - 4) = make_uint4(pk[0], pk[0], pk[0], pk[0]);          // clamp left
+                if (g == groups - 1) *reinterpret_cast<uint4 *>(sc + w) = make_uint4(pk[3], pk[3], pk[3], pk[3]);  // clamp right
+                stg_stream8(outY + 2 * x0, make_uint2(yo[0], yo[1]));
+            }
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+            const int x0 = g << 2;
+            // t[0..11] = packed c14 of columns x0-4 .. x0+7; chroma column 2g+j needs columns x0+2j-3 .. x0+2j+4 = t[2j+1 .. 2j+8]
+            unsigned t[12];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint4 v4 = *reinterpret_cast<const uint4 *>(sc + x0 - 4 + 4 * q);
+                t[4 * q] = v4.x, t[4 * q + 1] = v4.y, t[4 * q + 2] = v4.z, t[4 * q + 3] = v4.w;
+            }
+            unsigned uo = 0, vo = 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                // symmetric taps: add the mirrored columns while still packed (u and v sums stay below 2^16)
+                const unsigned s0 = t[2 * j + 1] + t[2 * j + 8], s1 = t[2 * j + 2] + t[2 * j + 7];
+                const unsigned s2 = t[2 * j + 3] + t[2 * j + 6], s3 = t[2 * j + 4] + t[2 * j + 5];
+                const int su = -230 * (int)(s0 & 0xFFFF) - 692 * (int)(s1 & 0xFFFF) + 1972 * (int)(s2 & 0xFFFF) + 7142 * (int)(s3 & 0xFFFF) + (16 << 13);
+                const int sv = -230 * (int)(s0 >> 16) - 692 * (int)(s1 >> 16) + 1972 * (int)(s2 >> 16) + 7142 * (int)(s3 >> 16) + (16 << 13);
+                // clip10((min(S >> 13, 32767) + 16) >> 5) == clamp((S + (16 << 13)) >> 18, 0, 1023)
+                uo |= (unsigned)clamp_u(su >> 18, 1023) << (16 * j);
+                vo |= (unsigned)clamp_u(sv >> 18, 1023) << (16 * j);
+            }
+            stg_stream4(outU + x0, uo);
+            stg_stream4(outV + x0, vo);
+        }
+        // the next row uses the other half of s_c14; its barrier orders these reads before that half is reused
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // yuv420p (8 bit) -> yuv420p   (BASELINE cfg 1 / 2)
 // A CTA owns one band of luma rows of one frame and walks down it; a thread owns 8-pixel column groups.
@@ -370,6 +588,26 @@ int launch422(const StageK &k, int float_mode, cudaStream_t st) {
     int per = (groups + 511) / 512;                   // groups per thread
     int threads = ((groups + per - 1) / per + 31) / 32 * 32;
     const long total_rows = (long)k.h * k.nframes;
+    if (k.idx_mode >= 0 && INTERP != LUTR_INTERP_NEAREST) {
+        const int idx = k.idx_mode == 0 ? 0 : (k.fk.idx_fold ? 1 : 2);
+        const size_t smem = (idx == 0 ? kIdxEntries10 * sizeof(uint2) : 0) + (size_t)2 * (k.w + 8) * sizeof(unsigned);
+        void (*fn)(const StageK) = nullptr;
+        const bool fma = float_mode == LUTR_FLOAT_FMA, clamp = k.clamp_out != 0;
+        const int mb = k.min_blocks == 4 ? 4 : 3;
+#define LUTR_PICK(F, C, I, M) \
+    if (fma == F && clamp == C && idx == I && mb == M) fn = k_yuv422p10_fast<INTERP, F, C, I, M>;
+#define LUTR_PICK_M(F, C, I) LUTR_PICK(F, C, I, 3) LUTR_PICK(F, C, I, 4)
+#define LUTR_PICK_I(F, C) LUTR_PICK_M(F, C, 0) LUTR_PICK_M(F, C, 1) LUTR_PICK_M(F, C, 2)
+        LUTR_PICK_I(false, false) LUTR_PICK_I(false, true) LUTR_PICK_I(true, false) LUTR_PICK_I(true, true)
+#undef LUTR_PICK_I
+#undef LUTR_PICK_M
+#undef LUTR_PICK
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        long grid = k.grid_ctas > 0 ? k.grid_ctas : 148 * mb;
+        if (grid > total_rows) grid = total_rows;
+        fn<<<(unsigned)grid, 256, smem, st>>>(k);
+        return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
+    }
     const unsigned grid = (unsigned)((total_rows + k.rows_per_cta - 1) / k.rows_per_cta);
     const size_t smem = (size_t)2 * k.w * sizeof(unsigned);
     auto fn = float_mode == LUTR_FLOAT_FMA ? k_yuv422p10<INTERP, true> : k_yuv422p10<INTERP, false>;
