@@ -57,7 +57,7 @@ struct lutr_stage {
     std::vector<IdxTable> idx_tables;
     int use_fast = 1;      // 0 forces the generic kernels (testing)
     int grid_ctas = 0;     // 0 = min_blocks CTAs per SM
-    int idx_mode = 1;      // 0 = shared-memory index table, 1 = arithmetic index
+    int idx_mode = 2;      // 0 = shared-memory index table, 1 = arithmetic index, 2 = arithmetic index + TMA-staged rows
     int min_blocks = 3;    // occupancy variant of the fast kernels
     std::atomic<int64_t> launches{0};
 };
@@ -223,7 +223,15 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : s->min_blocks * s->ctx->sm_count;
     if (fast_path_ok(s, lut)) {
         k.idx_mode = s->idx_mode;
-        if (s->idx_mode == 0) {
+        if (k.idx_mode == 2) {
+            // TMA-staged rows need 16-byte aligned bulk copies (row starts and row lengths) and the ring must fit in shared memory
+            bool ok = s->d.in_fmt == LUTR_PIX_YUV422P10LE && (k.w % 16) == 0 && (in->frame_step % 16) == 0;
+            for (int p = 0; p < 3; ++p) ok = ok && ((uintptr_t)in->data[p] % 16) == 0 && (in->stride[p] % 16) == 0;
+            const size_t smem = (size_t)8 * k.w + (size_t)2 * (k.w + 8) * 4 + 16;
+            if (smem * (size_t)s->min_blocks > 200 * 1024) ok = false;
+            if (!ok) k.idx_mode = 1;
+        }
+        if (k.idx_mode == 0) {
             rc = get_index_table(s, lut, st, &k.idx_tab);
             if (rc != LUTR_OK) return rc;
         }
@@ -660,7 +668,7 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     else if (!std::strcmp(name, "band_rows")) s->band_rows = value;
     else if (!std::strcmp(name, "fast_path")) s->use_fast = value;
     else if (!std::strcmp(name, "grid_ctas")) s->grid_ctas = value;
-    else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value ? 1 : 0;
+    else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value < 0 || value > 2 ? 1 : value;
     else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value == 4 ? 4 : 3;
     else if (!std::strcmp(name, "l2_persist")) {
         s->l2_persist = value;

@@ -469,6 +469,168 @@ __global__ void __launch_bounds__(256, MINB) k_yuv422p10_fast(const StageK K) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged variant of the fast 4:2:2 kernel.
+// One elected thread streams whole input rows (Y, U, V) into a 2-stage shared-memory ring with 1-D bulk async copies
+// (cp.async.bulk + mbarrier complete_tx), one to two rows ahead of the math, so no warp ever waits on an HBM load; pixel
+// inputs are then plain 32-bit-addressed LDS (no 64-bit address arithmetic, free chroma-window access at any alignment).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int INTERP, bool FMA, bool CLAMP, int IDX, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_yuv422p10_tma(const StageK K) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int w = K.w, groups = w >> 2, pitch = w + 8;
+    const unsigned row_bytes = 4u * (unsigned)w;  // Y: 2w, U: w, V: w
+    // layout: [in stage 0 | in stage 1 | c14 buffer 0 | c14 buffer 1 | 2 mbarriers]
+    unsigned char *s_in = smem_raw;
+    unsigned *s_c14 = reinterpret_cast<unsigned *>(smem_raw + 2 * row_bytes);
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + 2 * row_bytes + 2 * pitch * sizeof(unsigned));
+    const unsigned bar0 = smem_u32(s_bar), in0 = smem_u32(s_in);
+    const long total_rows = (long)K.h * K.nframes;
+    const long stride_rows = gridDim.x;
+
+    auto issue_row = [&](long grow, int stage) {  // thread 0 only
+        const int frame = (int)(grow / K.h), y = (int)(grow - (long)frame * K.h);
+        const unsigned bar = bar0 + 8u * stage, dst = in0 + stage * row_bytes;
+        mbar_expect_tx(bar, row_bytes);
+        bulk_g2s(dst, K.p.in[0] + frame * K.p.in_step + (long)y * K.p.in_stride[0], 2u * w, bar);
+        bulk_g2s(dst + 2u * w, K.p.in[1] + frame * K.p.in_step + (long)y * K.p.in_stride[1], (unsigned)w, bar);
+        bulk_g2s(dst + 3u * w, K.p.in[2] + frame * K.p.in_step + (long)y * K.p.in_stride[2], (unsigned)w, bar);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((long)blockIdx.x < total_rows) issue_row(blockIdx.x, 0);
+        if ((long)blockIdx.x + stride_rows < total_rows) issue_row(blockIdx.x + stride_rows, 1);
+    }
+    __syncthreads();
+
+    const Rgb2YuvK b = K.b;
+    const FastK fk = K.fk;
+    const char *tab = reinterpret_cast<const char *>(K.lut.tab);
+    const int n = K.lut.n, n2 = K.lut.n2;
+    const float out_scale = K.lut.out_scale, lut_max = K.lut.lut_max;
+    const unsigned kbase = 0u - kMagicBits * (unsigned)(n2 + n + 1);
+    int it = 0;
+
+    for (long grow = blockIdx.x; grow < total_rows; grow += stride_rows, ++it) {
+        const int stage = it & 1;
+        const unsigned phase = (it >> 1) & 1;
+        const int frame = (int)(grow / K.h), y = (int)(grow - (long)frame * K.h);
+        uint8_t *outY = K.p.out[0] + frame * K.p.out_step + (long)y * K.p.out_stride[0];
+        uint8_t *outU = K.p.out[1] + frame * K.p.out_step + (long)y * K.p.out_stride[1];
+        uint8_t *outV = K.p.out[2] + frame * K.p.out_step + (long)y * K.p.out_stride[2];
+        unsigned *sc = s_c14 + stage * pitch + 4;  // sc[x] for x in [-4, w+4)
+        const unsigned char *sY = s_in + stage * row_bytes, *sU = sY + 2 * w, *sV = sY + 3 * w;
+        mbar_wait(bar0 + 8u * stage, phase);
+
+        for (int g = threadIdx.x; g < groups; g += 256) {
+            const int x0 = g << 2;
+            const uint2 yv = *reinterpret_cast<const uint2 *>(sY + 2 * x0);
+            // chroma words: samples (2g-2, 2g-1), (2g, 2g+1), (2g+2, 2g+3); clamp at the row ends
+            const unsigned uw = *reinterpret_cast<const unsigned *>(sU + x0), vw = *reinterpret_cast<const unsigned *>(sV + x0);
+            unsigned ul, vl, ur, vr;
+            if (g > 0) ul = *reinterpret_cast<const unsigned *>(sU + x0 - 4), vl = *reinterpret_cast<const unsigned *>(sV + x0 - 4);
+            else ul = (uw & 0xFFFFu) * 0x10001u, vl = (vw & 0xFFFFu) * 0x10001u;
+            if (g < groups - 1) ur = *reinterpret_cast<const unsigned *>(sU + x0 + 4), vr = *reinterpret_cast<const unsigned *>(sV + x0 + 4);
+            else ur = (uw >> 16) * 0x10001u, vr = (vw >> 16) * 0x10001u;
+            const int eu[6] = {(int)(ul & 0xFFFF), (int)(ul >> 16), (int)(uw & 0xFFFF), (int)(uw >> 16), (int)(ur & 0xFFFF), (int)(ur >> 16)};
+            const int ev[6] = {(int)(vl & 0xFFFF), (int)(vl >> 16), (int)(vw & 0xFFFF), (int)(vw >> 16), (int)(vr & 0xFFFF), (int)(vr >> 16)};
+            unsigned yo[2], pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned yw = k < 2 ? yv.x : yv.y;
+                const unsigned Y = (k & 1) ? (yw >> 16) : (yw & 0xFFFF);
+                const int j = k >> 1;
+                int cu, cv;
+                if (!(k & 1)) {  // even column 2i: taps on C[i-2 .. i+1]
+                    cu = up4(eu[j], eu[j + 1], eu[j + 2], eu[j + 3], -461, 3943, 14284, -1382);
+                    cv = up4(ev[j], ev[j + 1], ev[j + 2], ev[j + 3], -461, 3943, 14284, -1382);
+                    if (g == 0) {  // the two left-most even columns use swscale's edge-normalised taps
+                        if (k == 0) {
+                            cu = min((17729 * eu[2] - 1345 * eu[3]) >> 9, 32767);
+                            cv = min((17729 * ev[2] - 1345 * ev[3]) >> 9, 32767);
+                        } else {
+                            cu = min((3835 * eu[2] + 13894 * eu[3] - 1345 * eu[4]) >> 9, 32767);
+                            cv = min((3835 * ev[2] + 13894 * ev[3] - 1345 * ev[4]) >> 9, 32767);
+                        }
+                    }
+                } else {  // odd column 2i+1: taps on C[i-1 .. i+2]
+                    cu = up4(eu[j + 1], eu[j + 2], eu[j + 3], eu[j + 4], -1382, 14284, 3943, -461);
+                    cv = up4(ev[j + 1], ev[j + 2], ev[j + 3], ev[j + 4], -1382, 14284, 3943, -461);
+                }
+                const unsigned yy = Y * fk.yA;
+                const int R = (int)(yy + (unsigned)cv * fk.vr4 + fk.kR);
+                const int G = (int)(yy + (unsigned)cv * fk.vg4 + (unsigned)cu * fk.ug4 + fk.kG);
+                const int B = (int)(yy + (unsigned)cu * fk.ub4 + fk.kB);
+                uint2 er, eg, eb;
+                idx_arith<IDX>(clamp_u(R >> 20, 1023), fk, lut_max, er.x, er.y);
+                idx_arith<IDX>(clamp_u(G >> 20, 1023), fk, lut_max, eg.x, eg.y);
+                idx_arith<IDX>(clamp_u(B >> 20, 1023), fk, lut_max, eb.x, eb.y);
+                unsigned rb, gb, bb;
+                lut3d_fast<INTERP, FMA, CLAMP>(tab, n, n2, kbase, fk.n2b, fk.nb, fk.totalb, out_scale, er.x, eg.x, eb.x, er.y, eg.y, eb.y,
+                                               rb, gb, bb);
+                const unsigned yq = (unsigned)((int)((unsigned)b.ry * rb + (unsigned)b.gy * gb + (unsigned)b.by * bb + fk.kY) >> 15);
+                const unsigned u14 = (unsigned)((int)((unsigned)b.ru * rb + (unsigned)b.gu * gb + (unsigned)b.bu * bb + fk.kU) >> 11);
+                const unsigned v14 = (unsigned)((int)((unsigned)b.rv * rb + (unsigned)b.gv * gb + (unsigned)b.bv * bb + fk.kV) >> 11);
+                pk[k] = (v14 << 16) + u14;
+                if (k & 1) yo[k >> 1] |= yq << 16;
+                else yo[k >> 1] = yq;
+            }
+            *reinterpret_cast<uint4 *>(sc + x0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (g == 0) *reinterpret_cast<uint4 *>(sc - 4) = make_uint4(pk[0], pk[0], pk[0], pk[0]);          // clamp left
+            if (g == groups - 1) *reinterpret_cast<uint4 *>(sc + w) = make_uint4(pk[3], pk[3], pk[3], pk[3]);  // clamp right
+            stg_stream8(outY + 2 * x0, make_uint2(yo[0], yo[1]));
+        }
+        __syncthreads();  // c14 of this row complete; nobody reads this input stage any more
+        if (threadIdx.x == 0 && grow + 2 * stride_rows < total_rows) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order the generic-proxy reads before the async refill
+            issue_row(grow + 2 * stride_rows, stage);
+        }
+        for (int g = threadIdx.x; g < groups; g += 256) {
+            const int x0 = g << 2;
+            unsigned t[12];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint4 v4 = *reinterpret_cast<const uint4 *>(sc + x0 - 4 + 4 * q);
+                t[4 * q] = v4.x, t[4 * q + 1] = v4.y, t[4 * q + 2] = v4.z, t[4 * q + 3] = v4.w;
+            }
+            unsigned uo = 0, vo = 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const unsigned s0 = t[2 * j + 1] + t[2 * j + 8], s1 = t[2 * j + 2] + t[2 * j + 7];
+                const unsigned s2 = t[2 * j + 3] + t[2 * j + 6], s3 = t[2 * j + 4] + t[2 * j + 5];
+                const int su = -230 * (int)(s0 & 0xFFFF) - 692 * (int)(s1 & 0xFFFF) + 1972 * (int)(s2 & 0xFFFF) + 7142 * (int)(s3 & 0xFFFF) + (16 << 13);
+                const int sv = -230 * (int)(s0 >> 16) - 692 * (int)(s1 >> 16) + 1972 * (int)(s2 >> 16) + 7142 * (int)(s3 >> 16) + (16 << 13);
+                uo |= (unsigned)clamp_u(su >> 18, 1023) << (16 * j);
+                vo |= (unsigned)clamp_u(sv >> 18, 1023) << (16 * j);
+            }
+            stg_stream4(outU + x0, uo);
+            stg_stream4(outV + x0, vo);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // yuv420p (8 bit) -> yuv420p   (BASELINE cfg 1 / 2)
 // A CTA owns one band of luma rows of one frame and walks down it; a thread owns 8-pixel column groups.
@@ -590,10 +752,22 @@ int launch422(const StageK &k, int float_mode, cudaStream_t st) {
     const long total_rows = (long)k.h * k.nframes;
     if (k.idx_mode >= 0 && INTERP != LUTR_INTERP_NEAREST) {
         const int idx = k.idx_mode == 0 ? 0 : (k.fk.idx_fold ? 1 : 2);
-        const size_t smem = (idx == 0 ? kIdxEntries10 * sizeof(uint2) : 0) + (size_t)2 * (k.w + 8) * sizeof(unsigned);
+        size_t smem = (idx == 0 ? kIdxEntries10 * sizeof(uint2) : 0) + (size_t)2 * (k.w + 8) * sizeof(unsigned);
         void (*fn)(const StageK) = nullptr;
         const bool fma = float_mode == LUTR_FLOAT_FMA, clamp = k.clamp_out != 0;
         const int mb = k.min_blocks == 4 ? 4 : 3;
+        if (k.idx_mode == 2) {  // TMA-staged input rows
+            smem = (size_t)8 * k.w + (size_t)2 * (k.w + 8) * sizeof(unsigned) + 16;
+#define LUTR_PICK_T(F, C, I, M) \
+    if (fma == F && clamp == C && idx == I && mb == M) fn = k_yuv422p10_tma<INTERP, F, C, I, M>;
+#define LUTR_PICK_TM(F, C, I) LUTR_PICK_T(F, C, I, 3) LUTR_PICK_T(F, C, I, 4)
+#define LUTR_PICK_TI(F, C) LUTR_PICK_TM(F, C, 1) LUTR_PICK_TM(F, C, 2)
+            LUTR_PICK_TI(false, false) LUTR_PICK_TI(false, true) LUTR_PICK_TI(true, false) LUTR_PICK_TI(true, true)
+#undef LUTR_PICK_TI
+#undef LUTR_PICK_TM
+#undef LUTR_PICK_T
+        }
+        if (!fn) {
 #define LUTR_PICK(F, C, I, M) \
     if (fma == F && clamp == C && idx == I && mb == M) fn = k_yuv422p10_fast<INTERP, F, C, I, M>;
 #define LUTR_PICK_M(F, C, I) LUTR_PICK(F, C, I, 3) LUTR_PICK(F, C, I, 4)
@@ -602,6 +776,7 @@ int launch422(const StageK &k, int float_mode, cudaStream_t st) {
 #undef LUTR_PICK_I
 #undef LUTR_PICK_M
 #undef LUTR_PICK
+        }
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         long grid = k.grid_ctas > 0 ? k.grid_ctas : 148 * mb;
         if (grid > total_rows) grid = total_rows;

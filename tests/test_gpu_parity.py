@@ -92,12 +92,14 @@ def test_yuv422p10_rows_per_cta_and_domain_scale():
 
 
 @pytest.mark.parametrize("options", [dict(fast_path=0), dict(idx_mode=0, min_blocks=3), dict(idx_mode=0, min_blocks=4),
-                                     dict(idx_mode=1, min_blocks=3), dict(idx_mode=1, min_blocks=4), dict(grid_ctas=1), dict(grid_ctas=7)])
+                                     dict(idx_mode=1, min_blocks=3), dict(idx_mode=1, min_blocks=4), dict(grid_ctas=1), dict(grid_ctas=7),
+                                     dict(idx_mode=2, min_blocks=3), dict(idx_mode=2, min_blocks=4), dict(idx_mode=2, grid_ctas=1),
+                                     dict(idx_mode=2, grid_ctas=2), dict(idx_mode=2, grid_ctas=5)])
 @pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
 def test_yuv422p10_kernel_variants(options, interp):
     """Every code path of the 4:2:2 stage (generic kernel, index table / arithmetic index, occupancy variants, tiny persistent
     grids) gives the same bits; LUTs: values inside [0,1] (no store clip), outside (clip), size-1 not a power of two."""
-    w, h = 648, 21
+    w, h = 656, 21
     frames = _frames("yuv422p10le", w, h, ["natural", "noise", "extremes"])
     for lut_name, table in (("look33", LUTS["look33"]()), ("rand64", LUTS["rand64"]()), ("wide9", synth.random_lut(9, 4) * 1.6 - 0.3)):
         table = table.astype(np.float32)
