@@ -58,7 +58,8 @@ struct lutr_stage {
     int use_fast = 1;      // 0 forces the generic kernels (testing)
     int grid_ctas = 0;     // 0 = min_blocks CTAs per SM
     int idx_mode = 2;      // 0 = shared-memory index table, 1 = arithmetic index, 2 = arithmetic index + TMA-staged rows
-    int min_blocks = 3;    // occupancy variant of the fast kernels
+    int min_blocks = 2;    // occupancy variant of the fast kernels (CTAs per SM)
+    int fast_threads = 0;  // threads per CTA of the TMA kernel (0 = auto)
     std::atomic<int64_t> launches{0};
 };
 
@@ -219,8 +220,8 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     k.idx_tab = nullptr;
     k.idx_mode = -1;
     k.min_blocks = s->min_blocks;
+    k.fast_threads = s->fast_threads;
     k.clamp_out = lut->needs_clamp ? 1 : 0;
-    k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : s->min_blocks * s->ctx->sm_count;
     if (fast_path_ok(s, lut)) {
         k.idx_mode = s->idx_mode;
         if (k.idx_mode == 2) {
@@ -229,7 +230,10 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             for (int p = 0; p < 3; ++p) ok = ok && ((uintptr_t)in->data[p] % 16) == 0 && (in->stride[p] % 16) == 0;
             const size_t smem = (size_t)8 * k.w + (size_t)2 * (k.w + 8) * 4 + 16;
             if (smem * (size_t)s->min_blocks > 200 * 1024) ok = false;
-            if (!ok) k.idx_mode = 1;
+            if (!ok) {
+                k.idx_mode = 1;
+                if (k.min_blocks < 3) k.min_blocks = 3;
+            }
         }
         if (k.idx_mode == 0) {
             rc = get_index_table(s, lut, st, &k.idx_tab);
@@ -262,6 +266,7 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         fk.idx_add = -(fk.idx_mul * 8388608.f);
         fk.maxv = maxv;
     }
+    k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : k.min_blocks * s->ctx->sm_count;
     if (s->d.in_fmt == LUTR_PIX_YUV422P10LE) {
         k.rows_per_cta = s->rows_per_cta > 0 ? s->rows_per_cta : 1;
         k.bands = 1;
@@ -669,7 +674,8 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     else if (!std::strcmp(name, "fast_path")) s->use_fast = value;
     else if (!std::strcmp(name, "grid_ctas")) s->grid_ctas = value;
     else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value < 0 || value > 2 ? 1 : value;
-    else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value == 4 ? 4 : 3;
+    else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value >= 2 && value <= 4 ? value : 3;
+    else if (!std::strcmp(name, "fast_threads")) s->fast_threads = value;
     else if (!std::strcmp(name, "l2_persist")) {
         s->l2_persist = value;
         s->persist_lut = nullptr;

@@ -90,7 +90,8 @@ struct StageK {
     int32_t clamp_out;        // 1: LUT entries leave [0,1], the store needs its clip
     int32_t grid_ctas;        // persistent grid size of the fast kernels
     int32_t idx_mode;         // 0: shared-memory index table, 1: arithmetic index (no table)
-    int32_t min_blocks;       // occupancy variant of the fast kernel (3 or 4 CTAs of 256 threads per SM)
+    int32_t min_blocks;       // occupancy variant of the fast kernel (2, 3 or 4 CTAs per SM)
+    int32_t fast_threads;     // threads per CTA of the TMA kernel (0 = 256)
 };
 
 // host-side construction of the index table (colour_tables.cpp): same float operations as lut3d's per-pixel prologue

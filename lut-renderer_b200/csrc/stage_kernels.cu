@@ -496,7 +496,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 }
 
 template <int INTERP, bool FMA, bool CLAMP, int IDX, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_yuv422p10_tma(const StageK K) {
+__global__ void __launch_bounds__(MINB == 2 ? 320 : 256, MINB) k_yuv422p10_tma(const StageK K) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int w = K.w, groups = w >> 2, pitch = w + 8;
     const unsigned row_bytes = 4u * (unsigned)w;  // Y: 2w, U: w, V: w
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256, MINB) k_yuv422p10_tma(const StageK K) {
         const unsigned char *sY = s_in + stage * row_bytes, *sU = sY + 2 * w, *sV = sY + 3 * w;
         mbar_wait(bar0 + 8u * stage, phase);
 
-        for (int g = threadIdx.x; g < groups; g += 256) {
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) {
             const int x0 = g << 2;
             const uint2 yv = *reinterpret_cast<const uint2 *>(sY + 2 * x0);
             // chroma words: samples (2g-2, 2g-1), (2g, 2g+1), (2g+2, 2g+3); clamp at the row ends
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(256, MINB) k_yuv422p10_tma(const StageK K) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order the generic-proxy reads before the async refill
             issue_row(grow + 2 * stride_rows, stage);
         }
-        for (int g = threadIdx.x; g < groups; g += 256) {
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) {
             const int x0 = g << 2;
             unsigned t[12];
 #pragma unroll
@@ -744,6 +744,128 @@ __global__ void __launch_bounds__(512, 2) k_yuv420p8(const StageK K) {
     }
 }
 
+// yuv420p (8 bit) -> yuv420p, fast path: same band / thread-private ring structure as k_yuv420p8, with the exact
+// conversion-free LUT prologue / epilogue of the 4:2:2 fast kernel and the next row's samples prefetched into registers
+// while the current row is computed (the only long-latency loads left are the LUT gathers).
+template <int INTERP, bool FMA, bool CLAMP, int IDX>
+__global__ void __launch_bounds__(256, 3) k_yuv420p8_fast(const StageK K) {
+    extern __shared__ uint4 s_ring[];  // [8][groups]: 4 x (u15 | v15 << 16) per row and group
+    const int w = K.w, h = K.h, groups = w >> 3, ch = h >> 1;
+    const int frame = blockIdx.x / K.bands, band = blockIdx.x - frame * K.bands;
+    const int y_begin = band * K.rows_per_cta;
+    const int y_end = min(h, y_begin + K.rows_per_cta);
+    if (y_begin >= h) return;
+    const Yuv2RgbK f = K.f;
+    const Rgb2YuvK b = K.b;
+    const FastK fk = K.fk;
+    const char *tab = reinterpret_cast<const char *>(K.lut.tab);
+    const int n = K.lut.n, n2 = K.lut.n2;
+    const float out_scale = K.lut.out_scale, lut_max = K.lut.lut_max;
+    const unsigned kbase = 0u - kMagicBits * (unsigned)(n2 + n + 1);
+    const uint8_t *inY = K.p.in[0] + frame * K.p.in_step, *inU = K.p.in[1] + frame * K.p.in_step, *inV = K.p.in[2] + frame * K.p.in_step;
+    uint8_t *outY = K.p.out[0] + frame * K.p.out_step, *outU = K.p.out[1] + frame * K.p.out_step, *outV = K.p.out[2] + frame * K.p.out_step;
+    const int taps[8] = {-58, -172, 492, 1786, 1786, 492, -172, -58};
+    const int r_first = max(0, y_begin - 3), r_last = min(h - 1, y_end + 2);
+
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const int x0 = g << 3, i0 = g << 2;
+        int y = r_first;
+        uint2 yv = ldg_stream8(inY + (long)y * K.p.in_stride[0] + x0);
+        unsigned uv = ldg_stream4(inU + (long)(y >> 1) * K.p.in_stride[1] + i0);
+        unsigned vv = ldg_stream4(inV + (long)(y >> 1) * K.p.in_stride[2] + i0);
+        for (int j = y_begin >> 1; j < (y_end >> 1); ++j) {
+            const int last_needed = min(h - 1, 2 * j + 4);
+            for (; y <= last_needed; ++y) {
+                // prefetch the next row of this column group
+                const int yn = min(y + 1, r_last);
+                const uint2 yv_n = ldg_stream8(inY + (long)yn * K.p.in_stride[0] + x0);
+                const unsigned uv_n = ldg_stream4(inU + (long)(yn >> 1) * K.p.in_stride[1] + i0);
+                const unsigned vv_n = ldg_stream4(inV + (long)(yn >> 1) * K.p.in_stride[2] + i0);
+                if (K.range_pass) {
+                    yv.x = map4(yv.x, false), yv.y = map4(yv.y, false);
+                    uv = map4(uv, true), vv = map4(vv, true);
+                }
+                unsigned yo[2] = {0u, 0u};
+                unsigned ring[4];
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {  // pixel pairs sharing one chroma sample
+                    const int u = (int)((uv >> (8 * pr)) & 0xFF) * 8 - 1024, v = (int)((vv >> (8 * pr)) & 0xFF) * 8 - 1024;
+                    const int cr = (v * f.vr) >> 16, cg = ((u * f.ug) >> 16) + ((v * f.vg) >> 16), cb = (u * f.ub) >> 16;
+                    unsigned rs = 0, gs = 0, bs = 0;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int k = 2 * pr + q;
+                        const int Y = (int)(((k < 4 ? yv.x : yv.y) >> (8 * (k & 3))) & 0xFF);
+                        const int yy = ((Y * 8 - f.yO8) * f.yC) >> 16;
+                        uint2 er, eg, eb;
+                        idx_arith<IDX>(clamp_u(yy + cr, 255), fk, lut_max, er.x, er.y);
+                        idx_arith<IDX>(clamp_u(yy + cg, 255), fk, lut_max, eg.x, eg.y);
+                        idx_arith<IDX>(clamp_u(yy + cb, 255), fk, lut_max, eb.x, eb.y);
+                        unsigned rb, gb, bb;
+                        lut3d_fast<INTERP, FMA, CLAMP>(tab, n, n2, kbase, fk.n2b, fk.nb, fk.totalb, out_scale, er.x, eg.x, eb.x, er.y, eg.y,
+                                                       eb.y, rb, gb, bb);
+                        // clip8((2*y14 + 64) >> 7), y14 = S >> 9  ==  (S + (32 << 9)) >> 15; no clip can bind (host-checked)
+                        const unsigned yq = (unsigned)((int)((unsigned)b.ry * rb + (unsigned)b.gy * gb + (unsigned)b.by * bb + fk.kY) >> 15);
+                        yo[k >> 2] |= yq << (8 * (k & 3));
+                        rs += rb, gs += gb, bs += bb;
+                    }
+                    // rgb24ToUV_half on the pair sums (each sum carries 2 x the 0x4B000000 bias, folded into kU / kV)
+                    const unsigned u14 = (unsigned)((int)((unsigned)b.ru * rs + (unsigned)b.gu * gs + (unsigned)b.bu * bs + fk.kU) >> 10);
+                    const unsigned v14 = (unsigned)((int)((unsigned)b.rv * rs + (unsigned)b.gv * gs + (unsigned)b.bv * bs + fk.kV) >> 10);
+                    ring[pr] = ((2u * v14) << 16) + 2u * u14;
+                }
+                s_ring[(y & 7) * groups + g] = make_uint4(ring[0], ring[1], ring[2], ring[3]);
+                if (y >= y_begin && y < y_end) stg_stream8(outY + (long)y * K.p.out_stride[0] + x0, make_uint2(yo[0], yo[1]));
+                yv = yv_n, uv = uv_n, vv = vv_n;
+            }
+            int au[4], av[4];
+            const bool exact = (j == ch - 1);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) au[c] = av[c] = exact ? (64 << 12) : 7;
+            if (2 * j - 3 >= 0 && 2 * j + 4 <= h - 1) {
+                // interior: 8 distinct rows, per-tap truncation (the SIMD vertical scaler)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint4 q = s_ring[((2 * j - 3 + k) & 7) * groups + g];
+                    const unsigned qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        au[c] += ((int)(qq[c] & 0xFFFF) * taps[k]) >> 16;
+                        av[c] += ((int)(qq[c] >> 16) * taps[k]) >> 16;
+                    }
+                }
+            } else {
+                int fold = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int row = max(0, min(h - 1, 2 * j - 3 + k));
+                    const int nrow = max(0, min(h - 1, 2 * j - 2 + k));
+                    fold += taps[k];
+                    if (k == 7 || nrow != row) {
+                        const uint4 q = s_ring[(row & 7) * groups + g];
+                        const unsigned qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int cu = (int)(qq[c] & 0xFFFF), cv = (int)(qq[c] >> 16);
+                            if (exact) au[c] += cu * fold, av[c] += cv * fold;
+                            else au[c] += (cu * fold) >> 16, av[c] += (cv * fold) >> 16;
+                        }
+                        fold = 0;
+                    }
+                }
+            }
+            unsigned uo = 0, vo = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uo |= (unsigned)clamp_u(au[c] >> (exact ? 19 : 3), 255) << (8 * c);
+                vo |= (unsigned)clamp_u(av[c] >> (exact ? 19 : 3), 255) << (8 * c);
+            }
+            stg_stream4(outU + (long)j * K.p.out_stride[1] + i0, uo);
+            stg_stream4(outV + (long)j * K.p.out_stride[2] + i0, vo);
+        }
+    }
+}
+
 template <int INTERP>
 int launch422(const StageK &k, int float_mode, cudaStream_t st) {
     const int groups = k.w >> 3;
@@ -755,12 +877,19 @@ int launch422(const StageK &k, int float_mode, cudaStream_t st) {
         size_t smem = (idx == 0 ? kIdxEntries10 * sizeof(uint2) : 0) + (size_t)2 * (k.w + 8) * sizeof(unsigned);
         void (*fn)(const StageK) = nullptr;
         const bool fma = float_mode == LUTR_FLOAT_FMA, clamp = k.clamp_out != 0;
-        const int mb = k.min_blocks == 4 ? 4 : 3;
+        int mb = k.min_blocks == 4 ? 4 : 3;
+        int fast_threads = 256;
         if (k.idx_mode == 2) {  // TMA-staged input rows
+            if (k.min_blocks == 2) mb = 2;
+            // threads per CTA: as close to the cap as divides the row's 4-pixel groups evenly (balanced phases, one barrier per row)
+            const int cap = mb == 2 ? 320 : 256, groups4 = k.w >> 2;
+            const int per = (groups4 + cap - 1) / cap;
+            fast_threads = k.fast_threads > 0 ? k.fast_threads : ((groups4 + per - 1) / per + 31) / 32 * 32;
+            if (fast_threads > cap) fast_threads = cap;
             smem = (size_t)8 * k.w + (size_t)2 * (k.w + 8) * sizeof(unsigned) + 16;
 #define LUTR_PICK_T(F, C, I, M) \
     if (fma == F && clamp == C && idx == I && mb == M) fn = k_yuv422p10_tma<INTERP, F, C, I, M>;
-#define LUTR_PICK_TM(F, C, I) LUTR_PICK_T(F, C, I, 3) LUTR_PICK_T(F, C, I, 4)
+#define LUTR_PICK_TM(F, C, I) LUTR_PICK_T(F, C, I, 2) LUTR_PICK_T(F, C, I, 3) LUTR_PICK_T(F, C, I, 4)
 #define LUTR_PICK_TI(F, C) LUTR_PICK_TM(F, C, 1) LUTR_PICK_TM(F, C, 2)
             LUTR_PICK_TI(false, false) LUTR_PICK_TI(false, true) LUTR_PICK_TI(true, false) LUTR_PICK_TI(true, true)
 #undef LUTR_PICK_TI
@@ -780,7 +909,7 @@ int launch422(const StageK &k, int float_mode, cudaStream_t st) {
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         long grid = k.grid_ctas > 0 ? k.grid_ctas : 148 * mb;
         if (grid > total_rows) grid = total_rows;
-        fn<<<(unsigned)grid, 256, smem, st>>>(k);
+        fn<<<(unsigned)grid, fast_threads, smem, st>>>(k);
         return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
     }
     const unsigned grid = (unsigned)((total_rows + k.rows_per_cta - 1) / k.rows_per_cta);
@@ -794,10 +923,25 @@ int launch422(const StageK &k, int float_mode, cudaStream_t st) {
 template <int INTERP>
 int launch420(const StageK &k, int float_mode, cudaStream_t st) {
     const int groups = k.w >> 3;
-    int per = (groups + 511) / 512;
-    int threads = ((groups + per - 1) / per + 31) / 32 * 32;
     const unsigned grid = (unsigned)(k.bands * k.nframes);
     const size_t smem = (size_t)8 * groups * sizeof(uint4);
+    if (k.idx_mode >= 0 && INTERP != LUTR_INTERP_NEAREST) {
+        const int idx = k.fk.idx_fold ? 1 : 2;
+        const bool fma = float_mode == LUTR_FLOAT_FMA, clamp = k.clamp_out != 0;
+        void (*fn)(const StageK) = nullptr;
+#define LUTR_PICK8(F, C, I) \
+    if (fma == F && clamp == C && idx == I) fn = k_yuv420p8_fast<INTERP, F, C, I>;
+#define LUTR_PICK8_I(F, C) LUTR_PICK8(F, C, 1) LUTR_PICK8(F, C, 2)
+        LUTR_PICK8_I(false, false) LUTR_PICK8_I(false, true) LUTR_PICK8_I(true, false) LUTR_PICK8_I(true, true)
+#undef LUTR_PICK8_I
+#undef LUTR_PICK8
+        const int threads = groups >= 256 ? 256 : (groups + 31) / 32 * 32;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fn<<<grid, threads, smem, st>>>(k);
+        return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
+    }
+    int per = (groups + 511) / 512;
+    int threads = ((groups + per - 1) / per + 31) / 32 * 32;
     auto fn = float_mode == LUTR_FLOAT_FMA ? k_yuv420p8<INTERP, true> : k_yuv420p8<INTERP, false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     fn<<<grid, threads, smem, st>>>(k);

@@ -110,6 +110,21 @@ def test_yuv422p10_kernel_variants(options, interp):
                              f"422p10 {options} {lut_name} {interp} frame {i}")
 
 
+@pytest.mark.parametrize("options", [dict(fast_path=0), dict(fast_path=1), dict(fast_path=1, band_rows=12), dict(fast_path=1, band_rows=26)])
+@pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
+def test_yuv420p_kernel_variants(options, interp):
+    w, h = 328, 54
+    frames = _frames("yuv420p", w, h, ["natural", "noise", "extremes"])
+    for lut_name, table in (("look33", LUTS["look33"]()), ("rand64", LUTS["rand64"]()), ("wide9", synth.random_lut(9, 4) * 1.6 - 0.3)):
+        table = table.astype(np.float32)
+        for kw in (dict(), dict(in_range="pc", norm_range="tv")):
+            got = gpu_stage("yuv420p", w, h, frames, table, interp=interp, options=options, **kw)
+            L = oracle_lut(table)
+            for i, f in enumerate(frames):
+                assert_bit_exact("yuv420p", w, h, got[i], oracle_stage("yuv420p", w, h, f, L, interp=interp, **kw),
+                                 f"420p {options} {lut_name} {interp} {kw} frame {i}")
+
+
 @pytest.mark.parametrize("lut_name", ["look33", "rand65", "ident33", "rand2"])
 @pytest.mark.parametrize("interp", ["tetrahedral", "trilinear", "nearest"])
 def test_yuv420p_interp_luts(lut_name, interp):
