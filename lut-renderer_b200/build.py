@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblutr.so")
-SOURCES = ["cube_parser.cpp", "colour_tables.cpp", "stage_kernels.cu", "lutr_api.cu"]
+SOURCES = ["cube_parser.cpp", "colour_tables.cpp", "stage_kernels.cu", "k422_warp.cu", "lutr_api.cu"]
 HEADERS = ["lutr_internal.h", os.path.join("..", "..", "include", "lutr.h")]
 GENCODE = "arch=compute_100a,code=sm_100a"
 
@@ -40,11 +40,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [
         nvcc_path(), "-shared", "-o", OUT,
         "-gencode", GENCODE, "-O3", "-lineinfo", "-std=c++17",
+        # lut3d's C semantics round every product and every sum: ptxas must never contract a mul + add pair (it does so for the
+        # packed mul.rn.f32x2 / add.rn.f32x2 pair unless told not to; wanted fmas are written as fma explicitly)
+        "-fmad=false",
         "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wextra,-ffp-contract=off",
         "-cudart", "static",
     ]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    if os.environ.get("LUTR_WK_EXPERIMENTS"):
+        cmd += ["-DLUTR_WK_EXPERIMENTS"]
+    if os.environ.get("LUTR_WK_UNROLL"):
+        cmd += ["-DLUTR_WK_UNROLL=" + os.environ["LUTR_WK_UNROLL"]]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -1,0 +1,543 @@
+// Warp-autonomous fused kernel for yuv422p10le -> lut3d -> yuv422p10le (BASELINE cfg 3 / 4).
+//
+// Same arithmetic as stage_kernels.cu (reference chain: src/lut_renderer/ffmpeg.py:211-247, 304-310; integer legs and
+// float32 lut3d as defined in DESIGN.md "Arithmetic"), different decomposition:
+//
+//  * work unit = one warp x one 128-column window of one row.  The window owns the outputs of its middle 120 columns and
+//    recomputes 4 halo columns on each side, so nothing is ever exchanged between warps: no __syncthreads, no row-sized
+//    shared-memory buffers (768 B per warp), the unified L1 stays almost entirely cache for the LUT gathers.
+//  * pass A (lane = 4 consecutive columns): 4-tap chroma upsample, packed (cu | cv << 16) per column to shared memory.
+//  * pass B (lane = ONE column, 32 consecutive columns per warp instruction): YUV->RGB matrix, lut3d, RGB->YUV.  Adjacent
+//    lanes hold adjacent pixels, so one LUT gather instruction touches ~4-5 distinct 128-byte lines instead of ~9 with
+//    4-column lanes (L1 wavefronts are the co-limiter of this stage next to instruction issue).
+//  * pass C (lane = 2 chroma samples): 8-tap horizontal decimation of the per-column chroma terms.
+//  * float work uses Blackwell's packed FP32 instructions (FFMA2 / FADD2 / FMUL2 with a broadcast scalar operand): exact
+//    per-element IEEE rounding, half the issue slots.
+//  * the next window's samples are prefetched into registers while the current one is computed.
+#include <cuda_runtime.h>
+
+#include "lutr_internal.h"
+
+namespace lutr {
+
+namespace {
+
+constexpr int kWin = 256;        // luma columns computed per window
+constexpr int kOut = 240;        // luma columns whose outputs the window owns (8 halo columns on each side)
+constexpr int kWarps = 8;        // warps per CTA (a CTA is only a container)
+constexpr unsigned kMagic = 0x4B000000u;  // bits of 8388608.0f
+constexpr int kCBias = 4096;     // the 15-bit upsampled chroma is stored biased so that it is an unsigned 16-bit field
+
+__device__ __forceinline__ uint2 ldg_s8(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_s16(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_s8(void *p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_s16(void *p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// The per-column words live in 4-word chunks; chunk c sits at c ^ bit3(c).  With that swizzle the 128-bit accesses of passes A
+// and C (8 lanes x 16 B, chunks 2 apart) and the 32-bit accesses of pass B (32 consecutive columns) are all bank-conflict free.
+__device__ __forceinline__ int swz_chunk(int c) { return c ^ ((c >> 3) & 1); }
+__device__ __forceinline__ int swz_slot(int j) { return (swz_chunk(j >> 2) << 2) | (j & 3); }
+
+// ---- two-wide float helpers: PK = packed f32x2 instructions, otherwise two scalar instructions with the same rounding ----
+struct f2 {
+    float x, y;
+};
+
+template <bool PK>
+__device__ __forceinline__ f2 mul2s(f2 a, float b) {  // a * b (b broadcast)
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; mul.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b));
+    } else {
+        r.x = __fmul_rn(a.x, b), r.y = __fmul_rn(a.y, b);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; mul.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    } else {
+        r.x = __fmul_rn(a.x, b.x), r.y = __fmul_rn(a.y, b.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; add.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    } else {
+        r.x = __fadd_rn(a.x, b.x), r.y = __fadd_rn(a.y, b.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; sub.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    } else {
+        r.x = __fsub_rn(a.x, b.x), r.y = __fsub_rn(a.y, b.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 add2s(f2 a, float b) {  // a + b (b broadcast), round to nearest
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; add.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b));
+    } else {
+        r.x = __fadd_rn(a.x, b), r.y = __fadd_rn(a.y, b);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 rsub2s(float a, f2 b) {  // a - b (a broadcast)
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%2}; mov.b64 b,{%3,%4}; sub.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a), "f"(b.x), "f"(b.y));
+    } else {
+        r.x = __fsub_rn(a, b.x), r.y = __fsub_rn(a, b.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 addrz2s(f2 a, float b) {  // a + b (b broadcast), round toward zero
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; add.rz.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b));
+    } else {
+        r.x = __fadd_rz(a.x, b), r.y = __fadd_rz(a.y, b);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 fma2s(f2 a, float b, float c) {  // fma(a, b, c), b and c broadcast
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; mov.b64 c,{%5,%5}; fma.rn.f32x2 d,a,b,c; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b), "f"(c));
+    } else {
+        r.x = __fmaf_rn(a.x, b, c), r.y = __fmaf_rn(a.y, b, c);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; mov.b64 c,{%6,%7}; fma.rn.f32x2 d,a,b,c; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    } else {
+        r.x = __fmaf_rn(a.x, b.x, c.x), r.y = __fmaf_rn(a.y, b.y, c.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 fma2ss(f2 a, float b, f2 c) {  // fma(a, b, c), b broadcast
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; mov.b64 c,{%5,%6}; fma.rn.f32x2 d,a,b,c; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b), "f"(c.x), "f"(c.y));
+    } else {
+        r.x = __fmaf_rn(a.x, b, c.x), r.y = __fmaf_rn(a.y, b, c.y);
+    }
+    return r;
+}
+
+// prod + acc where prod comes out of a multiply.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even with
+// -fmad=false), which would drop the product's rounding; fma(prod, one, acc) with `one` a run-time 1.0f it cannot see through is
+// the same single-rounding add and cannot be merged with the multiply.
+template <bool PK>
+__device__ __forceinline__ f2 addp2(f2 prod, f2 acc, float one) {
+    if (PK) return fma2ss<PK>(prod, one, acc);
+    return add2<PK>(prod, acc);
+}
+template <bool PK>
+__device__ __forceinline__ f2 addprz2s(f2 prod, float b, float one) {  // (prod + b) toward zero, b broadcast, prod from a multiply
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; mov.b64 c,{%5,%5}; fma.rz.f32x2 d,a,b,c; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(prod.x), "f"(prod.y), "f"(one), "f"(b));
+    } else {
+        r.x = __fadd_rz(prod.x, b), r.y = __fadd_rz(prod.y, b);
+    }
+    return r;
+}
+
+// acc (+)= w * c per element: C semantics = rounded product then rounded sum, FMA = one rounding (lut3d's x86 assembly)
+template <bool PK, bool FMA>
+__device__ __forceinline__ f2 wacc(f2 c, float w, f2 acc, float one) {
+    if (FMA) return fma2ss<PK>(c, w, acc);
+    return addp2<PK>(mul2s<PK>(c, w), acc, one);
+}
+
+struct Consts {
+    // YUV->RGB on the biased packed chroma word (see pass B)
+    unsigned yA, kR, kG, kB, vr4, vgx, ug4, ub4, ubx;
+    // lut3d index
+    float idx_mul, idx_add, idx_sr, lut_max, out_scale, one;
+    unsigned kbase;
+    int n, n2;
+    // RGB->YUV with the 0x4B000000 bias of the truncated floats folded in
+    unsigned ry, gy, by, ru, gu, bu, rv, gv, bv, kY, kU, kV;
+};
+
+// lut3d for NP (1 or 2) pixels of one lane.  m*: 0x4B000000 | code (i.e. the float 2^23 + code); outputs biased ints.
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK>
+__device__ __forceinline__ void lut3d_pair(const Consts &C, const float4 *tab, const unsigned mr[2],
+                                           const unsigned mg[2], const unsigned mb[2], unsigned ro[2], unsigned go[2], unsigned bo[2]) {
+    const int N = NSZ ? NSZ : C.n, N2 = NSZ ? NSZ * NSZ : C.n2;
+    // s = fl(fl(x / max) * scale): fma(2^23 + x, c, -2^23 c) has the exact product inside and one rounding, like the multiply
+    f2 s[3];
+    s[0] = fma2s<PK>(f2{__uint_as_float(mr[0]), __uint_as_float(mr[1])}, C.idx_mul, C.idx_add);
+    s[1] = fma2s<PK>(f2{__uint_as_float(mg[0]), __uint_as_float(mg[1])}, C.idx_mul, C.idx_add);
+    s[2] = fma2s<PK>(f2{__uint_as_float(mb[0]), __uint_as_float(mb[1])}, C.idx_mul, C.idx_add);
+    unsigned pv[3][2], dd[3][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (IDX == 2) s[c] = mul2s<PK>(s[c], C.idx_sr);
+        if (!NOMIN) s[c].x = fminf(s[c].x, C.lut_max), s[c].y = fminf(s[c].y, C.lut_max);
+        const f2 t = IDX == 2 ? addprz2s<PK>(s[c], 8388608.f, C.one) : addrz2s<PK>(s[c], 8388608.f);  // bits = 0x4B000000 | floor(s)
+        const f2 nfl = rsub2s<PK>(8388608.f, t);                                   // -floor(s), exact
+        const f2 d = IDX == 2 ? addp2<PK>(s[c], nfl, C.one) : add2<PK>(s[c], nfl);  // s - floor(s), exact
+        pv[c][0] = __float_as_uint(t.x), pv[c][1] = __float_as_uint(t.y);
+        dd[c][0] = __float_as_uint(d.x), dd[c][1] = __float_as_uint(d.y);
+    }
+    f2 cxy[2], czw[2];
+    if (INTERP == LUTR_INTERP_TRILINEAR) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const unsigned base = pv[0][p] * (unsigned)N2 + (pv[1][p] * (unsigned)N + C.kbase) + pv[2][p];
+            const float dr = __uint_as_float(dd[0][p]), dg = __uint_as_float(dd[1][p]), db = __uint_as_float(dd[2][p]);
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                v[q] = __ldg(tab + (base + (q & 4 ? N2 : 0) + (q & 2 ? N : 0) + (q & 1)));
+            // lerp(v0, v1, f) = v0 + (v1 - v0) * f along r, then g, then b
+            auto lerp = [&](f2 a, f2 b, float f) {
+                const f2 df = sub2<PK>(b, a);
+                return FMA ? fma2ss<PK>(df, f, a) : addp2<PK>(mul2s<PK>(df, f), a, C.one);
+            };
+            f2 xy[4], zw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                xy[q] = lerp(f2{v[q].x, v[q].y}, f2{v[q + 4].x, v[q + 4].y}, dr);
+                zw[q] = lerp(f2{v[q].z, v[q].w}, f2{v[q + 4].z, v[q + 4].w}, dr);
+            }
+            const f2 xy0 = lerp(xy[0], xy[2], dg), xy1 = lerp(xy[1], xy[3], dg);
+            const f2 zw0 = lerp(zw[0], zw[2], dg), zw1 = lerp(zw[1], zw[3], dg);
+            cxy[p] = lerp(xy0, xy1, db), czw[p] = lerp(zw0, zw1, db);
+        }
+    } else {
+        int mx[2], md[2], mn[2];
+        float4 v0[2], vA[2], vB[2], v1[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const unsigned base = pv[0][p] * (unsigned)N2 + (pv[1][p] * (unsigned)N + C.kbase) + pv[2][p];
+            // fractions are non-negative floats: they order like their bit patterns
+            const int ar = (int)dd[0][p], ag = (int)dd[1][p], ab = (int)dd[2][p];
+            mx[p] = __vimax3_s32(ar, ag, ab), mn[p] = __vimin3_s32(ar, ag, ab);
+            md[p] = ar ^ ag ^ ab ^ mx[p] ^ mn[p];
+            // step of the largest fraction first, of the smallest last; ties only swap vertices whose weight is exactly 0
+            const int o1 = (ar == mx[p]) ? N2 : ((ag == mx[p]) ? N : 1);
+            const int oB = (ab == mn[p]) ? N2 + N : ((ag == mn[p]) ? N2 + 1 : N + 1);
+            const float4 *p0 = tab + base;
+            v0[p] = __ldg(p0), vA[p] = __ldg(p0 + o1), vB[p] = __ldg(p0 + oB), v1[p] = __ldg(p0 + (N2 + N + 1));
+        }
+        // weights of both pixels as pairs: (1 - d1), (d1 - d2), (d2 - d3), d3
+        const f2 d1 = f2{__int_as_float(mx[0]), __int_as_float(mx[1])}, d2 = f2{__int_as_float(md[0]), __int_as_float(md[1])};
+        const f2 d3 = f2{__int_as_float(mn[0]), __int_as_float(mn[1])};
+        const f2 w0 = rsub2s<PK>(1.f, d1), w1 = sub2<PK>(d1, d2), w2 = sub2<PK>(d2, d3);
+        const float w0s[2] = {w0.x, w0.y}, w1s[2] = {w1.x, w1.y}, w2s[2] = {w2.x, w2.y}, w3s[2] = {d3.x, d3.y};
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            f2 axy = mul2s<PK>(f2{v0[p].x, v0[p].y}, w0s[p]), azw = mul2s<PK>(f2{v0[p].z, v0[p].w}, w0s[p]);
+            axy = wacc<PK, FMA>(f2{vA[p].x, vA[p].y}, w1s[p], axy, C.one), azw = wacc<PK, FMA>(f2{vA[p].z, vA[p].w}, w1s[p], azw, C.one);
+            axy = wacc<PK, FMA>(f2{vB[p].x, vB[p].y}, w2s[p], axy, C.one), azw = wacc<PK, FMA>(f2{vB[p].z, vB[p].w}, w2s[p], azw, C.one);
+            axy = wacc<PK, FMA>(f2{v1[p].x, v1[p].y}, w3s[p], axy, C.one), azw = wacc<PK, FMA>(f2{v1[p].z, v1[p].w}, w3s[p], azw, C.one);
+            cxy[p] = axy, czw[p] = azw;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        f2 fxy = mul2s<PK>(cxy[p], C.out_scale), fzw = mul2s<PK>(czw[p], C.out_scale);
+        if (CLAMP) {
+            fxy.x = fminf(fmaxf(fxy.x, 0.f), C.out_scale), fxy.y = fminf(fmaxf(fxy.y, 0.f), C.out_scale);
+            fzw.x = fminf(fmaxf(fzw.x, 0.f), C.out_scale);
+        }
+        // truncating store: + 2^23 toward zero leaves 0x4B000000 | (int)v in the bits
+        const f2 txy = addprz2s<PK>(fxy, 8388608.f, C.one), tzw = addprz2s<PK>(fzw, 8388608.f, C.one);
+        ro[p] = __float_as_uint(txy.x), go[p] = __float_as_uint(txy.y), bo[p] = __float_as_uint(tzw.x);
+    }
+}
+
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR>
+__global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
+    __shared__ __align__(16) unsigned s_all[kWarps][kWin + kWin / 2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lane_odd = lane ^ 4;
+    unsigned *sC = s_all[wib];                                                  // [256] (cu | cv << 16), later (u14 | v14 << 16)
+    unsigned *sYw = sC + kWin;                                                  // [128] luma samples, two per word
+    unsigned short *sY = reinterpret_cast<unsigned short *>(sYw);               // [256]
+
+    const int w = K.w, h = K.h, tpr = K.tiles_per_row, R = K.rows_per_cta;
+    const int nrb = (h + R - 1) / R;  // row blocks per frame
+    const unsigned total = (unsigned)K.nframes * (unsigned)nrb * (unsigned)tpr;
+    const FastK fk = K.fk;
+    const Rgb2YuvK b = K.b;
+
+    Consts C;
+    C.yA = fk.yA;
+    C.vr4 = fk.vr4, C.ug4 = fk.ug4, C.ub4 = fk.ub4;
+    C.vgx = fk.vg4 - 65536u * fk.ug4;
+    C.ubx = 0u - 65536u * fk.ub4;
+    C.kR = fk.kR - (unsigned)kCBias * fk.vr4;
+    C.kG = fk.kG - (unsigned)kCBias * fk.vg4 - (unsigned)kCBias * fk.ug4;
+    C.kB = fk.kB - (unsigned)kCBias * fk.ub4;
+    C.idx_mul = fk.idx_mul, C.idx_add = fk.idx_add, C.idx_sr = fk.idx_sr;
+    C.lut_max = K.lut.lut_max, C.out_scale = K.lut.out_scale, C.one = K.wk_one;
+    C.n = K.lut.n, C.n2 = K.lut.n2;
+    C.kbase = 0u - kMagic * (unsigned)(C.n2 + C.n + 1);
+    C.ry = (unsigned)b.ry, C.gy = (unsigned)b.gy, C.by = (unsigned)b.by;
+    C.ru = (unsigned)b.ru, C.gu = (unsigned)b.gu, C.bu = (unsigned)b.bu;
+    C.rv = (unsigned)b.rv, C.gv = (unsigned)b.gv, C.bv = (unsigned)b.bv;
+    C.kY = fk.kY, C.kU = fk.kU, C.kV = fk.kV;
+    const float4 *tab = K.lut.tab;
+
+    // unit = (frame, block of R rows, window), owned by a CTA: its 8 warps take the rows y0 + wib, y0 + wib + 8, ... so that the
+    // warps of an SM work on neighbouring rows of the same image region (similar colours -> the LUT lines they gather stay in L1).
+    // No synchronisation between the warps; a CTA walks units u, u + gridDim.x, ... and keeps the coordinates incrementally.
+    unsigned u = blockIdx.x;
+    if (u >= total) return;
+    unsigned tx = u % (unsigned)tpr, rb = (u / (unsigned)tpr) % (unsigned)nrb, frame = u / ((unsigned)tpr * (unsigned)nrb);
+    const unsigned stride = gridDim.x;
+    const unsigned dtx = stride % (unsigned)tpr, drb = (stride / (unsigned)tpr) % (unsigned)nrb, dfr = stride / ((unsigned)tpr * (unsigned)nrb);
+
+    for (; u < total; u += stride) {
+        const int a = (int)tx * kOut - 8;  // first column of the window
+        const bool edge_tile = tx == 0 || tx == (unsigned)tpr - 1;
+        const int y0 = (int)rb * R + wib, y1 = min(h, (int)rb * R + R);
+        const int x0 = a + 8 * lane, xc = min(max(x0, 0), w - 8);  // this lane's 8 columns in pass A (clamped into the row)
+        const uint8_t *pY = K.p.in[0] + (long)frame * K.p.in_step + (long)y0 * K.p.in_stride[0] + 2 * xc;
+        const uint8_t *pU = K.p.in[1] + (long)frame * K.p.in_step + (long)y0 * K.p.in_stride[1] + xc;
+        const uint8_t *pV = K.p.in[2] + (long)frame * K.p.in_step + (long)y0 * K.p.in_stride[2] + xc;
+        uint8_t *oY = K.p.out[0] + (long)frame * K.p.out_step + (long)y0 * K.p.out_stride[0] + 2 * (long)(a + 8 + 8 * lane);
+        uint8_t *oU = K.p.out[1] + (long)frame * K.p.out_step + (long)y0 * K.p.out_stride[1] + (long)(a + 8 + 8 * lane);
+        uint8_t *oV = K.p.out[2] + (long)frame * K.p.out_step + (long)y0 * K.p.out_stride[2] + (long)(a + 8 + 8 * lane);
+        const int nout = min(kOut, w - (a + 8));  // columns a+8 .. a+8+nout-1 are this window's outputs
+        const bool do_c = 8 * lane < nout;
+
+        uint4 ny = make_uint4(0u, 0u, 0u, 0u);
+        uint2 nu = make_uint2(0u, 0u), nv = make_uint2(0u, 0u);
+        if (y0 < y1) ny = ldg_s16(pY), nu = ldg_s8(pU), nv = ldg_s8(pV);
+        for (int y = y0; y < y1; y += kWarps) {
+            const uint4 cy = ny;
+            const uint2 cu2 = nu, cv2 = nv;
+            if (y + kWarps < y1) {  // prefetch this warp's next row of the window
+                pY += kWarps * (long)K.p.in_stride[0], pU += kWarps * (long)K.p.in_stride[1], pV += kWarps * (long)K.p.in_stride[2];
+                ny = ldg_s16(pY), nu = ldg_s8(pU), nv = ldg_s8(pV);
+            }
+
+            // ---------------- pass A: chroma upsample for columns a + 8*lane .. + 7 ------------------------------------
+            {
+                // chroma words of the neighbouring lanes: (C[i0-2], C[i0-1]) and (C[i0+4], C[i0+5])
+                unsigned ul = __shfl_up_sync(0xFFFFFFFFu, cu2.y, 1), vl = __shfl_up_sync(0xFFFFFFFFu, cv2.y, 1);
+                unsigned ur = __shfl_down_sync(0xFFFFFFFFu, cu2.x, 1), vr = __shfl_down_sync(0xFFFFFFFFu, cv2.x, 1);
+                if (edge_tile) {  // warp-uniform: replicate the first / last chroma sample beyond the row ends
+                    if (xc == 0) ul = (cu2.x & 0xFFFFu) * 0x10001u, vl = (cv2.x & 0xFFFFu) * 0x10001u;
+                    if (xc == w - 8) ur = (cu2.y >> 16) * 0x10001u, vr = (cv2.y >> 16) * 0x10001u;
+                }
+                // chroma window e[0..7] = C[i0-2 .. i0+5]
+                const int eu[8] = {(int)(ul & 0xFFFF),    (int)(ul >> 16),    (int)(cu2.x & 0xFFFF), (int)(cu2.x >> 16),
+                                   (int)(cu2.y & 0xFFFF), (int)(cu2.y >> 16), (int)(ur & 0xFFFF),    (int)(ur >> 16)};
+                const int ev[8] = {(int)(vl & 0xFFFF),    (int)(vl >> 16),    (int)(cv2.x & 0xFFFF), (int)(cv2.x >> 16),
+                                   (int)(cv2.y & 0xFFFF), (int)(cv2.y >> 16), (int)(vr & 0xFFFF),    (int)(vr >> 16)};
+                constexpr int kB9 = kCBias << 9, kTop = 32767 + kCBias;
+                unsigned wv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int j = k >> 1;
+                    int tu, tv;
+                    if (!(k & 1)) {  // even column 2i: taps on C[i-2 .. i+1]
+                        tu = -461 * eu[j] + 3943 * eu[j + 1] + 14284 * eu[j + 2] - 1382 * eu[j + 3] + kB9;
+                        tv = -461 * ev[j] + 3943 * ev[j + 1] + 14284 * ev[j + 2] - 1382 * ev[j + 3] + kB9;
+                    } else {  // odd column 2i+1: taps on C[i-1 .. i+2]
+                        tu = -1382 * eu[j + 1] + 14284 * eu[j + 2] + 3943 * eu[j + 3] - 461 * eu[j + 4] + kB9;
+                        tv = -1382 * ev[j + 1] + 14284 * ev[j + 2] + 3943 * ev[j + 3] - 461 * ev[j + 4] + kB9;
+                    }
+                    if (k == 0 || k == 2) {
+                        if (edge_tile && xc == 0) {  // the two left-most even columns of a row use swscale's edge-normalised taps
+                            if (k == 0) tu = 17729 * eu[2] - 1345 * eu[3] + kB9, tv = 17729 * ev[2] - 1345 * ev[3] + kB9;
+                            if (k == 2) tu = 3835 * eu[2] + 13894 * eu[3] - 1345 * eu[4] + kB9, tv = 3835 * ev[2] + 13894 * ev[3] - 1345 * ev[4] + kB9;
+                        }
+                    }
+                    // c15 = min(T >> 9, 32767), stored + 4096 (so it is never negative): both fit 16 bits
+                    const unsigned cu = (unsigned)min(tu >> 9, kTop), cv = (unsigned)min(tv >> 9, kTop);
+                    wv[k] = cv * 65536u + cu;
+                }
+                __syncwarp();  // pass C of the previous row has finished reading sC
+                *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane + 1)) = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+                *reinterpret_cast<uint4 *>(sYw + 4 * lane) = cy;
+                __syncwarp();
+            }
+
+            // ---------------- pass B: one column per lane, columns a + 32*k + lane ---------------------------------------
+#pragma unroll(UNR)
+            for (int kk = 0; kk < 8; kk += 2) {
+                unsigned mr[2], mg[2], mb[2];
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const int j = 32 * (kk + p) + lane;
+                    const unsigned Y = sY[j], wv = sC[32 * (kk + p) + (p ? lane_odd : lane)];  // == sC[swz_slot(j)]: kk is even
+                    const unsigned cvb = wv >> 16;
+                    // R = Y*yA + cv*vr4 + kR, G = .. + cv*vg4 + cu*ug4, B = .. + cu*ub4 (wrapping 32-bit, as the C code); the
+                    // packed word stands in for cu: wv*g == cu*g + 65536*cv*g (mod 2^32), the surplus is folded into the cv gain
+                    const int Rv = (int)(cvb * C.vr4 + (Y * C.yA + C.kR));
+                    const int Gv = (int)(wv * C.ug4 + (cvb * C.vgx + (Y * C.yA + C.kG)));
+                    const int Bv = (int)(cvb * C.ubx + (wv * C.ub4 + (Y * C.yA + C.kB)));
+                    // av_clip_uintp2(x, 30) >> 20, then 0x4B000000 + code: high word of x * 2^12 plus the magic bits
+                    mr[p] = (unsigned)__mulhi(__vimin_s32_relu(Rv, 0x3FFFFFFF), 4096) + kMagic;
+                    mg[p] = (unsigned)__mulhi(__vimin_s32_relu(Gv, 0x3FFFFFFF), 4096) + kMagic;
+                    mb[p] = (unsigned)__mulhi(__vimin_s32_relu(Bv, 0x3FFFFFFF), 4096) + kMagic;
+                }
+                unsigned ro[2], go[2], bo[2];
+                lut3d_pair<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, PK>(C, tab, mr, mg, mb, ro, go, bo);
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const int j = 32 * (kk + p) + lane;
+                    // Y: clip10((min(2*y14, 32767) + 16) >> 5), y14 = S >> 11  ==  (S + (8 << 11)) >> 15 (host-checked: no clip binds)
+                    const unsigned yq = (unsigned)((int)(C.ry * ro[p] + C.gy * go[p] + C.by * bo[p] + C.kY) >> 15);
+                    const unsigned u14 = (unsigned)((int)(C.ru * ro[p] + C.gu * go[p] + C.bu * bo[p] + C.kU) >> 11);
+                    const unsigned v14 = (unsigned)((int)(C.rv * ro[p] + C.gv * go[p] + C.bv * bo[p] + C.kV) >> 11);
+                    sC[32 * (kk + p) + (p ? lane_odd : lane)] = (v14 << 16) + u14;  // the same lane read this slot above: in place
+                    sY[j] = (unsigned short)yq;  // in place as well; pass C stores the window's own columns 16 bytes per lane
+                }
+            }
+            __syncwarp();
+            if (edge_tile) {  // warp-uniform: columns outside the row take the first / last column's chroma terms
+                const int last = w - 1 - a;  // window slot of the row's last column (>= 255 when the window ends inside the row)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int j = 32 * q + lane;
+                    if (a + j < 0) sC[swz_slot(j)] = sC[swz_slot(-a)];
+                    if (j > last) sC[swz_slot(j)] = sC[swz_slot(last)];
+                }
+                __syncwarp();
+            }
+
+            // ---------------- pass C: 8-tap decimation, lane = chroma samples (a+8)/2 + 4*lane .. + 3 -------------------------
+            if (do_c) {
+                // tt[0..15] = slots 8*lane+4 .. 8*lane+19; chroma sample j covers luma columns 2i-3 .. 2i+4 = tt[2j+1 .. 2j+8]
+                unsigned tt[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 v4 = *reinterpret_cast<const uint4 *>(sC + 4 * swz_chunk(2 * lane + 1 + q));
+                    tt[4 * q] = v4.x, tt[4 * q + 1] = v4.y, tt[4 * q + 2] = v4.z, tt[4 * q + 3] = v4.w;
+                }
+                unsigned uo[2] = {0u, 0u}, vo[2] = {0u, 0u};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // symmetric taps: add mirrored columns while packed (u and v sums stay below 2^16)
+                    const unsigned s0 = tt[2 * j + 1] + tt[2 * j + 8], s1 = tt[2 * j + 2] + tt[2 * j + 7];
+                    const unsigned s2 = tt[2 * j + 3] + tt[2 * j + 6], s3 = tt[2 * j + 4] + tt[2 * j + 5];
+                    // V from the high halves; U = (filter over the packed words) - 65536 * V  (mod 2^32; the true value fits)
+                    const int dv = -230 * (int)(s0 >> 16) - 692 * (int)(s1 >> 16) + 1972 * (int)(s2 >> 16) + 7142 * (int)(s3 >> 16);
+                    const unsigned e = 0u - 230u * s0 - 692u * s1 + 1972u * s2 + 7142u * s3 + (16u << 13);
+                    const int du = (int)(e - 65536u * (unsigned)dv);
+                    // clip10((min(S >> 13, 32767) + 16) >> 5) == clamp((S + (16 << 13)) >> 18, 0, 1023)
+                    uo[j >> 1] |= (unsigned)__vimin_s32_relu(du >> 18, 1023) << (16 * (j & 1));
+                    vo[j >> 1] |= (unsigned)__vimin_s32_relu((dv + (16 << 13)) >> 18, 1023) << (16 * (j & 1));
+                }
+                stg_s16(oY, *reinterpret_cast<const uint4 *>(sYw + 4 * lane + 4));  // luma of columns a+8+8*lane .. +7
+                stg_s8(oU, make_uint2(uo[0], uo[1]));
+                stg_s8(oV, make_uint2(vo[0], vo[1]));
+            }
+            oY += kWarps * (long)K.p.out_stride[0], oU += kWarps * (long)K.p.out_stride[1], oV += kWarps * (long)K.p.out_stride[2];
+        }
+
+        // next unit
+        tx += dtx;
+        unsigned c = tx >= (unsigned)tpr ? 1u : 0u;
+        tx -= c * (unsigned)tpr;
+        rb += drb + c;
+        c = rb >= (unsigned)nrb ? 1u : 0u;
+        rb -= c * (unsigned)nrb;
+        frame += dfr + c;
+    }
+}
+
+}  // namespace
+
+// ---- dispatch ---------------------------------------------------------------------------------------------------------------
+// Specialised on the LUT size (33 / 65: node strides become immediates) for the default semantics only; everything else runs
+// the size-generic instantiation.  IDX 1 = LUT scale folded into the input scale (size-1 a power of two) with the coordinate
+// clip proven dead on the host, IDX 2 = general.
+using KernelFn = void (*)(const StageK);
+
+template <int INTERP, bool FMA, bool CLAMP, int NSZ, bool PK, int MINB, int UNR>
+static KernelFn pick_idx(bool fold_nomin) {
+    if (fold_nomin) return k422_warp<INTERP, FMA, CLAMP, 1, true, NSZ, PK, MINB, UNR>;
+    return k422_warp<INTERP, FMA, CLAMP, 2, false, NSZ, PK, MINB, UNR>;
+}
+
+template <int INTERP, bool PK, int MINB, int UNR>
+static KernelFn pick_sem(bool fma, bool clamp, bool fold_nomin, int n) {
+    if (!fma && !clamp) {
+        if (n == 65) return pick_idx<INTERP, false, false, 65, PK, MINB, UNR>(fold_nomin);
+        if (n == 33) return pick_idx<INTERP, false, false, 33, PK, MINB, UNR>(fold_nomin);
+        return pick_idx<INTERP, false, false, 0, PK, MINB, UNR>(fold_nomin);
+    }
+    if (!fma) return pick_idx<INTERP, false, true, 0, PK, MINB, UNR>(fold_nomin);
+    return clamp ? pick_idx<INTERP, true, true, 0, PK, MINB, UNR>(fold_nomin) : pick_idx<INTERP, true, false, 0, PK, MINB, UNR>(fold_nomin);
+}
+
+int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream) {
+    const bool fma = float_mode == LUTR_FLOAT_FMA, clamp = k.clamp_out != 0;
+    const bool fold_nomin = k.fk.idx_fold && k.wk_nomin;
+    KernelFn fn = nullptr;
+#ifdef LUTR_WK_EXPERIMENTS
+    // occupancy / unroll / packed-vs-scalar float variants of the headline configuration, selected by stage options
+    if (interp == LUTR_INTERP_TETRAHEDRAL && !fma && !clamp && fold_nomin && k.lut.n == 65) {
+#define WK_CASE(P, M, U) \
+    if (k.wk_pk == P && k.min_blocks == M && k.wk_unroll == U) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, P != 0, M, U>;
+        WK_CASE(1, 2, 4) WK_CASE(1, 4, 4) WK_CASE(0, 3, 4) WK_CASE(1, 2, 2) WK_CASE(1, 3, 2) WK_CASE(1, 4, 2) WK_CASE(0, 3, 2)
+        WK_CASE(0, 4, 2) WK_CASE(1, 2, 1) WK_CASE(1, 3, 1) WK_CASE(1, 4, 1) WK_CASE(0, 3, 1) WK_CASE(0, 4, 1)
+#undef WK_CASE
+    }
+#endif
+    if (!fn) {
+        // tetrahedral: two columns per step, all four steps unrolled (8 gathers in flight); trilinear has 16 gathers per step
+        fn = interp == LUTR_INTERP_TRILINEAR ? pick_sem<LUTR_INTERP_TRILINEAR, true, 2, 1>(fma, clamp, fold_nomin, k.lut.n)
+                                             : pick_sem<LUTR_INTERP_TETRAHEDRAL, true, 3, 4>(fma, clamp, fold_nomin, k.lut.n);
+    }
+    const int minb = k.min_blocks >= 2 && k.min_blocks <= 4 ? k.min_blocks : 3;
+    const long total = (long)((k.h + k.rows_per_cta - 1) / k.rows_per_cta) * k.nframes * k.tiles_per_row;
+    long grid = k.grid_ctas > 0 ? k.grid_ctas : 148 * minb;
+    if (grid > total) grid = total;
+    fn<<<(unsigned)grid, kWarps * 32, 0, (cudaStream_t)stream>>>(k);
+    return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
+}
+
+}  // namespace lutr

@@ -57,9 +57,13 @@ struct lutr_stage {
     std::vector<IdxTable> idx_tables;
     int use_fast = 1;      // 0 forces the generic kernels (testing)
     int grid_ctas = 0;     // 0 = min_blocks CTAs per SM
-    int idx_mode = 2;      // 0 = shared-memory index table, 1 = arithmetic index, 2 = arithmetic index + TMA-staged rows
+    int idx_mode = 3;      // 0 = shared-memory index table, 1 = arithmetic index, 2 = arithmetic index + TMA-staged rows,
+                           // 3 = warp-window kernel (k422_warp.cu)
     int min_blocks = 2;    // occupancy variant of the fast kernels (CTAs per SM)
     int fast_threads = 0;  // threads per CTA of the TMA kernel (0 = auto)
+    int wk_pk = 1;         // warp-window kernel: packed f32x2 instructions
+    int wk_unroll = 4;     // warp-window kernel: pass B steps unrolled together (experiment builds)
+    int wk_minb = 3;       // warp-window kernel: CTAs per SM the register budget is set for
     std::atomic<int64_t> launches{0};
 };
 
@@ -222,8 +226,15 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     k.min_blocks = s->min_blocks;
     k.fast_threads = s->fast_threads;
     k.clamp_out = lut->needs_clamp ? 1 : 0;
+    bool warp_kernel = false;
     if (fast_path_ok(s, lut)) {
         k.idx_mode = s->idx_mode;
+        if (k.idx_mode == 3) {
+            // warp-window kernel: 8-column lanes (w % 8, 16-byte luma / 8-byte chroma vector accesses: check_planes), 32-bit unit counter
+            const long tiles = (long)((k.w + 239) / 240) * k.h * nframes;
+            warp_kernel = s->d.in_fmt == LUTR_PIX_YUV422P10LE && (k.w % 8) == 0 && k.w >= 16 && tiles < (1l << 31);
+            if (!warp_kernel) k.idx_mode = 2;
+        }
         if (k.idx_mode == 2) {
             // TMA-staged rows need 16-byte aligned bulk copies (row starts and row lengths) and the ring must fit in shared memory
             bool ok = s->d.in_fmt == LUTR_PIX_YUV422P10LE && (k.w % 16) == 0 && (in->frame_step % 16) == 0;
@@ -265,12 +276,35 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         fk.idx_sr = fk.idx_fold ? 1.f : sr;
         fk.idx_add = -(fk.idx_mul * 8388608.f);
         fk.maxv = maxv;
+        if (warp_kernel) {
+            k.tiles_per_row = (k.w + 239) / 240;
+            k.wk_pk = s->wk_pk;
+            k.wk_one = 1.0f;
+            k.wk_unroll = s->wk_unroll;
+            k.min_blocks = s->d.interp == LUTR_INTERP_TRILINEAR ? 2 : s->wk_minb;
+            // the clip of the LUT coordinate to lut_max is dead code unless some code value overshoots it: try them all
+            k.wk_nomin = 1;
+            for (int x = 0; x <= maxv; ++x) {
+                volatile float a = (float)x * fk.idx_mul;  // volatile: one rounding per operation
+                volatile float c = a * fk.idx_sr;
+                if (c > lut_max) k.wk_nomin = 0;
+            }
+        }
     }
     k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : k.min_blocks * s->ctx->sm_count;
     if (s->d.in_fmt == LUTR_PIX_YUV422P10LE) {
         k.rows_per_cta = s->rows_per_cta > 0 ? s->rows_per_cta : 1;
+        if (warp_kernel) {
+            // rows per CTA unit (8 warps, interleaved rows): as many as still leave every CTA of the persistent grid >= 32 units
+            long r = s->rows_per_cta;
+            if (r <= 0) {
+                r = (long)k.tiles_per_row * k.h * nframes / (32l * k.grid_ctas);
+                r = r < 8 ? 8 : (r > 64 ? 64 : r);
+            }
+            k.rows_per_cta = (int)((r + 7) / 8 * 8);
+        }
         k.bands = 1;
-        rc = launch_yuv422p10(k, s->d.interp, s->d.float_mode, st);
+        rc = warp_kernel ? launch_k422_warp(k, s->d.interp, s->d.float_mode, st) : launch_yuv422p10(k, s->d.interp, s->d.float_mode, st);
     } else {
         // bands per frame: enough CTAs to fill the device a few times over, but bands of >= 16 rows (7 halo rows each)
         int rows = s->band_rows;
@@ -673,7 +707,10 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     else if (!std::strcmp(name, "band_rows")) s->band_rows = value;
     else if (!std::strcmp(name, "fast_path")) s->use_fast = value;
     else if (!std::strcmp(name, "grid_ctas")) s->grid_ctas = value;
-    else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value < 0 || value > 2 ? 1 : value;
+    else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value < 0 || value > 3 ? 1 : value;
+    else if (!std::strcmp(name, "wk_pk")) s->wk_pk = value;
+    else if (!std::strcmp(name, "wk_unroll")) s->wk_unroll = value;
+    else if (!std::strcmp(name, "wk_minb")) s->wk_minb = value >= 2 && value <= 4 ? value : 3;
     else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value >= 2 && value <= 4 ? value : 3;
     else if (!std::strcmp(name, "fast_threads")) s->fast_threads = value;
     else if (!std::strcmp(name, "l2_persist")) {

@@ -92,6 +92,12 @@ struct StageK {
     int32_t idx_mode;         // 0: shared-memory index table, 1: arithmetic index (no table)
     int32_t min_blocks;       // occupancy variant of the fast kernel (2, 3 or 4 CTAs per SM)
     int32_t fast_threads;     // threads per CTA of the TMA kernel (0 = 256)
+    // warp-window kernel (k422_warp.cu)
+    int32_t tiles_per_row;       // ceil(w / 240)
+    int32_t wk_pk;               // 1: packed f32x2 instructions
+    float wk_one;                // 1.0f the compiler cannot constant-fold (see addp2 in k422_warp.cu)
+    int32_t wk_unroll;           // pass B double-iterations unrolled together (1, 2, 4)
+    int32_t wk_nomin;            // 1: the clip of the LUT coordinate to lut_max can never bind (host-checked), drop it
 };
 
 // host-side construction of the index table (colour_tables.cpp): same float operations as lut3d's per-pixel prologue
@@ -100,5 +106,6 @@ void build_index_table(int depth, int entries, float scale_times_lutmax, float l
 // launchers (stage_kernels.cu); `stream` is a cudaStream_t
 int launch_yuv422p10(const StageK &k, int interp, int float_mode, void *stream);
 int launch_yuv420p8(const StageK &k, int interp, int float_mode, void *stream);
+int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream);
 
 }  // namespace lutr

@@ -94,20 +94,45 @@ def test_yuv422p10_rows_per_cta_and_domain_scale():
 @pytest.mark.parametrize("options", [dict(fast_path=0), dict(idx_mode=0, min_blocks=3), dict(idx_mode=0, min_blocks=4),
                                      dict(idx_mode=1, min_blocks=3), dict(idx_mode=1, min_blocks=4), dict(grid_ctas=1), dict(grid_ctas=7),
                                      dict(idx_mode=2, min_blocks=3), dict(idx_mode=2, min_blocks=4), dict(idx_mode=2, grid_ctas=1),
-                                     dict(idx_mode=2, grid_ctas=2), dict(idx_mode=2, grid_ctas=5)])
+                                     dict(idx_mode=2, grid_ctas=2), dict(idx_mode=2, grid_ctas=5),
+                                     dict(idx_mode=3), dict(idx_mode=3, grid_ctas=1), dict(idx_mode=3, grid_ctas=3, rows_per_cta=8),
+                                     dict(idx_mode=3, rows_per_cta=64), dict(idx_mode=3, float_mode="fma")])
 @pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
 def test_yuv422p10_kernel_variants(options, interp):
     """Every code path of the 4:2:2 stage (generic kernel, index table / arithmetic index, occupancy variants, tiny persistent
     grids) gives the same bits; LUTs: values inside [0,1] (no store clip), outside (clip), size-1 not a power of two."""
     w, h = 656, 21
+    options = dict(options)
+    float_mode = options.pop("float_mode", "c")
     frames = _frames("yuv422p10le", w, h, ["natural", "noise", "extremes"])
-    for lut_name, table in (("look33", LUTS["look33"]()), ("rand64", LUTS["rand64"]()), ("wide9", synth.random_lut(9, 4) * 1.6 - 0.3)):
+    for lut_name, table in (("look33", LUTS["look33"]()), ("look65", LUTS["look65"]()), ("rand64", LUTS["rand64"]()),
+                            ("wide9", synth.random_lut(9, 4) * 1.6 - 0.3)):
         table = table.astype(np.float32)
-        got = gpu_stage("yuv422p10le", w, h, frames, table, interp=interp, options=options)
+        got = gpu_stage("yuv422p10le", w, h, frames, table, interp=interp, options=options, float_mode=float_mode)
+        if float_mode == "fma":  # opt-in contraction: same bits from every kernel that implements it
+            ref = gpu_stage("yuv422p10le", w, h, frames, table, interp=interp, options=dict(idx_mode=2), float_mode=float_mode)
+            for i in range(len(frames)):
+                assert np.array_equal(got[i], ref[i]), f"422p10 fma {lut_name} {interp} frame {i}"
+            continue
         L = oracle_lut(table)
         for i, f in enumerate(frames):
             assert_bit_exact("yuv422p10le", w, h, got[i], oracle_stage("yuv422p10le", w, h, f, L, interp=interp),
                              f"422p10 {options} {lut_name} {interp} frame {i}")
+
+
+@pytest.mark.parametrize("w", [16, 232, 240, 248, 256, 472, 480, 488, 496, 728, 1928])
+@pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
+def test_yuv422p10_window_edges(w, interp):
+    """Row widths around the 240-column windows of the warp-window kernel (exactly one window, one column group more or
+    less, ragged last windows), several frames, more rows than one CTA unit and a row count that is not a multiple of 8."""
+    h = 19
+    table = LUTS["look65"]().astype(np.float32)
+    frames = _frames("yuv422p10le", w, h, ["natural", "noise", "extremes"])
+    got = gpu_stage("yuv422p10le", w, h, frames, table, interp=interp, options=dict(idx_mode=3, rows_per_cta=8))
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        assert_bit_exact("yuv422p10le", w, h, got[i], oracle_stage("yuv422p10le", w, h, f, L, interp=interp),
+                         f"422p10 window edges w={w} {interp} frame {i}")
 
 
 @pytest.mark.parametrize("options", [dict(fast_path=0), dict(fast_path=1), dict(fast_path=1, band_rows=12), dict(fast_path=1, band_rows=26)])
