@@ -46,12 +46,13 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def ncu_traffic(config_name):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists for this config."""
+def ncu_traffic(config_name, frames_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from the committed `ncu --set full` capture of
+    this config (profiles/traffic.json holds bytes per frame of that capture), scaled to this run's frames per launch."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(config_name)
+            return int(json.load(f)[config_name]["dram_bytes_per_frame"] * frames_per_launch)
     except Exception:
         return None
 
@@ -326,7 +327,7 @@ def main():
         per_launch_ms = ms / args.steps
         achieved = bytes_per_frame * F / (per_launch_ms / 1e3) / 1e9
         peak, peak_src = measured_peak_hbm()
-        kernel = "k_yuv422p10" if cfg["pix_fmt"] == "yuv422p10le" else "k_yuv420p8"
+        kernel = stage.kernel_name
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_baseline as C
@@ -347,7 +348,7 @@ def main():
                        "sharding": "contiguous frame range per GPU, no collective", "parity_spot_check": parity},
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1),
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": ncu_traffic(args.config), "peak_source": peak_src,
+                         "traffic": ncu_traffic(args.config, F), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(bytes_per_frame * F), "frac_of_8TBs_nominal": round(achieved / 8000.0, 4), "per": "GPU"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }

@@ -149,8 +149,11 @@ LUTR_API int lutr_stage_run_host(lutr_stage *stage, const lutr_lut *lut, const v
 LUTR_API int lutr_stage_sync(lutr_stage *stage);
 /* number of kernel launches this stage has enqueued so far (bench.py's gpu_launches) */
 LUTR_API int64_t lutr_stage_launch_count(const lutr_stage *stage);
+/* name of the kernel family the most recent enqueue of this stage launched ("" before the first one); diagnostics */
+LUTR_API const char *lutr_stage_kernel_name(const lutr_stage *stage);
 /* run-time tunables, for benchmarking: "rows_per_cta", "band_rows", "l2_persist" (0/1), "fast_path" (0/1),
- * "grid_ctas" (persistent grid of the fast kernels) */
+ * "grid_ctas" (persistent grid of the fast kernels), "idx_mode" (4:2:2 kernel family: 3 = warp-window kernel, 2 = TMA-staged rows,
+ * 1 / 0 = earlier fast kernels), "min_blocks", "wk_minb" */
 LUTR_API int lutr_stage_set_option(lutr_stage *stage, const char *name, int32_t value);
 
 /* ---- coefficient tables (exposed so the parity tests can pin them against libswscale) --------------- */

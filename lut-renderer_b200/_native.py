@@ -66,6 +66,7 @@ SIGNATURES = {
     "lutr_stage_run_host": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32]),
     "lutr_stage_sync": (ctypes.c_int, [c_void_p]),
     "lutr_stage_launch_count": (c_int64, [c_void_p]),
+    "lutr_stage_kernel_name": (c_char_p, [c_void_p]),
     "lutr_stage_set_option": (ctypes.c_int, [c_void_p, c_char_p, c_int32]),
     "lutr_tables_yuv2rgb": (ctypes.c_int, [c_int32, c_int32, POINTER(c_int32)]),
     "lutr_tables_rgb2yuv": (ctypes.c_int, [c_int32, POINTER(c_int32)]),

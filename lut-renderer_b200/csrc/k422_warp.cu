@@ -392,9 +392,9 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                             if (k == 2) tu = 3835 * eu[2] + 13894 * eu[3] - 1345 * eu[4] + kB9, tv = 3835 * ev[2] + 13894 * ev[3] - 1345 * ev[4] + kB9;
                         }
                     }
-                    // c15 = min(T >> 9, 32767), stored + 4096 (so it is never negative): both fit 16 bits
-                    const unsigned cu = (unsigned)min(tu >> 9, kTop), cv = (unsigned)min(tv >> 9, kTop);
-                    wv[k] = cv * 65536u + cu;
+                    // c15 = min(T >> 9, 32767), stored + 4096 (so it is never negative).  Both fit 16 bits even before the min
+                    // (10-bit samples: 0 <= (T >> 9) + 4096 < 40600), so pack first and clip both halves with one instruction.
+                    wv[k] = __vminu2((unsigned)(tv >> 9) * 65536u + (unsigned)(tu >> 9), (unsigned)kTop * 0x10001u);
                 }
                 __syncwarp();  // pass C of the previous row has finished reading sC
                 *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);

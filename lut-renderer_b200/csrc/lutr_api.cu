@@ -65,6 +65,7 @@ struct lutr_stage {
     int wk_unroll = 4;     // warp-window kernel: pass B steps unrolled together (experiment builds)
     int wk_minb = 3;       // warp-window kernel: CTAs per SM the register budget is set for
     std::atomic<int64_t> launches{0};
+    const char *last_kernel = "";  // kernel family of the most recent enqueue (bench.py's roofline.kernel)
 };
 
 namespace {
@@ -305,6 +306,7 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         }
         k.bands = 1;
         rc = warp_kernel ? launch_k422_warp(k, s->d.interp, s->d.float_mode, st) : launch_yuv422p10(k, s->d.interp, s->d.float_mode, st);
+        s->last_kernel = warp_kernel ? "k422_warp" : (k.idx_mode == 2 ? "k_yuv422p10_tma" : (k.idx_mode >= 0 ? "k_yuv422p10_fast" : "k_yuv422p10"));
     } else {
         // bands per frame: enough CTAs to fill the device a few times over, but bands of >= 16 rows (7 halo rows each)
         int rows = s->band_rows;
@@ -320,6 +322,7 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         k.rows_per_cta = rows;
         k.bands = (k.h + rows - 1) / rows;
         rc = launch_yuv420p8(k, s->d.interp, s->d.float_mode, st);
+        s->last_kernel = k.idx_mode >= 0 && s->d.interp != LUTR_INTERP_NEAREST ? "k_yuv420p8_fast" : "k_yuv420p8";
     }
     if (rc != LUTR_OK) {
         set_error("kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -700,6 +703,8 @@ int lutr_stage_sync(lutr_stage *s) {
 }
 
 int64_t lutr_stage_launch_count(const lutr_stage *s) { return s ? s->launches.load() : 0; }
+
+const char *lutr_stage_kernel_name(const lutr_stage *s) { return s ? s->last_kernel : ""; }
 
 int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     if (!s || !name) return LUTR_ERR_INVALID_ARG;

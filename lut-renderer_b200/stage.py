@@ -197,6 +197,11 @@ class ColourStage:
     def launch_count(self) -> int:
         return int(N.lib().lutr_stage_launch_count(self._h))
 
+    @property
+    def kernel_name(self) -> str:
+        """Kernel family the most recent enqueue launched (diagnostics / bench.py's roofline.kernel)."""
+        return (N.lib().lutr_stage_kernel_name(self._h) or b"").decode()
+
     def close(self):
         if self._h:
             N.lib().lutr_stage_destroy(self._h)

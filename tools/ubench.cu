@@ -53,6 +53,38 @@ __global__ void __launch_bounds__(1024, 1) kern(float *out, unsigned long long *
                 asm volatile("mad.lo.u32 %4,%4,%10,%11; fma.rn.f32 %0,%0,%8,%9; mad.lo.u32 %5,%5,%10,%11; fma.rn.f32 %1,%1,%8,%9;"
                              "mad.lo.u32 %6,%6,%10,%11; fma.rn.f32 %2,%2,%8,%9; mad.lo.u32 %7,%7,%10,%11; fma.rn.f32 %3,%3,%8,%9;"
                              : "+f"(x0), "+f"(x1), "+f"(x2), "+f"(x3), "+r"(i0), "+r"(i1), "+r"(i2), "+r"(i3) : "f"(a), "f"(b), "r"(ia), "r"(ib));
+            } else if (MODE == 10) {  // 4 IMAD + 4 FFMA2
+                asm volatile("{.reg .b64 p,q,r,s,m,n; mov.b64 m,{%12,%12}; mov.b64 n,{%13,%13};"
+                             "mov.b64 p,{%0,%1}; mov.b64 q,{%2,%3}; mov.b64 r,{%4,%5}; mov.b64 s,{%6,%7};"
+                             "fma.rn.f32x2 p,p,m,n; mad.lo.u32 %8,%8,%14,%15; fma.rn.f32x2 q,q,m,n; mad.lo.u32 %9,%9,%14,%15;"
+                             "fma.rn.f32x2 r,r,m,n; mad.lo.u32 %10,%10,%14,%15; fma.rn.f32x2 s,s,m,n; mad.lo.u32 %11,%11,%14,%15;"
+                             "mov.b64 {%0,%1},p; mov.b64 {%2,%3},q; mov.b64 {%4,%5},r; mov.b64 {%6,%7},s;}"
+                             : "+f"(x0), "+f"(x1), "+f"(x2), "+f"(x3), "+f"(x4), "+f"(x5), "+f"(x6), "+f"(x7), "+r"(i0), "+r"(i1), "+r"(i2), "+r"(i3)
+                             : "f"(a), "f"(b), "r"(ia), "r"(ib));
+            } else if (MODE == 11) {  // 4 IMAD + 8 FFMA (the same float work as mode 10, scalar) -> counted as 12 instructions per 8
+                asm volatile("fma.rn.f32 %0,%0,%12,%13; fma.rn.f32 %1,%1,%12,%13; mad.lo.u32 %8,%8,%14,%15; fma.rn.f32 %2,%2,%12,%13; fma.rn.f32 %3,%3,%12,%13; mad.lo.u32 %9,%9,%14,%15;"
+                             "fma.rn.f32 %4,%4,%12,%13; fma.rn.f32 %5,%5,%12,%13; mad.lo.u32 %10,%10,%14,%15; fma.rn.f32 %6,%6,%12,%13; fma.rn.f32 %7,%7,%12,%13; mad.lo.u32 %11,%11,%14,%15;"
+                             : "+f"(x0), "+f"(x1), "+f"(x2), "+f"(x3), "+f"(x4), "+f"(x5), "+f"(x6), "+f"(x7), "+r"(i0), "+r"(i1), "+r"(i2), "+r"(i3)
+                             : "f"(a), "f"(b), "r"(ia), "r"(ib));
+            } else if (MODE == 12) {  // 2 IMAD + 2 LOP3 + 2 FFMA2 + 2 more LOP3 (kernel-like mix)
+                asm volatile("{.reg .b64 p,q,m,n; mov.b64 m,{%12,%12}; mov.b64 n,{%13,%13}; mov.b64 p,{%0,%1}; mov.b64 q,{%2,%3};"
+                             "fma.rn.f32x2 p,p,m,n; mad.lo.u32 %8,%8,%14,%15; lop3.b32 %10,%10,%14,%15,0x96; lop3.b32 %11,%11,%14,%15,0x96;"
+                             "fma.rn.f32x2 q,q,m,n; mad.lo.u32 %9,%9,%14,%15; lop3.b32 %10,%10,%15,%14,0x96; lop3.b32 %11,%11,%15,%14,0x96;"
+                             "mov.b64 {%0,%1},p; mov.b64 {%2,%3},q;}"
+                             : "+f"(x0), "+f"(x1), "+f"(x2), "+f"(x3), "+f"(x4), "+f"(x5), "+f"(x6), "+f"(x7), "+r"(i0), "+r"(i1), "+r"(i2), "+r"(i3)
+                             : "f"(a), "f"(b), "r"(ia), "r"(ib));
+            } else if (MODE == 13) {  // 8 FFMA with distinct constant operands per instruction pair (fewer register-bank clashes)
+                asm volatile("fma.rn.f32 %0,%0,%8,%9; fma.rn.f32 %1,%1,%9,%8; fma.rn.f32 %2,%2,%8,%9; fma.rn.f32 %3,%3,%9,%8;"
+                             "fma.rn.f32 %4,%4,%8,%9; fma.rn.f32 %5,%5,%9,%8; fma.rn.f32 %6,%6,%8,%9; fma.rn.f32 %7,%7,%9,%8;"
+                             : "+f"(x0), "+f"(x1), "+f"(x2), "+f"(x3), "+f"(x4), "+f"(x5), "+f"(x6), "+f"(x7) : "f"(a), "f"(b));
+            } else if (MODE == 14) {  // 8 IMAD with an immediate multiplier
+                asm volatile("mad.lo.u32 %0,%0,12345,%4; mad.lo.u32 %1,%1,12345,%4; mad.lo.u32 %2,%2,12345,%4; mad.lo.u32 %3,%3,12345,%4;"
+                             "mad.lo.u32 %0,%0,54321,%4; mad.lo.u32 %1,%1,54321,%4; mad.lo.u32 %2,%2,54321,%4; mad.lo.u32 %3,%3,54321,%4;"
+                             : "+r"(i0), "+r"(i1), "+r"(i2), "+r"(i3) : "r"(ia));
+            } else if (MODE == 15) {  // 8 IADD3
+                asm volatile("add.u32 %0,%0,%4; add.u32 %1,%1,%4; add.u32 %2,%2,%4; add.u32 %3,%3,%4;"
+                             "add.u32 %0,%0,%5; add.u32 %1,%1,%5; add.u32 %2,%2,%5; add.u32 %3,%3,%5;"
+                             : "+r"(i0), "+r"(i1), "+r"(i2), "+r"(i3) : "r"(ia), "r"(ib));
             } else if (MODE == 8) {  // 8 FADD (scalar)
                 asm volatile("add.rn.f32 %0,%0,%8; add.rn.f32 %1,%1,%8; add.rn.f32 %2,%2,%8; add.rn.f32 %3,%3,%8;"
                              "add.rn.f32 %4,%4,%8; add.rn.f32 %5,%5,%8; add.rn.f32 %6,%6,%8; add.rn.f32 %7,%7,%8;"
@@ -100,5 +132,11 @@ int main() {
     run<7>("IMAD+FFMA 1:1");
     run<8>("FADD");
     run<9>("VIMNMX");
+    run<10>("IMAD+FFMA2 1:1");
+    run<11>("IMAD+FFMA 1:2 (x1.5 instr)");
+    run<12>("FFMA2+IMAD+2xLOP3");
+    run<13>("FFMA alt operands");
+    run<14>("IMAD imm");
+    run<15>("IADD");
     return 0;
 }
