@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblutr.so")
-SOURCES = ["cube_parser.cpp", "colour_tables.cpp", "stage_kernels.cu", "k422_warp.cu", "lutr_api.cu"]
-HEADERS = ["lutr_internal.h", os.path.join("..", "..", "include", "lutr.h")]
+SOURCES = ["cube_parser.cpp", "colour_tables.cpp", "stage_kernels.cu", "k422_warp.cu", "k420_warp.cu", "lutr_api.cu"]
+HEADERS = ["lutr_internal.h", "warp_common.cuh", os.path.join("..", "..", "include", "lutr.h")]
 GENCODE = "arch=compute_100a,code=sm_100a"
 
 
@@ -37,28 +37,40 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
-    cmd = [
-        nvcc_path(), "-shared", "-o", OUT,
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    common = [
         "-gencode", GENCODE, "-O3", "-lineinfo", "-std=c++17",
-        # lut3d's C semantics round every product and every sum: ptxas must never contract a mul + add pair (it does so for the
-        # packed mul.rn.f32x2 / add.rn.f32x2 pair unless told not to; wanted fmas are written as fma explicitly)
+        # lut3d's C semantics round every product and every sum: ptxas must never contract a mul + add pair (the packed
+        # mul.rn.f32x2 / add.rn.f32x2 pair is contracted regardless, see addp2 in csrc/warp_common.cuh)
         "-fmad=false",
         "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wextra,-ffp-contract=off",
-        "-cudart", "static",
     ]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
+        common += ["-Xptxas", "-v"]
     if os.environ.get("LUTR_WK_EXPERIMENTS"):
-        cmd += ["-DLUTR_WK_EXPERIMENTS"]
-    if os.environ.get("LUTR_WK_UNROLL"):
-        cmd += ["-DLUTR_WK_UNROLL=" + os.environ["LUTR_WK_UNROLL"]]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
+        common += ["-DLUTR_WK_EXPERIMENTS"]
+    # one nvcc per translation unit, in parallel (the template-heavy kernel files dominate the build time)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc_path(), "-c", "-o", obj] + common + [os.path.join(CSRC, src)]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, _, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(out)
+        elif verbose:
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc failed building liblutr.so")
+    cmd = [nvcc_path(), "-shared", "-o", OUT, "-gencode", GENCODE, "-cudart", "static"] + [obj for _, obj, _ in procs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building liblutr.so")
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking liblutr.so")
     return OUT
 
 

@@ -63,6 +63,7 @@ struct lutr_stage {
     int fast_threads = 0;  // threads per CTA of the TMA kernel (0 = auto)
     int wk_pk = 1;         // warp-window kernel: packed f32x2 instructions
     int wk_unroll = 4;     // warp-window kernel: pass B steps unrolled together (experiment builds)
+    int wk_nk_forced = 0;  // 4:2:0 warp-window kernel: wk_unroll was set explicitly (2 or 4 steps of 64 columns per window)
     int wk_minb = 3;       // warp-window kernel: CTAs per SM the register budget is set for
     std::atomic<int64_t> launches{0};
     const char *last_kernel = "";  // kernel family of the most recent enqueue (bench.py's roofline.kernel)
@@ -233,7 +234,9 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         if (k.idx_mode == 3) {
             // warp-window kernel: 8-column lanes (w % 8, 16-byte luma / 8-byte chroma vector accesses: check_planes), 32-bit unit counter
             const long tiles = (long)((k.w + 239) / 240) * k.h * nframes;
-            warp_kernel = s->d.in_fmt == LUTR_PIX_YUV422P10LE && (k.w % 8) == 0 && k.w >= 16 && tiles < (1l << 31);
+            warp_kernel = (k.w % 8) == 0 && k.w >= 16 && tiles < (1l << 31);
+            // the 4:2:0 windows are 128 or 256 columns and never wider than the row (the last one is shifted, not clipped)
+            if (s->d.in_fmt == LUTR_PIX_YUV420P && k.w < 256) warp_kernel = false;
             if (!warp_kernel) k.idx_mode = 2;
         }
         if (k.idx_mode == 2) {
@@ -278,7 +281,7 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         fk.idx_add = -(fk.idx_mul * 8388608.f);
         fk.maxv = maxv;
         if (warp_kernel) {
-            k.tiles_per_row = (k.w + 239) / 240;
+            k.tiles_per_row = (k.w + 239) / 240;  // 4:2:2; the 4:2:0 windows are sized below
             k.wk_pk = s->wk_pk;
             k.wk_one = 1.0f;
             k.wk_unroll = s->wk_unroll;
@@ -307,6 +310,12 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         k.bands = 1;
         rc = warp_kernel ? launch_k422_warp(k, s->d.interp, s->d.float_mode, st) : launch_yuv422p10(k, s->d.interp, s->d.float_mode, st);
         s->last_kernel = warp_kernel ? "k422_warp" : (k.idx_mode == 2 ? "k_yuv422p10_tma" : (k.idx_mode >= 0 ? "k_yuv422p10_fast" : "k_yuv422p10"));
+    } else if (warp_kernel) {
+        // 4:2:0 warp-window kernel (window width and grid are chosen in the launcher)
+        k.wk_unroll = s->wk_nk_forced ? s->wk_unroll : 0;
+        k.rows_per_cta = 0, k.bands = 1;
+        rc = launch_k420_warp(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+        s->last_kernel = "k420_warp";
     } else {
         // bands per frame: enough CTAs to fill the device a few times over, but bands of >= 16 rows (7 halo rows each)
         int rows = s->band_rows;
@@ -714,7 +723,7 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     else if (!std::strcmp(name, "grid_ctas")) s->grid_ctas = value;
     else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value < 0 || value > 3 ? 1 : value;
     else if (!std::strcmp(name, "wk_pk")) s->wk_pk = value;
-    else if (!std::strcmp(name, "wk_unroll")) s->wk_unroll = value;
+    else if (!std::strcmp(name, "wk_unroll")) s->wk_unroll = value, s->wk_nk_forced = 1;
     else if (!std::strcmp(name, "wk_minb")) s->wk_minb = value >= 2 && value <= 4 ? value : 3;
     else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value >= 2 && value <= 4 ? value : 3;
     else if (!std::strcmp(name, "fast_threads")) s->fast_threads = value;

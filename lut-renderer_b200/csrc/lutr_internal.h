@@ -107,5 +107,6 @@ void build_index_table(int depth, int entries, float scale_times_lutmax, float l
 int launch_yuv422p10(const StageK &k, int interp, int float_mode, void *stream);
 int launch_yuv420p8(const StageK &k, int interp, int float_mode, void *stream);
 int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream);
+int launch_k420_warp(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);
 
 }  // namespace lutr

@@ -1,0 +1,264 @@
+// Shared device code of the warp-window kernels (k422_warp.cu, k420_warp.cu): two-wide float helpers on Blackwell's packed
+// FP32 instructions and the lut3d evaluation of two pixels per lane.  Arithmetic: FFmpeg vf_lut3d semantics as restated in
+// oracle/lutr_oracle.c (float32, one rounding per C operation, truncating store); reference call site
+// src/lut_renderer/ffmpeg.py:242-247.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "lutr_internal.h"
+
+namespace lutr {
+namespace {
+
+constexpr unsigned kMagic = 0x4B000000u;  // bits of 8388608.0f
+
+// ---- two-wide float helpers: PK = packed f32x2 instructions, otherwise two scalar instructions with the same rounding ----
+struct f2 {
+    float x, y;
+};
+
+template <bool PK>
+__device__ __forceinline__ f2 mul2s(f2 a, float b) {  // a * b (b broadcast)
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; mul.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b));
+    } else {
+        r.x = __fmul_rn(a.x, b), r.y = __fmul_rn(a.y, b);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; mul.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    } else {
+        r.x = __fmul_rn(a.x, b.x), r.y = __fmul_rn(a.y, b.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; add.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    } else {
+        r.x = __fadd_rn(a.x, b.x), r.y = __fadd_rn(a.y, b.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; sub.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    } else {
+        r.x = __fsub_rn(a.x, b.x), r.y = __fsub_rn(a.y, b.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 add2s(f2 a, float b) {  // a + b (b broadcast), round to nearest
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; add.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b));
+    } else {
+        r.x = __fadd_rn(a.x, b), r.y = __fadd_rn(a.y, b);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 rsub2s(float a, f2 b) {  // a - b (a broadcast)
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%2}; mov.b64 b,{%3,%4}; sub.rn.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a), "f"(b.x), "f"(b.y));
+    } else {
+        r.x = __fsub_rn(a, b.x), r.y = __fsub_rn(a, b.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 addrz2s(f2 a, float b) {  // a + b (b broadcast), round toward zero
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; add.rz.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b));
+    } else {
+        r.x = __fadd_rz(a.x, b), r.y = __fadd_rz(a.y, b);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 fma2s(f2 a, float b, float c) {  // fma(a, b, c), b and c broadcast
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; mov.b64 c,{%5,%5}; fma.rn.f32x2 d,a,b,c; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b), "f"(c));
+    } else {
+        r.x = __fmaf_rn(a.x, b, c), r.y = __fmaf_rn(a.y, b, c);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; mov.b64 c,{%6,%7}; fma.rn.f32x2 d,a,b,c; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    } else {
+        r.x = __fmaf_rn(a.x, b.x, c.x), r.y = __fmaf_rn(a.y, b.y, c.y);
+    }
+    return r;
+}
+template <bool PK>
+__device__ __forceinline__ f2 fma2ss(f2 a, float b, f2 c) {  // fma(a, b, c), b broadcast
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; mov.b64 c,{%5,%6}; fma.rn.f32x2 d,a,b,c; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b), "f"(c.x), "f"(c.y));
+    } else {
+        r.x = __fmaf_rn(a.x, b, c.x), r.y = __fmaf_rn(a.y, b, c.y);
+    }
+    return r;
+}
+
+// prod + acc where prod comes out of a multiply.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even with
+// -fmad=false), which would drop the product's rounding; fma(prod, one, acc) with `one` a run-time 1.0f it cannot see through is
+// the same single-rounding add and cannot be merged with the multiply.
+template <bool PK>
+__device__ __forceinline__ f2 addp2(f2 prod, f2 acc, float one) {
+    if (PK) return fma2ss<PK>(prod, one, acc);
+    return add2<PK>(prod, acc);
+}
+template <bool PK>
+__device__ __forceinline__ f2 addprz2s(f2 prod, float b, float one) {  // (prod + b) toward zero, b broadcast, prod from a multiply
+    f2 r;
+    if (PK) {
+        asm("{.reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; mov.b64 c,{%5,%5}; fma.rz.f32x2 d,a,b,c; mov.b64 {%0,%1},d;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(prod.x), "f"(prod.y), "f"(one), "f"(b));
+    } else {
+        r.x = __fadd_rz(prod.x, b), r.y = __fadd_rz(prod.y, b);
+    }
+    return r;
+}
+
+// acc (+)= w * c per element: C semantics = rounded product then rounded sum, FMA = one rounding (lut3d's x86 assembly)
+template <bool PK, bool FMA>
+__device__ __forceinline__ f2 wacc(f2 c, float w, f2 acc, float one) {
+    if (FMA) return fma2ss<PK>(c, w, acc);
+    return addp2<PK>(mul2s<PK>(c, w), acc, one);
+}
+
+// lut3d constants of one launch
+struct LutC {
+    float idx_mul, idx_add, idx_sr, lut_max, out_scale, one;
+    unsigned kbase;  // -0x4B000000 * (n*n + n + 1): removes the float bias of the three node indices (wrapping arithmetic)
+    int n, n2;
+};
+
+__device__ __forceinline__ LutC make_lutc(const StageK &K) {
+    LutC C;
+    C.idx_mul = K.fk.idx_mul, C.idx_add = K.fk.idx_add, C.idx_sr = K.fk.idx_sr;
+    C.lut_max = K.lut.lut_max, C.out_scale = K.lut.out_scale, C.one = K.wk_one;
+    C.n = K.lut.n, C.n2 = K.lut.n2;
+    C.kbase = 0u - kMagic * (unsigned)(C.n2 + C.n + 1);
+    return C;
+}
+
+// lut3d for NP (1 or 2) pixels of one lane.  m*: 0x4B000000 | code (i.e. the float 2^23 + code); outputs biased ints.
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK>
+__device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, const unsigned mr[2],
+                                           const unsigned mg[2], const unsigned mb[2], unsigned ro[2], unsigned go[2], unsigned bo[2]) {
+    const int N = NSZ ? NSZ : C.n, N2 = NSZ ? NSZ * NSZ : C.n2;
+    // s = fl(fl(x / max) * scale): fma(2^23 + x, c, -2^23 c) has the exact product inside and one rounding, like the multiply
+    f2 s[3];
+    s[0] = fma2s<PK>(f2{__uint_as_float(mr[0]), __uint_as_float(mr[1])}, C.idx_mul, C.idx_add);
+    s[1] = fma2s<PK>(f2{__uint_as_float(mg[0]), __uint_as_float(mg[1])}, C.idx_mul, C.idx_add);
+    s[2] = fma2s<PK>(f2{__uint_as_float(mb[0]), __uint_as_float(mb[1])}, C.idx_mul, C.idx_add);
+    unsigned pv[3][2], dd[3][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (IDX == 2) s[c] = mul2s<PK>(s[c], C.idx_sr);
+        if (!NOMIN) s[c].x = fminf(s[c].x, C.lut_max), s[c].y = fminf(s[c].y, C.lut_max);
+        const f2 t = IDX == 2 ? addprz2s<PK>(s[c], 8388608.f, C.one) : addrz2s<PK>(s[c], 8388608.f);  // bits = 0x4B000000 | floor(s)
+        const f2 nfl = rsub2s<PK>(8388608.f, t);                                   // -floor(s), exact
+        const f2 d = IDX == 2 ? addp2<PK>(s[c], nfl, C.one) : add2<PK>(s[c], nfl);  // s - floor(s), exact
+        pv[c][0] = __float_as_uint(t.x), pv[c][1] = __float_as_uint(t.y);
+        dd[c][0] = __float_as_uint(d.x), dd[c][1] = __float_as_uint(d.y);
+    }
+    f2 cxy[2], czw[2];
+    if (INTERP == LUTR_INTERP_TRILINEAR) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const unsigned base = pv[0][p] * (unsigned)N2 + (pv[1][p] * (unsigned)N + C.kbase) + pv[2][p];
+            const float dr = __uint_as_float(dd[0][p]), dg = __uint_as_float(dd[1][p]), db = __uint_as_float(dd[2][p]);
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                v[q] = __ldg(tab + (base + (q & 4 ? N2 : 0) + (q & 2 ? N : 0) + (q & 1)));
+            // lerp(v0, v1, f) = v0 + (v1 - v0) * f along r, then g, then b
+            auto lerp = [&](f2 a, f2 b, float f) {
+                const f2 df = sub2<PK>(b, a);
+                return FMA ? fma2ss<PK>(df, f, a) : addp2<PK>(mul2s<PK>(df, f), a, C.one);
+            };
+            f2 xy[4], zw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                xy[q] = lerp(f2{v[q].x, v[q].y}, f2{v[q + 4].x, v[q + 4].y}, dr);
+                zw[q] = lerp(f2{v[q].z, v[q].w}, f2{v[q + 4].z, v[q + 4].w}, dr);
+            }
+            const f2 xy0 = lerp(xy[0], xy[2], dg), xy1 = lerp(xy[1], xy[3], dg);
+            const f2 zw0 = lerp(zw[0], zw[2], dg), zw1 = lerp(zw[1], zw[3], dg);
+            cxy[p] = lerp(xy0, xy1, db), czw[p] = lerp(zw0, zw1, db);
+        }
+    } else {
+        int mx[2], md[2], mn[2];
+        float4 v0[2], vA[2], vB[2], v1[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const unsigned base = pv[0][p] * (unsigned)N2 + (pv[1][p] * (unsigned)N + C.kbase) + pv[2][p];
+            // fractions are non-negative floats: they order like their bit patterns
+            const int ar = (int)dd[0][p], ag = (int)dd[1][p], ab = (int)dd[2][p];
+            mx[p] = __vimax3_s32(ar, ag, ab), mn[p] = __vimin3_s32(ar, ag, ab);
+            md[p] = ar ^ ag ^ ab ^ mx[p] ^ mn[p];
+            // step of the largest fraction first, of the smallest last; ties only swap vertices whose weight is exactly 0
+            const int o1 = (ar == mx[p]) ? N2 : ((ag == mx[p]) ? N : 1);
+            const int oB = (ab == mn[p]) ? N2 + N : ((ag == mn[p]) ? N2 + 1 : N + 1);
+            const float4 *p0 = tab + base;
+            v0[p] = __ldg(p0), vA[p] = __ldg(p0 + o1), vB[p] = __ldg(p0 + oB), v1[p] = __ldg(p0 + (N2 + N + 1));
+        }
+        // weights of both pixels as pairs: (1 - d1), (d1 - d2), (d2 - d3), d3
+        const f2 d1 = f2{__int_as_float(mx[0]), __int_as_float(mx[1])}, d2 = f2{__int_as_float(md[0]), __int_as_float(md[1])};
+        const f2 d3 = f2{__int_as_float(mn[0]), __int_as_float(mn[1])};
+        const f2 w0 = rsub2s<PK>(1.f, d1), w1 = sub2<PK>(d1, d2), w2 = sub2<PK>(d2, d3);
+        const float w0s[2] = {w0.x, w0.y}, w1s[2] = {w1.x, w1.y}, w2s[2] = {w2.x, w2.y}, w3s[2] = {d3.x, d3.y};
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            f2 axy = mul2s<PK>(f2{v0[p].x, v0[p].y}, w0s[p]), azw = mul2s<PK>(f2{v0[p].z, v0[p].w}, w0s[p]);
+            axy = wacc<PK, FMA>(f2{vA[p].x, vA[p].y}, w1s[p], axy, C.one), azw = wacc<PK, FMA>(f2{vA[p].z, vA[p].w}, w1s[p], azw, C.one);
+            axy = wacc<PK, FMA>(f2{vB[p].x, vB[p].y}, w2s[p], axy, C.one), azw = wacc<PK, FMA>(f2{vB[p].z, vB[p].w}, w2s[p], azw, C.one);
+            axy = wacc<PK, FMA>(f2{v1[p].x, v1[p].y}, w3s[p], axy, C.one), azw = wacc<PK, FMA>(f2{v1[p].z, v1[p].w}, w3s[p], azw, C.one);
+            cxy[p] = axy, czw[p] = azw;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        f2 fxy = mul2s<PK>(cxy[p], C.out_scale), fzw = mul2s<PK>(czw[p], C.out_scale);
+        if (CLAMP) {
+            fxy.x = fminf(fmaxf(fxy.x, 0.f), C.out_scale), fxy.y = fminf(fmaxf(fxy.y, 0.f), C.out_scale);
+            fzw.x = fminf(fmaxf(fzw.x, 0.f), C.out_scale);
+        }
+        // truncating store: + 2^23 toward zero leaves 0x4B000000 | (int)v in the bits
+        const f2 txy = addprz2s<PK>(fxy, 8388608.f, C.one), tzw = addprz2s<PK>(fzw, 8388608.f, C.one);
+        ro[p] = __float_as_uint(txy.x), go[p] = __float_as_uint(txy.y), bo[p] = __float_as_uint(tzw.x);
+    }
+}
+
+}  // namespace
+}  // namespace lutr

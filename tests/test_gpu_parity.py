@@ -135,7 +135,8 @@ def test_yuv422p10_window_edges(w, interp):
                          f"422p10 window edges w={w} {interp} frame {i}")
 
 
-@pytest.mark.parametrize("options", [dict(fast_path=0), dict(fast_path=1), dict(fast_path=1, band_rows=12), dict(fast_path=1, band_rows=26)])
+@pytest.mark.parametrize("options", [dict(fast_path=0), dict(idx_mode=1), dict(idx_mode=1, band_rows=12), dict(idx_mode=1, band_rows=26),
+                                     dict(idx_mode=3), dict(idx_mode=3, grid_ctas=2)])
 @pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
 def test_yuv420p_kernel_variants(options, interp):
     w, h = 328, 54
@@ -148,6 +149,23 @@ def test_yuv420p_kernel_variants(options, interp):
             for i, f in enumerate(frames):
                 assert_bit_exact("yuv420p", w, h, got[i], oracle_stage("yuv420p", w, h, f, L, interp=interp, **kw),
                                  f"420p {options} {lut_name} {interp} {kw} frame {i}")
+
+
+@pytest.mark.parametrize("w,h,options", [
+    (256, 12, dict()), (264, 14, dict()), (320, 38, dict(wk_unroll=2)), (384, 38, dict(wk_unroll=3)), (448, 22, dict(wk_unroll=4)),
+    (1928, 16, dict()), (640, 54, dict(grid_ctas=1)), (640, 54, dict(grid_ctas=2, wk_unroll=2)), (640, 54, dict(grid_ctas=5, wk_unroll=3)),
+    (704, 30, dict(grid_ctas=3, wk_unroll=4))])
+@pytest.mark.parametrize("interp,kw", [("tetrahedral", dict()), ("trilinear", dict(in_range="pc", norm_range="tv"))])
+def test_yuv420p_warp_windows(w, h, options, interp, kw):
+    """The 4:2:0 warp-window kernel: rows narrower / wider than its windows (shifted last window), every window width, shares
+    that span several windows and frames (tiny grids), frame heights down to the 12-row minimum, with and without the pc->tv pass."""
+    table = LUTS["look33"]().astype(np.float32)
+    frames = _frames("yuv420p", w, h, ["natural", "noise", "extremes", "noise"])
+    got = gpu_stage("yuv420p", w, h, frames, table, interp=interp, options=dict(idx_mode=3, **options), **kw)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        assert_bit_exact("yuv420p", w, h, got[i], oracle_stage("yuv420p", w, h, f, L, interp=interp, **kw),
+                         f"420p warp windows {w}x{h} {options} {interp} frame {i}")
 
 
 @pytest.mark.parametrize("lut_name", ["look33", "rand65", "ident33", "rand2"])
@@ -177,7 +195,7 @@ def test_yuv420p_band_decomposition(band_rows):
     w, h = 96, 62
     table = LUTS["rand17"]().astype(np.float32)
     frames = _frames("yuv420p", w, h, ["noise", "natural", "extremes"])
-    got = gpu_stage("yuv420p", w, h, frames, table, options={"band_rows": band_rows})
+    got = gpu_stage("yuv420p", w, h, frames, table, options={"band_rows": band_rows, "idx_mode": 1})
     L = oracle_lut(table)
     for i, f in enumerate(frames):
         assert_bit_exact("yuv420p", w, h, got[i], oracle_stage("yuv420p", w, h, f, L), f"420p band_rows={band_rows} frame {i}")

@@ -37,8 +37,12 @@ DEFAULT_VARIANTS = [
 ]
 
 
+FMT = "yuv422p10le"
+STAGE_KW = {}
+
+
 def make_stage(w, h, interp, opts):
-    st = ColourStage(w, h, "yuv422p10le", interp=interp, device=0)
+    st = ColourStage(w, h, FMT, interp=interp, device=0, **STAGE_KW)
     for k, v in opts.items():
         st.set_option(k, v)
     return st
@@ -55,7 +59,13 @@ def main():
     ap.add_argument("--content", default="natural")
     ap.add_argument("--variants", default=None, help="JSON list of option dicts")
     ap.add_argument("--skip-oracle", action="store_true")
+    ap.add_argument("--fmt", default="yuv422p10le", choices=["yuv422p10le", "yuv420p"])
+    ap.add_argument("--range-pass", action="store_true", help="full-range source, pc->tv pass in front (cfg 2)")
     args = ap.parse_args()
+    global FMT
+    FMT = args.fmt
+    if args.range_pass:
+        STAGE_KW.update(in_range="pc", norm_range="tv")
     variants = json.loads(args.variants) if args.variants else DEFAULT_VARIANTS
     dev = torch.device("cuda:0")
     table = synth.look_lut(args.lut).astype(np.float32)
@@ -64,20 +74,25 @@ def main():
     small = None
     if not args.skip_oracle:
         from oracle import oracle as O
-        sw, sh = 744, 20
-        frames = [synth.natural_frame("yuv422p10le", sw, sh, t=3), synth.noise_frame("yuv422p10le", sw, sh, seed=5)]
+        sw, sh = 744, 38
+        frames = [synth.natural_frame(FMT, sw, sh, t=3, full_range=args.range_pass), synth.noise_frame(FMT, sw, sh, seed=5)]
         L = O.OracleLut.from_table(table)
         exp = []
         for fr in frames:
-            Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(fr, "yuv422p10le", sw, sh)]
-            exp.append(synth.pack_planes(O.stage_yuv422p10(L, Y, U, V, interp=args.interp)))
+            Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(fr, FMT, sw, sh)]
+            if FMT == "yuv422p10le":
+                exp.append(synth.pack_planes(O.stage_yuv422p10(L, Y, U, V, interp=args.interp)))
+            else:
+                exp.append(synth.pack_planes(O.stage_yuv420p(L, Y, U, V, interp=args.interp, range_pass=args.range_pass)))
         small = (sw, sh, np.concatenate(frames), np.concatenate(exp))
 
     w, h, n = args.w, args.h, args.frames
-    gen = synth.natural_frame if args.content == "natural" else None
     host = []
     for t in range(n):
-        host.append(gen("yuv422p10le", w, h, t=t) if gen else synth.noise_frame("yuv422p10le", w, h, seed=100 + t))
+        if args.content == "natural":
+            host.append(synth.natural_frame(FMT, w, h, t=t % 16, full_range=args.range_pass) if t < 16 else np.roll(host[t % 16], 8 * (t // 16)))
+        else:
+            host.append(synth.noise_frame(FMT, w, h, seed=100 + t))
     src = torch.from_numpy(np.concatenate(host)).to(dev)
     fb = src.numel() // n
     ref = None
@@ -119,7 +134,8 @@ def main():
             rec["ms_per_launch"] = round(ms, 4)
             rec["fps"] = round(n / ms * 1e3, 1)
             rec["gpix_s"] = round(n * w * h / ms / 1e6, 2)
-            rec["hbm_gbs"] = round(n * w * h * 8 / ms / 1e6, 1)
+            rec["hbm_gbs"] = round(n * w * h * (8 if FMT == "yuv422p10le" else 3) / ms / 1e6, 1)
+            rec["kernel"] = st.kernel_name
             st.close()
             lut.close()
         except Exception as e:  # noqa: BLE001
