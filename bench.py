@@ -31,6 +31,10 @@ CONFIGS = {
                  frames_per_step=256, desc="1080p yuv420p full-range source, pc->tv pass, bt709 forced, 33-point, trilinear"),
     "cfg3": dict(pix_fmt="yuv422p10le", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv", norm_range="tv",
                  frames_per_step=64, desc="4K UHD yuv422p10le, 65-point look .cube, tetrahedral, bt709 tv->tv"),
+    # not a BASELINE config: pro-mode stage 1 on an 8-bit camera file (1.5 + 4 = 5.5 B/px)
+    "master8": dict(pix_fmt="yuv420p", out_pix_fmt="yuv422p10le", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv",
+                    norm_range="tv", frames_per_step=64,
+                    desc="4K UHD yuv420p 8-bit source -> 65-point look .cube, tetrahedral -> yuv422p10le master"),
     "cfg4": dict(pix_fmt="yuv422p10le", w=7680, h=4320, lut=65, interp="tetrahedral", in_range="tv", norm_range="tv",
                  frames_per_step=16, desc="8K yuv422p10le, 65-point look .cube, tetrahedral, frame-range sharded"),
 }
@@ -159,10 +163,12 @@ def run_reference(args, cfg, rank, world):
     # a step = a bounded sample: every host thread converts frames for `sample_s` seconds
     sample_s = max(1.0, min(8.0, 60.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        C.time_cpu_path(cfg["pix_fmt"], cfg["w"], cfg["h"], lut, frames, seconds=min(sample_s, 1.0), interp=cfg["interp"])
+        C.time_cpu_path(cfg["pix_fmt"], cfg["w"], cfg["h"], lut, frames, seconds=min(sample_s, 1.0), interp=cfg["interp"],
+                        out_pix_fmt=cfg.get("out_pix_fmt"))
     total_frames, total_s, legs = 0, 0.0, ""
     for _ in range(args.steps):
-        r = C.time_cpu_path(cfg["pix_fmt"], cfg["w"], cfg["h"], lut, frames, seconds=sample_s, interp=cfg["interp"])
+        r = C.time_cpu_path(cfg["pix_fmt"], cfg["w"], cfg["h"], lut, frames, seconds=sample_s, interp=cfg["interp"],
+                            out_pix_fmt=cfg.get("out_pix_fmt"))
         total_frames += r["frames"]
         total_s += r["seconds"]
         legs = r["legs"]
@@ -225,7 +231,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     F = cfg["frames_per_step"]
-    stage = ColourStage(cfg["w"], cfg["h"], cfg["pix_fmt"], in_range=cfg["in_range"], norm_range=cfg["norm_range"],
+    stage = ColourStage(cfg["w"], cfg["h"], cfg["pix_fmt"], out_pix_fmt=cfg.get("out_pix_fmt"), in_range=cfg["in_range"], norm_range=cfg["norm_range"],
                         interp=cfg["interp"], float_mode=args.float_mode, device=local_rank)
     if args.rows_per_cta:
         stage.set_option("rows_per_cta", args.rows_per_cta)
@@ -287,6 +293,8 @@ def main():
             Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(first, cfg["pix_fmt"], cfg["w"], cfg["h"])]
             if cfg["pix_fmt"] == "yuv422p10le":
                 exp = O.stage_yuv422p10(L, Y, U, V, interp=cfg["interp"])
+            elif cfg.get("out_pix_fmt") == "yuv422p10le":
+                exp = O.stage_yuv420p_to_yuv422p10(L, Y, U, V, interp=cfg["interp"])
             else:
                 exp = O.stage_yuv420p(L, Y, U, V, interp=cfg["interp"], range_pass=cfg["in_range"] == "pc" and cfg["norm_range"] == "tv")
             parity = "bit-exact" if np.array_equal(got, synth.pack_planes(exp)) else "MISMATCH"
@@ -323,7 +331,7 @@ def main():
     if rank == 0:
         fps = world * F * args.steps / (ms / 1e3)
         mpix = cfg["w"] * cfg["h"] / 1e6
-        bytes_per_frame = 2 * BYTES_PER_PIXEL[cfg["pix_fmt"]] * cfg["w"] * cfg["h"]
+        bytes_per_frame = (BYTES_PER_PIXEL[cfg["pix_fmt"]] + BYTES_PER_PIXEL[cfg.get("out_pix_fmt") or cfg["pix_fmt"]]) * cfg["w"] * cfg["h"]
         per_launch_ms = ms / args.steps
         achieved = bytes_per_frame * F / (per_launch_ms / 1e3) / 1e9
         peak, peak_src = measured_peak_hbm()
@@ -333,7 +341,7 @@ def main():
             from oracle import cpu_baseline as C
             from oracle import oracle as O
             r = C.time_cpu_path(cfg["pix_fmt"], cfg["w"], cfg["h"], O.OracleLut.from_table(table), base_frames,
-                                seconds=args.cpu_seconds, interp=cfg["interp"])
+                                seconds=args.cpu_seconds, interp=cfg["interp"], out_pix_fmt=cfg.get("out_pix_fmt"))
             cpu = {"value": round(r["fps"], 3), "unit": "frames/s", "cores": r["threads"], "kind": "port",
                    "sample": f"{r['legs']}; {r['frames']} frames of the same workload in {r['seconds']:.1f}s, "
                              f"{r['threads']} frame-parallel threads"}
@@ -344,7 +352,7 @@ def main():
             "dtype": "u16+f32" if cfg["pix_fmt"] == "yuv422p10le" else "u8+f32", "data": "synthetic",
             "gpix_per_s": round(fps * mpix / 1e3, 3),
             "config": {"workload": cfg["desc"], "content": args.content, "frames_per_step": F, "float_mode": args.float_mode, "options": args.opt,
-                       "l2": f"inputs larger than L2 ({F * bytes_per_frame / 2 / 1e6:.0f} MB read + same written per step)",
+                       "l2": f"inputs larger than L2 ({F * stage.in_frame_bytes / 1e6:.0f} MB read + {F * stage.out_frame_bytes / 1e6:.0f} MB written per step)",
                        "sharding": "contiguous frame range per GPU, no collective", "parity_spot_check": parity},
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1),
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

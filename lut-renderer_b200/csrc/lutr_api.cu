@@ -236,7 +236,7 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             const long tiles = (long)((k.w + 239) / 240) * k.h * nframes;
             warp_kernel = (k.w % 8) == 0 && k.w >= 16 && tiles < (1l << 31);
             // the 4:2:0 windows are 128 or 256 columns and never wider than the row (the last one is shifted, not clipped)
-            if (s->d.in_fmt == LUTR_PIX_YUV420P && k.w < 256) warp_kernel = false;
+            if (s->d.in_fmt == LUTR_PIX_YUV420P && k.w < 256 && s->d.out_fmt == s->d.in_fmt) warp_kernel = false;
             if (!warp_kernel) k.idx_mode = 2;
         }
         if (k.idx_mode == 2) {
@@ -314,8 +314,21 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         // 4:2:0 warp-window kernel (window width and grid are chosen in the launcher)
         k.wk_unroll = s->wk_nk_forced ? s->wk_unroll : 0;
         k.rows_per_cta = 0, k.bands = 1;
-        rc = launch_k420_warp(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
-        s->last_kernel = "k420_warp";
+        if (s->d.out_fmt == LUTR_PIX_YUV422P10LE) {
+            rc = launch_k420_warp10(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = "k420_warp10";
+        } else {
+            rc = launch_k420_warp(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = "k420_warp";
+        }
+        if (rc == LUTR_ERR_UNSUPPORTED) {
+            set_error("stage: this LUT / option combination needs a row of at least 256 columns");
+            return rc;
+        }
+    } else if (s->d.out_fmt != s->d.in_fmt) {
+        set_error("stage: yuv420p->yuv422p10le needs one LUT domain scale for all channels, width >= 256 (or 128 with a standard LUT) "
+                  "and the default kernel family");
+        return LUTR_ERR_UNSUPPORTED;
     } else {
         // bands per frame: enough CTAs to fill the device a few times over, but bands of >= 16 rows (7 halo rows each)
         int rows = s->band_rows;
@@ -544,8 +557,14 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
         set_error("stage: bad geometry or enum value");
         return LUTR_ERR_INVALID_ARG;
     }
-    if (d.in_fmt != d.out_fmt || (d.in_fmt != LUTR_PIX_YUV420P && d.in_fmt != LUTR_PIX_YUV422P10LE)) {
-        set_error("stage: only yuv420p->yuv420p and yuv422p10le->yuv422p10le are implemented");
+    const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
+    const bool to_master = d.in_fmt == LUTR_PIX_YUV420P && d.out_fmt == LUTR_PIX_YUV422P10LE;  // pro-mode master from an 8-bit source
+    if (!same_fmt && !to_master) {
+        set_error("stage: implemented are yuv420p->yuv420p, yuv422p10le->yuv422p10le and yuv420p->yuv422p10le");
+        return LUTR_ERR_UNSUPPORTED;
+    }
+    if (to_master && (d.width < 128 || d.interp == LUTR_INTERP_NEAREST)) {
+        set_error("stage: yuv420p->yuv422p10le needs width >= 128 and interp trilinear / tetrahedral");
         return LUTR_ERR_UNSUPPORTED;
     }
     if (d.out_range != LUTR_RANGE_TV) {

@@ -108,5 +108,6 @@ int launch_yuv422p10(const StageK &k, int interp, int float_mode, void *stream);
 int launch_yuv420p8(const StageK &k, int interp, int float_mode, void *stream);
 int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream);
 int launch_k420_warp(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);
+int launch_k420_warp10(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);  // yuv422p10le out
 
 }  // namespace lutr

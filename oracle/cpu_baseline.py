@@ -23,22 +23,26 @@ from . import swscale_real as S
 class CpuStage:
     """One worker's contexts for a given configuration."""
 
-    def __init__(self, pix_fmt, w, h, lut, interp="tetrahedral", in_matrix="bt709", out_matrix="bt709", use_swscale=True):
+    def __init__(self, pix_fmt, w, h, lut, interp="tetrahedral", in_matrix="bt709", out_matrix="bt709", use_swscale=True,
+                 out_pix_fmt=None):
         self.pix_fmt, self.w, self.h, self.lut, self.interp = pix_fmt, w, h, lut, interp
+        self.out_pix_fmt = out_pix_fmt or pix_fmt
         self.in_matrix, self.out_matrix = in_matrix, out_matrix
         self.use_swscale = use_swscale and S.available()
         if self.use_swscale:
             mid = "gbrp10le" if pix_fmt == "yuv422p10le" else "rgb24"
             self.fwd = S.SwsConverter(w, h, pix_fmt, mid, src_matrix=in_matrix, dst_matrix=in_matrix)
-            self.back = S.SwsConverter(w, h, mid, pix_fmt, src_matrix=out_matrix, dst_matrix=out_matrix)
+            self.back = S.SwsConverter(w, h, mid, self.out_pix_fmt, src_matrix=out_matrix, dst_matrix=out_matrix)
             self.mid = S.alloc_planes(mid, w, h)
-            self.out = S.alloc_planes(pix_fmt, w, h)
+            self.out = S.alloc_planes(self.out_pix_fmt, w, h)
 
     def run(self, planes):
         Y, U, V = planes
         if not self.use_swscale:
             if self.pix_fmt == "yuv422p10le":
                 return O.stage_yuv422p10(self.lut, Y, U, V, self.interp, self.in_matrix, False, self.out_matrix)
+            if self.out_pix_fmt == "yuv422p10le":
+                return O.stage_yuv420p_to_yuv422p10(self.lut, Y, U, V, self.interp, False, self.in_matrix, False, self.out_matrix)
             return O.stage_yuv420p(self.lut, Y, U, V, self.interp, False, self.in_matrix, False, self.out_matrix)
         self.fwd.convert([Y, U, V], self.mid)
         if self.pix_fmt == "yuv422p10le":
@@ -51,12 +55,12 @@ class CpuStage:
         return self.out
 
 
-def time_cpu_path(pix_fmt, w, h, lut, frames, seconds=12.0, threads=None, interp="tetrahedral", use_swscale=True):
+def time_cpu_path(pix_fmt, w, h, lut, frames, seconds=12.0, threads=None, interp="tetrahedral", use_swscale=True, out_pix_fmt=None):
     """Run the CPU chain frame-parallel for about `seconds`; returns dict(fps, frames, seconds, threads, legs)."""
     threads = threads or os.cpu_count() or 1
     from lut_renderer_b200 import synth  # frame splitting only (numpy views)
     plane_sets = [[np.ascontiguousarray(p) for p in synth.split_planes(f, pix_fmt, w, h)] for f in frames]
-    stages = [CpuStage(pix_fmt, w, h, lut, interp, use_swscale=use_swscale) for _ in range(threads)]
+    stages = [CpuStage(pix_fmt, w, h, lut, interp, use_swscale=use_swscale, out_pix_fmt=out_pix_fmt) for _ in range(threads)]
     for st in stages[:1]:
         st.run(plane_sets[0])  # warm-up: page in code and tables
     counts = [0] * threads

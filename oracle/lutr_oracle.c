@@ -11,7 +11,7 @@
  * FFmpeg ("ffmpeg on PATH", un-pinned: readme.md:29,115).  We pin FFmpeg 8.0.1 semantics, because a real
  * libswscale 9.1.100 / libavutil 60.8.100 from that release ships in this image (opencv_python_headless.libs):
  *
- *   PINNED   swscale legs (orc_yuv420p_to_rgb24, orc_rgb24_to_yuv420p, orc_yuv422p10_to_gbrp10,
+ *   PINNED   swscale legs (orc_yuv420p_to_rgb24, orc_rgb24_to_yuv420p, orc_rgb24_to_yuv422p10, orc_yuv422p10_to_gbrp10,
  *            orc_gbrp10_to_yuv422p10, orc_range_pc_to_tv_8): closed-form integer restatements of the code
  *            paths libswscale takes for these conversions with flags=bicubic.  They are
  *            checked bit-exactly against the real binary (oracle/swscale_real.py) in
@@ -677,6 +677,63 @@ ORC_API int orc_stage_yuv422p10(const OrcLut *l, int interp, int in_matrix, int 
     orc_lut3d_planar16(l, interp, 10, R, G, B, w, R, G, B, w, w, h);
     orc_gbrp10_to_yuv422p10(R, G, B, w, Yo, w, Uo, Vo, w / 2, w, h, out_matrix);
     free(rgb);
+    return ORC_OK;
+}
+
+/* rgb24 -> yuv422p10le: the return leg of the pro-mode master when the source is 8 bit (lut3d works on rgb24, the
+ * `format=yuv422p10le` behind it is an auto-inserted scaler; ffmpeg.py:417-433, 309-310).  PINNED against libswscale
+ * 9.1.100 (tests/test_oracle_swscale.py): rgb24ToY / rgb24ToUV_half as in orc_rgb24_to_yuv420p, no vertical filter
+ * (4:2:2 keeps every row), 15-bit intermediates 2*y14 / 2*c14 straight into the 10-bit output stage (+16) >> 5. */
+ORC_API void orc_rgb24_to_yuv422p10(const uint8_t *rgb, int rs, uint16_t *Y, int ys, uint16_t *U, uint16_t *V, int cs,
+                                    int w, int h, int matrix_id)
+{
+    int32_t c[9];
+    orc_rgb2yuv_setup(matrix_id, c);
+    const int cw = w / 2;
+    for (int y = 0; y < h; y++) {
+        const uint8_t *p = rgb + y * rs;
+        for (int x = 0; x < w; x++) {
+            int r = p[3 * x], g = p[3 * x + 1], b = p[3 * x + 2];
+            int y14 = (c[0] * r + c[1] * g + c[2] * b + (32 << 14) + (1 << 8)) >> 9;
+            Y[y * ys + x] = (uint16_t)clip_u((2 * y14 + 16) >> 5, 1023);
+        }
+        for (int i = 0; i < cw; i++) {
+            int r = p[6 * i] + p[6 * i + 3], g = p[6 * i + 1] + p[6 * i + 4], b = p[6 * i + 2] + p[6 * i + 5];
+            int u14 = (c[3] * r + c[4] * g + c[5] * b + (256 << 15) + (1 << 9)) >> 10;
+            int v14 = (c[6] * r + c[7] * g + c[8] * b + (256 << 15) + (1 << 9)) >> 10;
+            U[y * cs + i] = (uint16_t)clip_u((2 * u14 + 16) >> 5, 1023);
+            V[y * cs + i] = (uint16_t)clip_u((2 * v14 + 16) >> 5, 1023);
+        }
+    }
+}
+
+/* pro-mode stage 1 on an 8-bit 4:2:0 source: [range pass,] (auto-)scale -> rgb24, lut3d, format=yuv422p10le
+ * (ffmpeg.py:417-433 with an 8-bit VideoInfo; plan_colour_stage: in yuv420p, out yuv422p10le, rgb24 intermediate). */
+ORC_API int orc_stage_yuv420p_to_yuv422p10(const OrcLut *l, int interp, int range_pass, int in_matrix, int in_full_range,
+                                           int out_matrix, const uint8_t *Y, const uint8_t *U, const uint8_t *V, uint16_t *Yo,
+                                           uint16_t *Uo, uint16_t *Vo, int w, int h)
+{
+    size_t n = (size_t)w * h;
+    uint8_t *rgb = (uint8_t *)malloc(3 * n);
+    uint8_t *tmp = NULL;
+    if (!rgb)
+        return ORC_ENOMEM;
+    if (range_pass) {
+        tmp = (uint8_t *)malloc(n + n / 2);
+        if (!tmp) {
+            free(rgb);
+            return ORC_ENOMEM;
+        }
+        orc_range_pc_to_tv_8(Y, w, tmp, w, w, h, 0);
+        orc_range_pc_to_tv_8(U, w / 2, tmp + n, w / 2, w / 2, h / 2, 1);
+        orc_range_pc_to_tv_8(V, w / 2, tmp + n + n / 4, w / 2, w / 2, h / 2, 1);
+        Y = tmp, U = tmp + n, V = tmp + n + n / 4;
+    }
+    orc_yuv420p_to_rgb24(Y, w, U, V, w / 2, rgb, 3 * w, w, h, in_matrix, in_full_range);
+    orc_lut3d_rgb24(l, interp, rgb, 3 * w, rgb, 3 * w, w, h);
+    orc_rgb24_to_yuv422p10(rgb, 3 * w, Yo, w, Uo, Vo, w / 2, w, h, out_matrix);
+    free(rgb);
+    free(tmp);
     return ORC_OK;
 }
 

@@ -129,6 +129,13 @@ def rgb24_to_yuv420p(rgb, matrix="bt709"):
     return Y, U, V
 
 
+def rgb24_to_yuv422p10(rgb, matrix="bt709"):
+    h, w = rgb.shape[0], rgb.shape[1] // 3
+    Y, U, V = np.empty((h, w), np.uint16), np.empty((h, w // 2), np.uint16), np.empty((h, w // 2), np.uint16)
+    lib().orc_rgb24_to_yuv422p10(_p(rgb), rgb.strides[0], _p(Y), w, _p(U), _p(V), w // 2, w, h, MATRIX_ID[matrix])
+    return Y, U, V
+
+
 def yuv422p10_to_gbrp10(Y, U, V, matrix="bt709", full_range=False):
     h, w = Y.shape
     R, G, B = (np.empty((h, w), np.uint16) for _ in range(3))
@@ -178,4 +185,16 @@ def stage_yuv420p(lut, Y, U, V, interp="tetrahedral", range_pass=False, in_matri
                                 MATRIX_ID[out_matrix], _p(Y), _p(U), _p(V), _p(Yo), _p(Uo), _p(Vo), w, h)
     if r:
         raise RuntimeError(f"orc_stage_yuv420p: {r}")
+    return Yo, Uo, Vo
+
+
+def stage_yuv420p_to_yuv422p10(lut, Y, U, V, interp="tetrahedral", range_pass=False, in_matrix="bt709", in_full_range=False,
+                               out_matrix="bt709"):
+    """Pro-mode stage 1 on an 8-bit 4:2:0 source: planes uint8 (h,w),(h/2,w/2),(h/2,w/2) -> uint16 (h,w),(h,w/2),(h,w/2)."""
+    h, w = Y.shape
+    Yo, Uo, Vo = np.empty((h, w), np.uint16), np.empty((h, w // 2), np.uint16), np.empty((h, w // 2), np.uint16)
+    r = lib().orc_stage_yuv420p_to_yuv422p10(lut._h, INTERP_ID[interp], int(range_pass), MATRIX_ID[in_matrix], int(in_full_range),
+                                             MATRIX_ID[out_matrix], _p(Y), _p(U), _p(V), _p(Yo), _p(Uo), _p(Vo), w, h)
+    if r:
+        raise RuntimeError(f"orc_stage_yuv420p_to_yuv422p10: {r}")
     return Yo, Uo, Vo

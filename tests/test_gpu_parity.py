@@ -168,6 +168,26 @@ def test_yuv420p_warp_windows(w, h, options, interp, kw):
                          f"420p warp windows {w}x{h} {options} {interp} frame {i}")
 
 
+@pytest.mark.parametrize("w,h,options", [(128, 12, dict()), (256, 14, dict()), (328, 22, dict()), (448, 38, dict(wk_unroll=2)),
+                                         (640, 54, dict(grid_ctas=1, wk_unroll=3)), (704, 30, dict(grid_ctas=3, wk_unroll=4)),
+                                         (1920, 24, dict())])
+@pytest.mark.parametrize("interp,lut_name,kw", [("tetrahedral", "look65", dict()), ("tetrahedral", "rand64", dict(out_matrix="bt601")),
+                                                ("trilinear", "look33", dict(in_range="pc", norm_range="tv")),
+                                                ("tetrahedral", "wide9", dict(in_matrix="bt601"))])
+def test_yuv420p_to_yuv422p10_master(w, h, options, interp, lut_name, kw):
+    """Pro-mode stage 1 on an 8-bit 4:2:0 source (reference ffmpeg.py:417-433 with an 8-bit VideoInfo): yuv420p in, rgb24 LUT
+    domain, yuv422p10le out.  Bit-exact against the oracle chain whose rgb24->yuv422p10le leg is pinned to libswscale."""
+    table = (LUTS[lut_name]() if lut_name in LUTS else synth.random_lut(9, 4) * 1.6 - 0.3).astype(np.float32)
+    if lut_name != "look65" and w < 256:
+        pytest.skip("narrow rows are implemented for standard LUTs only")
+    frames = _frames("yuv420p", w, h, ["natural", "noise", "extremes"])
+    got = gpu_stage("yuv420p", w, h, frames, table, interp=interp, out_pix_fmt="yuv422p10le", options=options, **kw)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        exp = oracle_stage("yuv420p", w, h, f, L, interp=interp, out_pix_fmt="yuv422p10le", **kw)
+        assert_bit_exact("yuv422p10le", w, h, got[i], exp, f"420p->422p10 {w}x{h} {options} {interp} {lut_name} frame {i}")
+
+
 @pytest.mark.parametrize("lut_name", ["look33", "rand65", "ident33", "rand2"])
 @pytest.mark.parametrize("interp", ["tetrahedral", "trilinear", "nearest"])
 def test_yuv420p_interp_luts(lut_name, interp):

@@ -58,6 +58,23 @@ def test_yuv422p10_legs_match_libswscale(w, h, matrix):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 32), (64, 16), (34, 12), (1000, 18), (16, 2)])
+@pytest.mark.parametrize("matrix", ["bt709", "bt601", "bt2020"])
+def test_rgb24_to_yuv422p10_matches_libswscale(w, h, matrix):
+    """Return leg of the pro-mode master for 8-bit sources (rgb24 -> yuv422p10le): bit-exact incl. saturated colours."""
+    rng = np.random.default_rng(w * 13 + h)
+    rgb = rng.integers(0, 256, (h, 3 * w), dtype=np.uint8)
+    sel = rng.random(rgb.shape) < 0.3
+    rgb[sel] = np.where(rng.random(int(sel.sum())) < 0.5, 0, 255).astype(np.uint8)
+    ref = S.SwsConverter(w, h, "rgb24", "yuv422p10le", src_matrix=matrix, dst_matrix=matrix).convert(
+        [rgb], S.alloc_planes("yuv422p10le", w, h))
+    for a, b in zip(O.rgb24_to_yuv422p10(rgb, matrix), ref):
+        assert np.array_equal(a, b)
+    grey = np.full((h, 3 * w), 128, np.uint8)          # SURVEY B.6: grey 128 -> (504, 512, 512)
+    Y, U, V = O.rgb24_to_yuv422p10(grey)
+    assert (int(Y[0, 0]), int(U[0, 0]), int(V[0, 0])) == (504, 512, 512)
+
+
 def test_range_pass_tables_match_libswscale():
     tl, tc = O.range_tables()
     w, h = 256, 12
@@ -96,11 +113,11 @@ def test_composite_with_real_swscale_legs_equals_oracle_composite():
     """The full chain with REAL libswscale around the lut3d restatement == the all-oracle chain (what the GPU is held to)."""
     from lut_renderer_b200 import synth
     from oracle import cpu_baseline as C
-    for fmt, w, h, n in (("yuv422p10le", 640, 48, 33), ("yuv420p", 320, 36, 17)):
+    for fmt, out_fmt, w, h, n in (("yuv422p10le", None, 640, 48, 33), ("yuv420p", None, 320, 36, 17), ("yuv420p", "yuv422p10le", 320, 36, 33)):
         lut = O.OracleLut.from_table(synth.look_lut(n).astype(np.float32))
         for frame in (synth.natural_frame(fmt, w, h, 2), synth.noise_frame(fmt, w, h, 4)):
             planes = [np.ascontiguousarray(p) for p in synth.split_planes(frame, fmt, w, h)]
-            a = C.CpuStage(fmt, w, h, lut, use_swscale=True).run(planes)
-            b = C.CpuStage(fmt, w, h, lut, use_swscale=False).run(planes)
+            a = C.CpuStage(fmt, w, h, lut, use_swscale=True, out_pix_fmt=out_fmt).run(planes)
+            b = C.CpuStage(fmt, w, h, lut, use_swscale=False, out_pix_fmt=out_fmt).run(planes)
             for x, y in zip(a, b):
                 assert np.array_equal(x, y)
