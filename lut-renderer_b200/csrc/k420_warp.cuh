@@ -110,13 +110,15 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
                 __syncwarp();  // everybody is done with the previous row's staged samples
                 if (loader) {
                     *reinterpret_cast<YLoad *>(sY + YB * lane) = ny;
-                    *reinterpret_cast<CLoad *>(sU + CB * lane) = nu;
-                    *reinterpret_cast<CLoad *>(sV + CB * lane) = nv;
+                    if (!(y & 1) || y == r_first) {  // an odd row re-uses the chroma row its even neighbour staged
+                        *reinterpret_cast<CLoad *>(sU + CB * lane) = nu;
+                        *reinterpret_cast<CLoad *>(sV + CB * lane) = nv;
+                    }
                 }
                 if (loader && y < r_last) {  // prefetch the next row into registers
                     pY += K.p.in_stride[0];
                     ny = load_y(pY);
-                    nu = load_c(bU, y + 1, K.p.in_stride[1]), nv = load_c(bV, y + 1, K.p.in_stride[2]);
+                    if (y & 1) nu = load_c(bU, y + 1, K.p.in_stride[1]), nv = load_c(bV, y + 1, K.p.in_stride[2]);
                 }
                 __syncwarp();
                 const bool own_row = y >= y_begin && y < y_end;
