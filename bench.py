@@ -35,13 +35,16 @@ CONFIGS = {
     "master8": dict(pix_fmt="yuv420p", out_pix_fmt="yuv422p10le", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv",
                     norm_range="tv", frames_per_step=64,
                     desc="4K UHD yuv420p 8-bit source -> 65-point look .cube, tetrahedral -> yuv422p10le master"),
+    "master10": dict(pix_fmt="yuv420p10le", out_pix_fmt="yuv422p10le", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv",
+                     norm_range="tv", frames_per_step=64,
+                     desc="4K UHD yuv420p10le 10-bit 4:2:0 source -> 65-point look .cube, tetrahedral -> yuv422p10le master"),
     "cfg4": dict(pix_fmt="yuv422p10le", w=7680, h=4320, lut=65, interp="tetrahedral", in_range="tv", norm_range="tv",
                  frames_per_step=16, desc="8K yuv422p10le, 65-point look .cube, tetrahedral, frame-range sharded"),
 }
 # BASELINE.json configs[4]: batch queue of 64 mixed clips with per-clip LUTs, sharded by clip (handled by run_cfg5)
 CFG5 = dict(clips=64, frames_per_clip=24,
             desc="batch queue of 64 mixed 1080p yuv420p (33-point) / 4K yuv422p10le (65-point) clips, per-clip .cube LUTs, sharded by clip")
-BYTES_PER_PIXEL = {"yuv420p": 1.5, "yuv422p10le": 4.0}  # per side; algorithmic bytes/frame = (in + out) * w * h
+BYTES_PER_PIXEL = {"yuv420p": 1.5, "yuv422p10le": 4.0, "yuv420p10le": 3.0}  # per side; algorithmic bytes/frame = (in + out) * w * h
 
 
 def measured_peak_hbm():
@@ -424,6 +427,8 @@ def main():
             Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(first, cfg["pix_fmt"], cfg["w"], cfg["h"])]
             if cfg["pix_fmt"] == "yuv422p10le":
                 exp = O.stage_yuv422p10(L, Y, U, V, interp=cfg["interp"])
+            elif cfg["pix_fmt"] == "yuv420p10le":
+                exp = O.stage_yuv420p10_to_yuv422p10(L, Y, U, V, interp=cfg["interp"])
             elif cfg.get("out_pix_fmt") == "yuv422p10le":
                 exp = O.stage_yuv420p_to_yuv422p10(L, Y, U, V, interp=cfg["interp"])
             else:
@@ -435,7 +440,7 @@ def main():
     # end to end: the call a user makes (ColourStage.run_host) on pinned host frames, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        Fe = max(1, min(F, 16 if cfg["pix_fmt"] == "yuv422p10le" else 64))
+        Fe = max(1, min(F, 16 if "10" in cfg["pix_fmt"] else 64))
         pin_in = stage.ctx.pinned_buffer(Fe * stage.in_frame_bytes)
         pin_out = stage.ctx.pinned_buffer(Fe * stage.out_frame_bytes)
         for i in range(Fe):
@@ -480,7 +485,7 @@ def main():
             "metric": "4K 10-bit frames/s" if args.config == "cfg3" else f"{args.config} frames/s",
             "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(per_launch_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u16+f32" if cfg["pix_fmt"] == "yuv422p10le" else "u8+f32", "data": "synthetic",
+            "dtype": "u16+f32" if "10" in cfg["pix_fmt"] else "u8+f32", "data": "synthetic",
             "gpix_per_s": round(fps * mpix / 1e3, 3),
             "config": {"workload": cfg["desc"], "content": args.content, "frames_per_step": F, "float_mode": args.float_mode, "options": args.opt,
                        "l2": f"inputs larger than L2 ({F * stage.in_frame_bytes / 1e6:.0f} MB read + {F * stage.out_frame_bytes / 1e6:.0f} MB written per step)",

@@ -23,33 +23,6 @@ namespace lutr {
 
 namespace {
 
-constexpr int kWin = 256;        // luma columns computed per window
-constexpr int kOut = 240;        // luma columns whose outputs the window owns (8 halo columns on each side)
-constexpr int kWarps = 8;        // warps per CTA (a CTA is only a container)
-constexpr int kCBias = 4096;     // the 15-bit upsampled chroma is stored biased so that it is an unsigned 16-bit field
-
-__device__ __forceinline__ uint2 ldg_s8(const void *p) {
-    uint2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint4 ldg_s16(const void *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void stg_s8(void *p, uint2 v) {
-    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
-}
-__device__ __forceinline__ void stg_s16(void *p, uint4 v) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// The per-column words live in 4-word chunks; chunk c sits at c ^ bit3(c).  With that swizzle the 128-bit accesses of passes A
-// and C (8 lanes x 16 B, chunks 2 apart) and the 32-bit accesses of pass B (32 consecutive columns) are all bank-conflict free.
-__device__ __forceinline__ int swz_chunk(int c) { return c ^ ((c >> 3) & 1); }
-__device__ __forceinline__ int swz_slot(int j) { return (swz_chunk(j >> 2) << 2) | (j & 3); }
-
 template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR>
 __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
     __shared__ __align__(16) unsigned s_all[kWarps][kWin + kWin / 2];

@@ -46,6 +46,7 @@ struct lutr_stage {
     // host pipeline: NBUF device slots of `chunk` frames each
     static constexpr int NBUF = 3;
     int chunk = 0;
+    int chunk_mb = 64;     // host pipeline: input megabytes per slot (option "host_chunk_mb")
     uint8_t *dev_in[NBUF] = {nullptr, nullptr, nullptr}, *dev_out[NBUF] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_in[NBUF]{}, ev_done[NBUF]{}, ev_out[NBUF]{};
     bool ev_ok = false;
@@ -80,9 +81,9 @@ namespace {
         }                                                                                  \
     } while (0)
 
-int plane_rows(int fmt, int h, int p) { return (fmt == LUTR_PIX_YUV420P && p > 0) ? h / 2 : h; }
+int plane_rows(int fmt, int h, int p) { return ((fmt == LUTR_PIX_YUV420P || fmt == LUTR_PIX_YUV420P10LE) && p > 0) ? h / 2 : h; }
 int plane_row_bytes(int fmt, int w, int p) {
-    const int bps = fmt == LUTR_PIX_YUV422P10LE ? 2 : 1;
+    const int bps = fmt == LUTR_PIX_YUV420P ? 1 : 2;
     return (p == 0 ? w : w / 2) * bps;
 }
 size_t frame_bytes(int fmt, int w, int h) {
@@ -145,7 +146,7 @@ int check_planes(const lutr_stage *s, const lutr_planes *pl, int fmt, int nframe
             return LUTR_ERR_INVALID_ARG;
         }
         // vector accesses: one 8-pixel group of Y (16 B at 10 bit, 8 B at 8 bit), half of that for a chroma group
-        const int ya = fmt == LUTR_PIX_YUV422P10LE ? 16 : 8;
+        const int ya = fmt == LUTR_PIX_YUV420P ? 8 : 16;
         const int a = p == 0 ? ya : ya / 2;
         if (((uintptr_t)pl->data[p] % a) || (pl->stride[p] % a) || (nframes > 1 && (pl->frame_step % ya))) {
             set_error("%s plane %d: pointer and stride must be %d-byte aligned, frame_step %d-byte aligned", what, p, a, ya);
@@ -241,7 +242,7 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         }
         if (k.idx_mode == 2) {
             // TMA-staged rows need 16-byte aligned bulk copies (row starts and row lengths) and the ring must fit in shared memory
-            bool ok = s->d.in_fmt == LUTR_PIX_YUV422P10LE && (k.w % 16) == 0 && (in->frame_step % 16) == 0;
+            bool ok = s->d.in_fmt == LUTR_PIX_YUV422P10LE && (k.w % 16) == 0 && (in->frame_step % 16) == 0;  // (never 4:2:0 10-bit)
             for (int p = 0; p < 3; ++p) ok = ok && ((uintptr_t)in->data[p] % 16) == 0 && (in->stride[p] % 16) == 0;
             const size_t smem = (size_t)8 * k.w + (size_t)2 * (k.w + 8) * 4 + 16;
             if (smem * (size_t)s->min_blocks > 200 * 1024) ok = false;
@@ -296,7 +297,17 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         }
     }
     k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : k.min_blocks * s->ctx->sm_count;
-    if (s->d.in_fmt == LUTR_PIX_YUV422P10LE) {
+    if (s->d.in_fmt == LUTR_PIX_YUV420P10LE) {
+        if (!warp_kernel) {
+            set_error("stage: yuv420p10le->yuv422p10le needs one LUT domain scale for all channels and the default kernel family");
+            return LUTR_ERR_UNSUPPORTED;
+        }
+        k.rows_per_cta = 0, k.bands = 1;
+        k.grid_ctas = s->grid_ctas;
+        k.min_blocks = s->wk_minb;
+        rc = launch_k420p10_warp(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+        s->last_kernel = "k420p10_warp";
+    } else if (s->d.in_fmt == LUTR_PIX_YUV422P10LE) {
         k.rows_per_cta = s->rows_per_cta > 0 ? s->rows_per_cta : 1;
         if (warp_kernel) {
             // rows per CTA unit (8 warps, interleaved rows): as many as still leave every CTA of the persistent grid >= 32 units
@@ -559,8 +570,15 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
     }
     const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
     const bool to_master = d.in_fmt == LUTR_PIX_YUV420P && d.out_fmt == LUTR_PIX_YUV422P10LE;  // pro-mode master from an 8-bit source
-    if (!same_fmt && !to_master) {
-        set_error("stage: implemented are yuv420p->yuv420p, yuv422p10le->yuv422p10le and yuv420p->yuv422p10le");
+    const bool to_master10 = d.in_fmt == LUTR_PIX_YUV420P10LE && d.out_fmt == LUTR_PIX_YUV422P10LE;  // ... from a 10-bit 4:2:0 source
+    if (!same_fmt && !to_master && !to_master10) {
+        set_error("stage: implemented are yuv420p->yuv420p, yuv422p10le->yuv422p10le, yuv420p->yuv422p10le and yuv420p10le->yuv422p10le");
+        return LUTR_ERR_UNSUPPORTED;
+    }
+    if (to_master10 && (d.interp == LUTR_INTERP_NEAREST || (d.height % 2) || d.height < 14 ||
+                        (d.in_range == LUTR_RANGE_PC && d.norm_range == LUTR_RANGE_TV))) {
+        // height: the vertical chroma filter model is pinned to libswscale for even heights >= 14 (tests/test_oracle_swscale.py)
+        set_error("stage: yuv420p10le->yuv422p10le needs an even height >= 14, interp trilinear / tetrahedral and no pc->tv pass");
         return LUTR_ERR_UNSUPPORTED;
     }
     if (to_master && (d.width < 128 || d.interp == LUTR_INTERP_NEAREST)) {
@@ -594,7 +612,7 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
     if (!s) return LUTR_ERR_NOMEM;
     s->ctx = ctx;
     s->d = d;
-    s->depth = d.in_fmt == LUTR_PIX_YUV422P10LE ? 10 : 8;
+    s->depth = d.in_fmt == LUTR_PIX_YUV420P ? 8 : 10;
     // YUV->RGB sees the range left by the normalisation pass
     make_yuv2rgb(d.in_matrix, d.norm_range == LUTR_RANGE_PC, s->f);
     make_rgb2yuv(d.out_matrix, s->b);
@@ -679,7 +697,7 @@ int lutr_stage_run_host(lutr_stage *s, const lutr_lut *lut, const void *in_host,
     // chunk = frames per pipeline slot: ~64 MB of input per slot keeps PCIe busy without hoarding HBM
     if (s->chunk == 0) {
         size_t per = s->in_bytes > s->out_bytes ? s->in_bytes : s->out_bytes;
-        int chunk = (int)((64u << 20) / per);
+        int chunk = (int)(((size_t)s->chunk_mb << 20) / per);
         if (chunk < 1) chunk = 1;
         if (chunk > 64) chunk = 64;
         for (int i = 0; i < lutr_stage::NBUF; ++i) {
@@ -741,7 +759,14 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     else if (!std::strcmp(name, "fast_path")) s->use_fast = value;
     else if (!std::strcmp(name, "grid_ctas")) s->grid_ctas = value;
     else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value < 0 || value > 3 ? 1 : value;
-    else if (!std::strcmp(name, "wk_pk")) s->wk_pk = value;
+    else if (!std::strcmp(name, "host_chunk_mb")) {
+        if (value < 1 || value > 4096) {
+            set_error("host_chunk_mb must be in [1, 4096]");
+            return LUTR_ERR_INVALID_ARG;
+        }
+        if (s->chunk) free_host_pipeline(s);
+        s->chunk_mb = value;
+    } else if (!std::strcmp(name, "wk_pk")) s->wk_pk = value;
     else if (!std::strcmp(name, "wk_unroll")) s->wk_unroll = value, s->wk_nk_forced = 1;
     else if (!std::strcmp(name, "wk_minb")) s->wk_minb = value >= 2 && value <= 4 ? value : 3;
     else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value >= 2 && value <= 4 ? value : 3;

@@ -108,6 +108,7 @@ int launch_yuv422p10(const StageK &k, int interp, int float_mode, void *stream);
 int launch_yuv420p8(const StageK &k, int interp, int float_mode, void *stream);
 int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream);
 int launch_k420_warp(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);
+int launch_k420p10_warp(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);  // yuv420p10le in
 int launch_k420_warp10(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);  // yuv422p10le out
 
 }  // namespace lutr

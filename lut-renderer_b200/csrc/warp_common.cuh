@@ -12,6 +12,35 @@ namespace {
 
 constexpr unsigned kMagic = 0x4B000000u;  // bits of 8388608.0f
 
+// geometry of the 4:2:2-output warp-window kernels (k422_warp.cu, k420p10_warp.cu)
+constexpr int kWin = 256;        // luma columns computed per window
+constexpr int kOut = 240;        // luma columns whose outputs the window owns (8 halo columns on each side)
+constexpr int kWarps = 8;        // warps per CTA (a CTA is only a container)
+constexpr int kCBias = 4096;     // the 15-bit upsampled chroma is stored biased so that it is an unsigned 16-bit field
+
+__device__ __forceinline__ uint2 ldg_s8(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_s16(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_s8(void *p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_s16(void *p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// The per-column words live in 4-word chunks; chunk c sits at c ^ bit3(c).  With that swizzle the 128-bit accesses of passes A
+// and C (8 lanes x 16 B, chunks 2 apart) and the 32-bit accesses of pass B (32 consecutive columns) are all bank-conflict free.
+__device__ __forceinline__ int swz_chunk(int c) { return c ^ ((c >> 3) & 1); }
+__device__ __forceinline__ int swz_slot(int j) { return (swz_chunk(j >> 2) << 2) | (j & 3); }
+
+
 // ---- two-wide float helpers: PK = packed f32x2 instructions, otherwise two scalar instructions with the same rounding ----
 struct f2 {
     float x, y;

@@ -19,6 +19,8 @@ def plane_shapes(pix_fmt: str, w: int, h: int):
         return [(h, w), (h // 2, w // 2), (h // 2, w // 2)], np.uint8
     if pix_fmt == "yuv422p10le":
         return [(h, w), (h, w // 2), (h, w // 2)], np.dtype("<u2")
+    if pix_fmt == "yuv420p10le":
+        return [(h, w), (h // 2, w // 2), (h // 2, w // 2)], np.dtype("<u2")
     raise ValueError(pix_fmt)
 
 
@@ -72,14 +74,14 @@ def _rgb_to_yuv_planes(rgb: np.ndarray, pix_fmt: str, full_range: bool):
     yf = _KR * r + (1 - _KR - _KB) * g + _KB * b
     uf = (b - yf) / (2 * (1 - _KB))
     vf = (r - yf) / (2 * (1 - _KR))
-    depth = 10 if pix_fmt == "yuv422p10le" else 8
+    depth = 10 if "10" in pix_fmt else 8
     s = 1 << (depth - 8)
     if full_range:
         mx = (1 << depth) - 1
         Y, U, V = yf * mx, uf * mx + 128 * s, vf * mx + 128 * s
     else:
         Y, U, V = (16 + 219 * yf) * s, (128 + 224 * uf) * s, (128 + 224 * vf) * s
-    if pix_fmt == "yuv420p":
+    if pix_fmt in ("yuv420p", "yuv420p10le"):
         U = U.reshape(h // 2, 2, w // 2, 2).mean(axis=(1, 3))
         V = V.reshape(h // 2, 2, w // 2, 2).mean(axis=(1, 3))
     else:
@@ -99,14 +101,14 @@ def noise_frame(pix_fmt: str, w: int, h: int, seed: int = 1) -> np.ndarray:
     """Content class B ("worst-case gather"): iid uniform over the full code range of every sample."""
     rng = np.random.default_rng(seed)
     shapes, dt = plane_shapes(pix_fmt, w, h)
-    hi = 1024 if pix_fmt == "yuv422p10le" else 256
+    hi = 1024 if "10" in pix_fmt else 256
     return pack_planes([rng.integers(0, hi, size=s, dtype=np.uint16).astype(dt) for s in shapes])
 
 
 def ramp_frame(pix_fmt: str, w: int, h: int) -> np.ndarray:
     """Content class C: horizontal luma ramp, vertical chroma ramps (hits every code value and the edges)."""
     shapes, dt = plane_shapes(pix_fmt, w, h)
-    hi = 1023 if pix_fmt == "yuv422p10le" else 255
+    hi = 1023 if "10" in pix_fmt else 255
     Y = np.broadcast_to(np.linspace(0, hi, shapes[0][1]).round()[None, :], shapes[0]).astype(dt)
     U = np.broadcast_to(np.linspace(0, hi, shapes[1][0]).round()[:, None], shapes[1]).astype(dt)
     V = np.broadcast_to(np.linspace(hi, 0, shapes[2][1]).round()[None, :], shapes[2]).astype(dt)

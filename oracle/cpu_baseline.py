@@ -30,7 +30,7 @@ class CpuStage:
         self.in_matrix, self.out_matrix = in_matrix, out_matrix
         self.use_swscale = use_swscale and S.available()
         if self.use_swscale:
-            mid = "gbrp10le" if pix_fmt == "yuv422p10le" else "rgb24"
+            mid = "gbrp10le" if "10" in pix_fmt else "rgb24"
             self.fwd = S.SwsConverter(w, h, pix_fmt, mid, src_matrix=in_matrix, dst_matrix=in_matrix)
             self.back = S.SwsConverter(w, h, mid, self.out_pix_fmt, src_matrix=out_matrix, dst_matrix=out_matrix)
             self.mid = S.alloc_planes(mid, w, h)
@@ -41,11 +41,13 @@ class CpuStage:
         if not self.use_swscale:
             if self.pix_fmt == "yuv422p10le":
                 return O.stage_yuv422p10(self.lut, Y, U, V, self.interp, self.in_matrix, False, self.out_matrix)
+            if self.pix_fmt == "yuv420p10le":
+                return O.stage_yuv420p10_to_yuv422p10(self.lut, Y, U, V, self.interp, self.in_matrix, False, self.out_matrix)
             if self.out_pix_fmt == "yuv422p10le":
                 return O.stage_yuv420p_to_yuv422p10(self.lut, Y, U, V, self.interp, False, self.in_matrix, False, self.out_matrix)
             return O.stage_yuv420p(self.lut, Y, U, V, self.interp, False, self.in_matrix, False, self.out_matrix)
         self.fwd.convert([Y, U, V], self.mid)
-        if self.pix_fmt == "yuv422p10le":
+        if "10" in self.pix_fmt:
             g, b, r = self.mid
             r2, g2, b2 = O.lut3d_planar16(self.lut, r, g, b, 10, self.interp)
             self.back.convert([g2, b2, r2], self.out)

@@ -314,6 +314,73 @@ ORC_API void orc_yuv422p10_to_gbrp10(const uint16_t *Y, int ys, const uint16_t *
     }
 }
 
+/* yuv420p10le -> gbrp10le: forward leg of the pro-mode master for 10-bit 4:2:0 sources (ffmpeg.py:417-433; the intermediate
+ * is gbrp10le as for 4:2:2).  PINNED against libswscale 9.1.100 (tests/test_oracle_swscale.py).  swscale scales chroma
+ * horizontally first (the 4-tap filter of chroma_up_422, to 15 bits, per chroma row) and vertically inside the output function
+ * (yuv2gbrp_full_X): Q12 bicubic taps at the quarter phases over 4 chroma rows, the two top luma rows with edge-normalised taps:
+ *   y = 0:              4432 C15[0] - 336 C15[1]
+ *   y = 2:              959 C15[0] + 3473 C15[1] - 336 C15[2]
+ *   y = 2j   (others):  -115 C15[j-2] + 985 C15[j-1] + 3572 C15[j] - 346 C15[j+1]
+ *   y = 2j+1:           -346 C15[j-1] + 3572 C15[j] + 985 C15[j+1] - 115 C15[j+2]      (row indices clamped to the plane)
+ * then u17 = ((1<<9) - (128<<19) + sum) >> 10 and the matrix / clip of orc_yuv422p10_to_gbrp10. */
+static void vtaps_420(int y, int ch, int rows[4], int taps[4])
+{
+    const int j = y >> 1;
+    if (y & 1) {
+        rows[0] = j - 1, rows[1] = j, rows[2] = j + 1, rows[3] = j + 2;
+        taps[0] = -346, taps[1] = 3572, taps[2] = 985, taps[3] = -115;
+    } else {
+        rows[0] = j - 2, rows[1] = j - 1, rows[2] = j, rows[3] = j + 1;
+        if (y == 0)
+            taps[0] = 0, taps[1] = 0, taps[2] = 4432, taps[3] = -336;
+        else if (y == 2)
+            taps[0] = 0, taps[1] = 959, taps[2] = 3473, taps[3] = -336;
+        else
+            taps[0] = -115, taps[1] = 985, taps[2] = 3572, taps[3] = -346;
+    }
+    for (int k = 0; k < 4; k++)
+        rows[k] = clampi(rows[k], 0, ch - 1);
+}
+
+ORC_API void orc_yuv420p10_to_gbrp10(const uint16_t *Y, int ys, const uint16_t *U, const uint16_t *V, int cs, uint16_t *R,
+                                     uint16_t *G, uint16_t *B, int os, int w, int h, int matrix_id, int full_range)
+{
+    /* strides in elements */
+    OrcYuv2Rgb t;
+    orc_yuv2rgb_setup(matrix_id, full_range, &t);
+    const int cw = w / 2, ch = h / 2;
+    /* horizontally upsampled 15-bit chroma of every chroma row */
+    int32_t *hu = (int32_t *)malloc(sizeof(int32_t) * (size_t)w * ch);
+    int32_t *hv = (int32_t *)malloc(sizeof(int32_t) * (size_t)w * ch);
+    for (int j = 0; j < ch; j++)
+        for (int x = 0; x < w; x++) {
+            hu[(size_t)j * w + x] = chroma_up_422(U + j * cs, cw, x);
+            hv[(size_t)j * w + x] = chroma_up_422(V + j * cs, cw, x);
+        }
+    for (int y = 0; y < h; y++) {
+        int rows[4], taps[4];
+        vtaps_420(y, ch, rows, taps);
+        for (int x = 0; x < w; x++) {
+            int64_t su = 0, sv = 0;
+            for (int k = 0; k < 4; k++) {
+                su += (int64_t)hu[(size_t)rows[k] * w + x] * taps[k];
+                sv += (int64_t)hv[(size_t)rows[k] * w + x] * taps[k];
+            }
+            int32_t u17 = (int32_t)(((1 << 9) - (128 << 19) + su) >> 10);
+            int32_t v17 = (int32_t)(((1 << 9) - (128 << 19) + sv) >> 10);
+            uint32_t yy = (uint32_t)(Y[y * ys + x] * 128 - t.yOff10) * (uint32_t)t.yC + (1u << 19);
+            uint32_t r = yy + (uint32_t)v17 * (uint32_t)t.vr;
+            uint32_t g = yy + (uint32_t)v17 * (uint32_t)t.vg + (uint32_t)u17 * (uint32_t)t.ug;
+            uint32_t b = yy + (uint32_t)u17 * (uint32_t)t.ub;
+            R[y * os + x] = clip30_shift20((int32_t)r);
+            G[y * os + x] = clip30_shift20((int32_t)g);
+            B[y * os + x] = clip30_shift20((int32_t)b);
+        }
+    }
+    free(hu);
+    free(hv);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* B.4  gbrp10le -> yuv422p10le   (planar_rgb16_to_y/uv + 8-tap horizontal bicubic + yuv2plane1_10)   */
 /* ------------------------------------------------------------------------------------------------ */
@@ -674,6 +741,23 @@ ORC_API int orc_stage_yuv422p10(const OrcLut *l, int interp, int in_matrix, int 
         return ORC_ENOMEM;
     uint16_t *R = rgb, *G = rgb + n, *B = rgb + 2 * n;
     orc_yuv422p10_to_gbrp10(Y, w, U, V, w / 2, R, G, B, w, w, h, in_matrix, in_full_range);
+    orc_lut3d_planar16(l, interp, 10, R, G, B, w, R, G, B, w, w, h);
+    orc_gbrp10_to_yuv422p10(R, G, B, w, Yo, w, Uo, Vo, w / 2, w, h, out_matrix);
+    free(rgb);
+    return ORC_OK;
+}
+
+/* pro-mode stage 1 on a 10-bit 4:2:0 source: (auto-)scale -> gbrp10le, lut3d, format=yuv422p10le (ffmpeg.py:417-433). */
+ORC_API int orc_stage_yuv420p10_to_yuv422p10(const OrcLut *l, int interp, int in_matrix, int in_full_range, int out_matrix,
+                                             const uint16_t *Y, const uint16_t *U, const uint16_t *V, uint16_t *Yo, uint16_t *Uo,
+                                             uint16_t *Vo, int w, int h)
+{
+    size_t n = (size_t)w * h;
+    uint16_t *rgb = (uint16_t *)malloc(3 * n * sizeof(uint16_t));
+    if (!rgb)
+        return ORC_ENOMEM;
+    uint16_t *R = rgb, *G = rgb + n, *B = rgb + 2 * n;
+    orc_yuv420p10_to_gbrp10(Y, w, U, V, w / 2, R, G, B, w, w, h, in_matrix, in_full_range);
     orc_lut3d_planar16(l, interp, 10, R, G, B, w, R, G, B, w, w, h);
     orc_gbrp10_to_yuv422p10(R, G, B, w, Yo, w, Uo, Vo, w / 2, w, h, out_matrix);
     free(rgb);

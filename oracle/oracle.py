@@ -144,6 +144,14 @@ def yuv422p10_to_gbrp10(Y, U, V, matrix="bt709", full_range=False):
     return R, G, B
 
 
+def yuv420p10_to_gbrp10(Y, U, V, matrix="bt709", full_range=False):
+    h, w = Y.shape
+    R, G, B = (np.empty((h, w), np.uint16) for _ in range(3))
+    lib().orc_yuv420p10_to_gbrp10(_p(Y), w, _p(U), _p(V), w // 2, _p(R), _p(G), _p(B), w, w, h, MATRIX_ID[matrix],
+                                  int(full_range))
+    return R, G, B
+
+
 def gbrp10_to_yuv422p10(R, G, B, matrix="bt709"):
     h, w = R.shape
     Y, U, V = np.empty((h, w), np.uint16), np.empty((h, w // 2), np.uint16), np.empty((h, w // 2), np.uint16)
@@ -197,4 +205,15 @@ def stage_yuv420p_to_yuv422p10(lut, Y, U, V, interp="tetrahedral", range_pass=Fa
                                              MATRIX_ID[out_matrix], _p(Y), _p(U), _p(V), _p(Yo), _p(Uo), _p(Vo), w, h)
     if r:
         raise RuntimeError(f"orc_stage_yuv420p_to_yuv422p10: {r}")
+    return Yo, Uo, Vo
+
+
+def stage_yuv420p10_to_yuv422p10(lut, Y, U, V, interp="tetrahedral", in_matrix="bt709", in_full_range=False, out_matrix="bt709"):
+    """Pro-mode stage 1 on a 10-bit 4:2:0 source: planes uint16 (h,w),(h/2,w/2),(h/2,w/2) -> uint16 (h,w),(h,w/2),(h,w/2)."""
+    h, w = Y.shape
+    Yo, Uo, Vo = np.empty((h, w), np.uint16), np.empty((h, w // 2), np.uint16), np.empty((h, w // 2), np.uint16)
+    r = lib().orc_stage_yuv420p10_to_yuv422p10(lut._h, INTERP_ID[interp], MATRIX_ID[in_matrix], int(in_full_range),
+                                               MATRIX_ID[out_matrix], _p(Y), _p(U), _p(V), _p(Yo), _p(Uo), _p(Vo), w, h)
+    if r:
+        raise RuntimeError(f"orc_stage_yuv420p10_to_yuv422p10: {r}")
     return Yo, Uo, Vo

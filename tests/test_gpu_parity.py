@@ -34,7 +34,7 @@ def _frames(pix_fmt, w, h, kinds):
             out.append(synth.ramp_frame(pix_fmt, w, h))
         elif k == "extremes":
             f = synth.noise_frame(pix_fmt, w, h, seed=12)
-            hi = 1023 if pix_fmt == "yuv422p10le" else 255
+            hi = 1023 if "10" in pix_fmt else 255
             v = f.view(np.dtype("<u2") if hi > 255 else np.uint8)
             sel = np.random.default_rng(13).random(v.shape) < 0.5
             v[sel] = np.where(np.random.default_rng(14).random(int(sel.sum())) < 0.5, 0, hi).astype(v.dtype)
@@ -186,6 +186,23 @@ def test_yuv420p_to_yuv422p10_master(w, h, options, interp, lut_name, kw):
     for i, f in enumerate(frames):
         exp = oracle_stage("yuv420p", w, h, f, L, interp=interp, out_pix_fmt="yuv422p10le", **kw)
         assert_bit_exact("yuv422p10le", w, h, got[i], exp, f"420p->422p10 {w}x{h} {options} {interp} {lut_name} frame {i}")
+
+
+@pytest.mark.parametrize("w,h,options", [(16, 14, dict()), (240, 16, dict()), (248, 18, dict()), (488, 30, dict(grid_ctas=1)),
+                                         (728, 54, dict(grid_ctas=2)), (1928, 22, dict()), (656, 38, dict(grid_ctas=7))])
+@pytest.mark.parametrize("interp,lut_name,kw", [("tetrahedral", "look65", dict()), ("tetrahedral", "rand64", dict(out_matrix="bt601")),
+                                                ("trilinear", "look33", dict(in_matrix="bt2020", out_matrix="bt2020")),
+                                                ("tetrahedral", "wide9", dict(in_range="pc", norm_range="pc"))])
+def test_yuv420p10_to_yuv422p10_master(w, h, options, interp, lut_name, kw):
+    """Pro-mode stage 1 on a 10-bit 4:2:0 source: separable 4x4-tap chroma upsampling (edge tap sets on the top rows / left
+    columns), gbrp10le LUT domain, yuv422p10le out.  Shares that start anywhere in a window column (tiny grids), several frames."""
+    table = (LUTS[lut_name]() if lut_name in LUTS else synth.random_lut(9, 4) * 1.6 - 0.3).astype(np.float32)
+    frames = _frames("yuv420p10le", w, h, ["natural", "noise", "extremes", "ramp"])
+    got = gpu_stage("yuv420p10le", w, h, frames, table, interp=interp, out_pix_fmt="yuv422p10le", options=options, **kw)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        exp = oracle_stage("yuv420p10le", w, h, f, L, interp=interp, **kw)
+        assert_bit_exact("yuv422p10le", w, h, got[i], exp, f"420p10->422p10 {w}x{h} {options} {interp} {lut_name} frame {i}")
 
 
 @pytest.mark.parametrize("lut_name", ["look33", "rand65", "ident33", "rand2"])

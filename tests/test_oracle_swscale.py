@@ -75,6 +75,23 @@ def test_rgb24_to_yuv422p10_matches_libswscale(w, h, matrix):
     assert (int(Y[0, 0]), int(U[0, 0]), int(V[0, 0])) == (504, 512, 512)
 
 
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 24), (64, 32), (34, 14), (1000, 18), (16, 16), (22, 30), (48, 20)])
+@pytest.mark.parametrize("matrix", ["bt709", "bt601", "bt2020"])
+def test_yuv420p10_to_gbrp10_matches_libswscale(w, h, matrix):
+    """Forward leg of the master for 10-bit 4:2:0 sources: separable 4-tap horizontal x 4-tap vertical chroma upsampling with
+    the edge-normalised tap sets on the two top rows / left columns; full code range, both source ranges.  Valid domain found by
+    probing the binary: even heights >= 14 (shorter frames make swscale shrink its vertical filters differently)."""
+    rng = np.random.default_rng(w * 7 + h)
+    for full in (0, 1):
+        Y = rng.integers(0, 1024, (h, w), dtype=np.uint16)
+        U = rng.integers(0, 1024, (h // 2, w // 2), dtype=np.uint16)
+        V = rng.integers(0, 1024, (h // 2, w // 2), dtype=np.uint16)
+        g, b, r = S.SwsConverter(w, h, "yuv420p10le", "gbrp10le", src_range=full, src_matrix=matrix, dst_matrix=matrix).convert(
+            [Y, U, V], S.alloc_planes("gbrp10le", w, h))
+        R, G, B = O.yuv420p10_to_gbrp10(Y, U, V, matrix, full)
+        assert np.array_equal(R, r) and np.array_equal(G, g) and np.array_equal(B, b)
+
+
 def test_range_pass_tables_match_libswscale():
     tl, tc = O.range_tables()
     w, h = 256, 12
@@ -113,7 +130,8 @@ def test_composite_with_real_swscale_legs_equals_oracle_composite():
     """The full chain with REAL libswscale around the lut3d restatement == the all-oracle chain (what the GPU is held to)."""
     from lut_renderer_b200 import synth
     from oracle import cpu_baseline as C
-    for fmt, out_fmt, w, h, n in (("yuv422p10le", None, 640, 48, 33), ("yuv420p", None, 320, 36, 17), ("yuv420p", "yuv422p10le", 320, 36, 33)):
+    for fmt, out_fmt, w, h, n in (("yuv422p10le", None, 640, 48, 33), ("yuv420p", None, 320, 36, 17), ("yuv420p", "yuv422p10le", 320, 36, 33),
+                                  ("yuv420p10le", "yuv422p10le", 320, 36, 33)):
         lut = O.OracleLut.from_table(synth.look_lut(n).astype(np.float32))
         for frame in (synth.natural_frame(fmt, w, h, 2), synth.noise_frame(fmt, w, h, 4)):
             planes = [np.ascontiguousarray(p) for p in synth.split_planes(frame, fmt, w, h)]
