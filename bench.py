@@ -38,6 +38,12 @@ CONFIGS = {
     "master10": dict(pix_fmt="yuv420p10le", out_pix_fmt="yuv422p10le", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv",
                      norm_range="tv", frames_per_step=64,
                      desc="4K UHD yuv420p10le 10-bit 4:2:0 source -> 65-point look .cube, tetrahedral -> yuv422p10le master"),
+    "hevc10": dict(pix_fmt="yuv420p10le", out_pix_fmt="yuv420p10le", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv",
+                   norm_range="tv", frames_per_step=64,
+                   desc="4K UHD yuv420p10le source -> 65-point look .cube, tetrahedral -> yuv420p10le (libx265 preserve)"),
+    "hevc10_422": dict(pix_fmt="yuv422p10le", out_pix_fmt="yuv420p10le", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv",
+                       norm_range="tv", frames_per_step=64,
+                       desc="4K UHD yuv422p10le source -> 65-point look .cube, tetrahedral -> yuv420p10le (libx265 preserve)"),
     "cfg4": dict(pix_fmt="yuv422p10le", w=7680, h=4320, lut=65, interp="tetrahedral", in_range="tv", norm_range="tv",
                  frames_per_step=16, desc="8K yuv422p10le, 65-point look .cube, tetrahedral, frame-range sharded"),
 }
@@ -184,7 +190,7 @@ def run_reference(args, cfg, rank, world):
         "impl": "reference", "metric": "4K 10-bit frames/s" if args.config == "cfg3" else f"{args.config} frames/s",
         "value": round(fps, 3), "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 * total_s / max(1, args.steps), 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u16+f32" if cfg["pix_fmt"] == "yuv422p10le" else "u8+f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u16+f32" if "10" in cfg["pix_fmt"] else "u8+f32", "data": "synthetic",
         "gpix_per_s": round(fps * mpix / 1e3, 4),
         "config": {"workload": cfg["desc"], "content": args.content, "frames_per_step": round(total_frames / max(1, args.steps), 1)},
         "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
@@ -425,10 +431,9 @@ def main():
             first = src[:stage.in_frame_bytes].cpu().numpy()
             L = O.OracleLut.from_table(table)
             Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(first, cfg["pix_fmt"], cfg["w"], cfg["h"])]
-            if cfg["pix_fmt"] == "yuv422p10le":
-                exp = O.stage_yuv422p10(L, Y, U, V, interp=cfg["interp"])
-            elif cfg["pix_fmt"] == "yuv420p10le":
-                exp = O.stage_yuv420p10_to_yuv422p10(L, Y, U, V, interp=cfg["interp"])
+            if "10" in cfg["pix_fmt"]:
+                exp = O.stage_10bit(L, Y, U, V, in_420=cfg["pix_fmt"] == "yuv420p10le",
+                                    out_420=cfg.get("out_pix_fmt", cfg["pix_fmt"]) == "yuv420p10le", interp=cfg["interp"])
             elif cfg.get("out_pix_fmt") == "yuv422p10le":
                 exp = O.stage_yuv420p_to_yuv422p10(L, Y, U, V, interp=cfg["interp"])
             else:

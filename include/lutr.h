@@ -53,7 +53,7 @@ typedef enum lutr_status {
 typedef enum lutr_pix_fmt {
     LUTR_PIX_YUV420P = 0,     /* 8-bit 4:2:0 planar  (fast-delivery default / force_8bit)                 */
     LUTR_PIX_YUV422P10LE = 1, /* 10-bit 4:2:2 planar in LE u16 (pro-mode ProRes master, ffmpeg.py:417-433) */
-    LUTR_PIX_YUV420P10LE = 2  /* 10-bit 4:2:0 planar in LE u16 (input only: 10-bit camera / HEVC sources of the master stage) */
+    LUTR_PIX_YUV420P10LE = 2  /* 10-bit 4:2:0 planar in LE u16 (10-bit camera / HEVC sources; libx265 'preserve' output, ffmpeg.py:297-298) */
 } lutr_pix_fmt;
 
 typedef enum lutr_range { LUTR_RANGE_TV = 0, LUTR_RANGE_PC = 1 } lutr_range;

@@ -297,16 +297,17 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         }
     }
     k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : k.min_blocks * s->ctx->sm_count;
-    if (s->d.in_fmt == LUTR_PIX_YUV420P10LE) {
+    if (s->d.in_fmt == LUTR_PIX_YUV420P10LE || s->d.out_fmt == LUTR_PIX_YUV420P10LE) {
         if (!warp_kernel) {
-            set_error("stage: yuv420p10le->yuv422p10le needs one LUT domain scale for all channels and the default kernel family");
+            set_error("stage: 10-bit 4:2:0 input / output needs one LUT domain scale for all channels and the default kernel family");
             return LUTR_ERR_UNSUPPORTED;
         }
+        const bool in420 = s->d.in_fmt == LUTR_PIX_YUV420P10LE, out420 = s->d.out_fmt == LUTR_PIX_YUV420P10LE;
         k.rows_per_cta = 0, k.bands = 1;
         k.grid_ctas = s->grid_ctas;
         k.min_blocks = s->wk_minb;
-        rc = launch_k420p10_warp(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
-        s->last_kernel = "k420p10_warp";
+        rc = launch_k10_warp(k, in420, out420, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+        s->last_kernel = !out420 ? "k10_warp<420,422>" : (in420 ? "k10_warp<420,420>" : "k10_warp<422,420>");
     } else if (s->d.in_fmt == LUTR_PIX_YUV422P10LE) {
         k.rows_per_cta = s->rows_per_cta > 0 ? s->rows_per_cta : 1;
         if (warp_kernel) {
@@ -570,15 +571,18 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
     }
     const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
     const bool to_master = d.in_fmt == LUTR_PIX_YUV420P && d.out_fmt == LUTR_PIX_YUV422P10LE;  // pro-mode master from an 8-bit source
-    const bool to_master10 = d.in_fmt == LUTR_PIX_YUV420P10LE && d.out_fmt == LUTR_PIX_YUV422P10LE;  // ... from a 10-bit 4:2:0 source
-    if (!same_fmt && !to_master && !to_master10) {
-        set_error("stage: implemented are yuv420p->yuv420p, yuv422p10le->yuv422p10le, yuv420p->yuv422p10le and yuv420p10le->yuv422p10le");
+    // 10-bit chains whose rows are walked in order (k10_warp.cu): 4:2:0 source -> master, and the 10-bit 4:2:0 outputs
+    const bool in10 = d.in_fmt == LUTR_PIX_YUV420P10LE || d.in_fmt == LUTR_PIX_YUV422P10LE;
+    const bool ordered10 = in10 && (d.in_fmt == LUTR_PIX_YUV420P10LE || d.out_fmt == LUTR_PIX_YUV420P10LE) &&
+                           (d.out_fmt == LUTR_PIX_YUV422P10LE || d.out_fmt == LUTR_PIX_YUV420P10LE);
+    if (!same_fmt && !to_master && !ordered10) {
+        set_error("stage: implemented are yuv420p->yuv420p, yuv420p->yuv422p10le and yuv420p10le|yuv422p10le->yuv420p10le|yuv422p10le");
         return LUTR_ERR_UNSUPPORTED;
     }
-    if (to_master10 && (d.interp == LUTR_INTERP_NEAREST || (d.height % 2) || d.height < 14 ||
-                        (d.in_range == LUTR_RANGE_PC && d.norm_range == LUTR_RANGE_TV))) {
-        // height: the vertical chroma filter model is pinned to libswscale for even heights >= 14 (tests/test_oracle_swscale.py)
-        set_error("stage: yuv420p10le->yuv422p10le needs an even height >= 14, interp trilinear / tetrahedral and no pc->tv pass");
+    if (ordered10 && (d.interp == LUTR_INTERP_NEAREST || (d.height % 2) || d.height < 14 ||
+                      (d.in_range == LUTR_RANGE_PC && d.norm_range == LUTR_RANGE_TV))) {
+        // height: the vertical chroma filter models are pinned to libswscale for even heights >= 14 (tests/test_oracle_swscale.py)
+        set_error("stage: 10-bit 4:2:0 input / output needs an even height >= 14, interp trilinear / tetrahedral and no pc->tv pass");
         return LUTR_ERR_UNSUPPORTED;
     }
     if (to_master && (d.width < 128 || d.interp == LUTR_INTERP_NEAREST)) {

@@ -108,7 +108,8 @@ int launch_yuv422p10(const StageK &k, int interp, int float_mode, void *stream);
 int launch_yuv420p8(const StageK &k, int interp, int float_mode, void *stream);
 int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream);
 int launch_k420_warp(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);
-int launch_k420p10_warp(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);  // yuv420p10le in
+// 10-bit chains with a 4:2:0 side (k10_warp.cu): yuv420p10le in and / or yuv420p10le out
+int launch_k10_warp(const StageK &k, bool in420, bool out420, int interp, int float_mode, bool grid_forced, void *stream);
 int launch_k420_warp10(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);  // yuv422p10le out
 
 }  // namespace lutr

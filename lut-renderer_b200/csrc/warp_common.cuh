@@ -12,7 +12,7 @@ namespace {
 
 constexpr unsigned kMagic = 0x4B000000u;  // bits of 8388608.0f
 
-// geometry of the 4:2:2-output warp-window kernels (k422_warp.cu, k420p10_warp.cu)
+// geometry of the 4:2:2-output warp-window kernels (k422_warp.cu, k10_warp.cu)
 constexpr int kWin = 256;        // luma columns computed per window
 constexpr int kOut = 240;        // luma columns whose outputs the window owns (8 halo columns on each side)
 constexpr int kWarps = 8;        // warps per CTA (a CTA is only a container)

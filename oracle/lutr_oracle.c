@@ -426,6 +426,63 @@ ORC_API void orc_gbrp10_to_yuv422p10(const uint16_t *R, const uint16_t *G, const
     free(v14);
 }
 
+/* gbrp10le -> yuv420p10le: return leg when the encoder wants 10-bit 4:2:0 (libx265 / hevc_videotoolbox with
+ * bit_depth_policy preserve, ffmpeg.py:297-298, 309-310).  PINNED against libswscale 9.1.100
+ * (tests/test_oracle_swscale.py).  Luma and the per-column chroma terms as orc_gbrp10_to_yuv422p10; swscale then scales
+ * chroma horizontally (the 8-tap Q14 filter, to 15 bits with the 32767 clip, per luma row) and vertically in
+ * yuv2planeX_10: Q12 taps {-58,-172,492,1786,1786,492,-172,-58} over luma rows 2j-3 .. 2j+4 (row indices clamped to the
+ * frame = swscale's edge-folded coefficients, the accumulation is exact), out = clip10((sum + (1 << 16)) >> 17). */
+ORC_API void orc_gbrp10_to_yuv420p10(const uint16_t *R, const uint16_t *G, const uint16_t *B, int is, uint16_t *Y, int ys,
+                                     uint16_t *U, uint16_t *V, int cs, int w, int h, int matrix_id)
+{
+    int32_t c[9];
+    orc_rgb2yuv_setup(matrix_id, c);
+    const int cw = w / 2, ch = h / 2;
+    int32_t *u14 = (int32_t *)malloc(sizeof(int32_t) * (size_t)w);
+    int32_t *v14 = (int32_t *)malloc(sizeof(int32_t) * (size_t)w);
+    int32_t *hu = (int32_t *)malloc(sizeof(int32_t) * (size_t)cw * h); /* 15-bit horizontally decimated rows */
+    int32_t *hv = (int32_t *)malloc(sizeof(int32_t) * (size_t)cw * h);
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            int r = R[y * is + x], g = G[y * is + x], b = B[y * is + x];
+            int y14 = (c[0] * r + c[1] * g + c[2] * b + (16 << 17) + (1 << 10)) >> 11;
+            int y15 = 2 * y14;
+            if (y15 > 32767)
+                y15 = 32767;
+            Y[y * ys + x] = (uint16_t)clip_u((y15 + 16) >> 5, 1023);
+            u14[x] = (c[3] * r + c[4] * g + c[5] * b + (128 << 17) + (1 << 10)) >> 11;
+            v14[x] = (c[6] * r + c[7] * g + c[8] * b + (128 << 17) + (1 << 10)) >> 11;
+        }
+        for (int i = 0; i < cw; i++) {
+            int64_t su = 0, sv = 0;
+            for (int k = 0; k < 8; k++) {
+                int x = clampi(2 * i - 3 + k, 0, w - 1);
+                su += (int64_t)u14[x] * k_h422_taps[k];
+                sv += (int64_t)v14[x] * k_h422_taps[k];
+            }
+            su >>= 13;
+            sv >>= 13;
+            hu[(size_t)y * cw + i] = su > 32767 ? 32767 : (int32_t)su;
+            hv[(size_t)y * cw + i] = sv > 32767 ? 32767 : (int32_t)sv;
+        }
+    }
+    for (int j = 0; j < ch; j++)
+        for (int i = 0; i < cw; i++) {
+            int64_t su = 1 << 16, sv = 1 << 16;
+            for (int k = 0; k < 8; k++) {
+                int y = clampi(2 * j - 3 + k, 0, h - 1);
+                su += (int64_t)hu[(size_t)y * cw + i] * k_v420_taps[k];
+                sv += (int64_t)hv[(size_t)y * cw + i] * k_v420_taps[k];
+            }
+            U[j * cs + i] = (uint16_t)clip_u((int)(su >> 17), 1023);
+            V[j * cs + i] = (uint16_t)clip_u((int)(sv >> 17), 1023);
+        }
+    free(u14);
+    free(v14);
+    free(hu);
+    free(hv);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* vf_lut3d restatement: .cube parser                                                                */
 /* ------------------------------------------------------------------------------------------------ */
@@ -848,5 +905,29 @@ ORC_API int orc_stage_yuv420p(const OrcLut *l, int interp, int range_pass, int i
     orc_rgb24_to_yuv420p(rgb, 3 * w, Yo, w, Uo, Vo, w / 2, w, h, out_matrix);
     free(rgb);
     free(tmp);
+    return ORC_OK;
+}
+
+/* 10-bit chains through gbrp10le with either chroma layout on each side: in_420 / out_420 select yuv420p10le, otherwise
+ * yuv422p10le.  out 4:2:0 = libx265 / hevc_videotoolbox "preserve" outputs (ffmpeg.py:297-298), out 4:2:2 = pro-mode master. */
+ORC_API int orc_stage_10bit(const OrcLut *l, int interp, int in_420, int out_420, int in_matrix, int in_full_range,
+                            int out_matrix, const uint16_t *Y, const uint16_t *U, const uint16_t *V, uint16_t *Yo, uint16_t *Uo,
+                            uint16_t *Vo, int w, int h)
+{
+    size_t n = (size_t)w * h;
+    uint16_t *rgb = (uint16_t *)malloc(3 * n * sizeof(uint16_t));
+    if (!rgb)
+        return ORC_ENOMEM;
+    uint16_t *R = rgb, *G = rgb + n, *B = rgb + 2 * n;
+    if (in_420)
+        orc_yuv420p10_to_gbrp10(Y, w, U, V, w / 2, R, G, B, w, w, h, in_matrix, in_full_range);
+    else
+        orc_yuv422p10_to_gbrp10(Y, w, U, V, w / 2, R, G, B, w, w, h, in_matrix, in_full_range);
+    orc_lut3d_planar16(l, interp, 10, R, G, B, w, R, G, B, w, w, h);
+    if (out_420)
+        orc_gbrp10_to_yuv420p10(R, G, B, w, Yo, w, Uo, Vo, w / 2, w, h, out_matrix);
+    else
+        orc_gbrp10_to_yuv422p10(R, G, B, w, Yo, w, Uo, Vo, w / 2, w, h, out_matrix);
+    free(rgb);
     return ORC_OK;
 }

@@ -159,6 +159,13 @@ def gbrp10_to_yuv422p10(R, G, B, matrix="bt709"):
     return Y, U, V
 
 
+def gbrp10_to_yuv420p10(R, G, B, matrix="bt709"):
+    h, w = R.shape
+    Y, U, V = np.empty((h, w), np.uint16), np.empty((h // 2, w // 2), np.uint16), np.empty((h // 2, w // 2), np.uint16)
+    lib().orc_gbrp10_to_yuv420p10(_p(R), _p(G), _p(B), w, _p(Y), w, _p(U), _p(V), w // 2, w, h, MATRIX_ID[matrix])
+    return Y, U, V
+
+
 def lut3d_rgb24(lut: OracleLut, rgb, interp="tetrahedral"):
     h, w = rgb.shape[0], rgb.shape[1] // 3
     out = np.empty_like(rgb)
@@ -216,4 +223,17 @@ def stage_yuv420p10_to_yuv422p10(lut, Y, U, V, interp="tetrahedral", in_matrix="
                                                MATRIX_ID[out_matrix], _p(Y), _p(U), _p(V), _p(Yo), _p(Uo), _p(Vo), w, h)
     if r:
         raise RuntimeError(f"orc_stage_yuv420p10_to_yuv422p10: {r}")
+    return Yo, Uo, Vo
+
+
+def stage_10bit(lut, Y, U, V, in_420=False, out_420=False, interp="tetrahedral", in_matrix="bt709", in_full_range=False,
+                out_matrix="bt709"):
+    """10-bit chain through gbrp10le; chroma planes uint16 (h/2 or h, w/2) on each side as in_420 / out_420 say."""
+    h, w = Y.shape
+    co = (h // 2 if out_420 else h, w // 2)
+    Yo, Uo, Vo = np.empty((h, w), np.uint16), np.empty(co, np.uint16), np.empty(co, np.uint16)
+    r = lib().orc_stage_10bit(lut._h, INTERP_ID[interp], int(in_420), int(out_420), MATRIX_ID[in_matrix], int(in_full_range),
+                              MATRIX_ID[out_matrix], _p(Y), _p(U), _p(V), _p(Yo), _p(Uo), _p(Vo), w, h)
+    if r:
+        raise RuntimeError(f"orc_stage_10bit: {r}")
     return Yo, Uo, Vo

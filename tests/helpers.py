@@ -15,12 +15,9 @@ def oracle_stage(pix_fmt, w, h, frame, lut, interp="tetrahedral", in_matrix="bt7
     if pix_fmt == "yuv420p" and out_pix_fmt == "yuv422p10le":
         out = O.stage_yuv420p_to_yuv422p10(lut, Y, U, V, interp=interp, range_pass=(in_range == "pc" and norm_range == "tv"),
                                            in_matrix=in_matrix, in_full_range=(norm_range == "pc"), out_matrix=out_matrix)
-    elif pix_fmt == "yuv420p10le":
-        out = O.stage_yuv420p10_to_yuv422p10(lut, Y, U, V, interp=interp, in_matrix=in_matrix, in_full_range=(norm_range == "pc"),
-                                             out_matrix=out_matrix)
-    elif pix_fmt == "yuv422p10le":
-        out = O.stage_yuv422p10(lut, Y, U, V, interp=interp, in_matrix=in_matrix, in_full_range=(norm_range == "pc"),
-                                out_matrix=out_matrix)
+    elif pix_fmt in ("yuv420p10le", "yuv422p10le"):
+        out = O.stage_10bit(lut, Y, U, V, in_420=(pix_fmt == "yuv420p10le"), out_420=((out_pix_fmt or pix_fmt) == "yuv420p10le"),
+                            interp=interp, in_matrix=in_matrix, in_full_range=(norm_range == "pc"), out_matrix=out_matrix)
     else:
         out = O.stage_yuv420p(lut, Y, U, V, interp=interp, range_pass=(in_range == "pc" and norm_range == "tv"),
                               in_matrix=in_matrix, in_full_range=(norm_range == "pc"), out_matrix=out_matrix)

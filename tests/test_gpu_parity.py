@@ -201,8 +201,40 @@ def test_yuv420p10_to_yuv422p10_master(w, h, options, interp, lut_name, kw):
     got = gpu_stage("yuv420p10le", w, h, frames, table, interp=interp, out_pix_fmt="yuv422p10le", options=options, **kw)
     L = oracle_lut(table)
     for i, f in enumerate(frames):
-        exp = oracle_stage("yuv420p10le", w, h, f, L, interp=interp, **kw)
+        exp = oracle_stage("yuv420p10le", w, h, f, L, interp=interp, out_pix_fmt="yuv422p10le", **kw)
         assert_bit_exact("yuv422p10le", w, h, got[i], exp, f"420p10->422p10 {w}x{h} {options} {interp} {lut_name} frame {i}")
+
+
+@pytest.mark.parametrize("pix_fmt", ["yuv420p10le", "yuv422p10le"])
+@pytest.mark.parametrize("w,h,options", [(16, 14, dict()), (240, 16, dict()), (248, 18, dict()), (488, 30, dict(grid_ctas=1)),
+                                         (728, 54, dict(grid_ctas=2)), (1928, 22, dict()), (656, 38, dict(grid_ctas=7)),
+                                         (512, 64, dict(grid_ctas=5))])
+@pytest.mark.parametrize("interp,lut_name,kw", [("tetrahedral", "look65", dict()), ("tetrahedral", "rand64", dict(out_matrix="bt601")),
+                                                ("trilinear", "look33", dict(in_matrix="bt2020", out_matrix="bt2020")),
+                                                ("tetrahedral", "wide9", dict(in_range="pc", norm_range="pc"))])
+def test_10bit_to_yuv420p10(pix_fmt, w, h, options, interp, lut_name, kw):
+    """10-bit 4:2:0 OUTPUT (libx265 / hevc_videotoolbox 'preserve', reference ffmpeg.py:297-298) from 10-bit 4:2:0 and 4:2:2 sources:
+    8-tap horizontal + 8-tap vertical chroma decimation with the output-row ring; shares that start anywhere in a window column
+    (tiny grids: halo rows above / below a share), frame top / bottom clamping, several frames."""
+    table = (LUTS[lut_name]() if lut_name in LUTS else synth.random_lut(9, 4) * 1.6 - 0.3).astype(np.float32)
+    frames = _frames(pix_fmt, w, h, ["natural", "noise", "extremes", "ramp"])
+    got = gpu_stage(pix_fmt, w, h, frames, table, interp=interp, out_pix_fmt="yuv420p10le", options=options, **kw)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        exp = oracle_stage(pix_fmt, w, h, f, L, interp=interp, out_pix_fmt="yuv420p10le", **kw)
+        assert_bit_exact("yuv420p10le", w, h, got[i], exp, f"{pix_fmt}->420p10 {w}x{h} {options} {interp} {lut_name} frame {i}")
+
+
+@pytest.mark.parametrize("pix_fmt", ["yuv420p10le", "yuv422p10le"])
+def test_full_4k_frame_to_yuv420p10(pix_fmt):
+    w, h = 3840, 2160
+    table = synth.look_lut(65).astype(np.float32)
+    frames = [synth.natural_frame(pix_fmt, w, h, t=5), synth.noise_frame(pix_fmt, w, h, seed=3)]
+    got = gpu_stage(pix_fmt, w, h, frames, table, out_pix_fmt="yuv420p10le")
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        exp = oracle_stage(pix_fmt, w, h, f, L, out_pix_fmt="yuv420p10le")
+        assert_bit_exact("yuv420p10le", w, h, got[i], exp, f"{pix_fmt}->420p10 4K frame {i}")
 
 
 @pytest.mark.parametrize("lut_name", ["look33", "rand65", "ident33", "rand2"])

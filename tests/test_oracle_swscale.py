@@ -92,6 +92,23 @@ def test_yuv420p10_to_gbrp10_matches_libswscale(w, h, matrix):
         assert np.array_equal(R, r) and np.array_equal(G, g) and np.array_equal(B, b)
 
 
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 24), (64, 32), (34, 14), (1000, 18), (16, 16), (22, 30), (48, 20)])
+@pytest.mark.parametrize("matrix", ["bt709", "bt601", "bt2020"])
+def test_gbrp10_to_yuv420p10_matches_libswscale(w, h, matrix):
+    """Return leg for 10-bit 4:2:0 outputs (libx265 preserve, ffmpeg.py:297-298): 8-tap horizontal then 8-tap vertical chroma
+    decimation, exact accumulation; random full-code-range RGB with saturated patches (hits the 32767 clip of the 15-bit rows)."""
+    rng = np.random.default_rng(w * 11 + h)
+    R, G, B = (rng.integers(0, 1024, (h, w), dtype=np.uint16) for _ in range(3))
+    for P in (R, G, B):
+        sel = rng.random(P.shape) < 0.3
+        P[sel] = np.where(rng.random(int(sel.sum())) < 0.5, 0, 1023).astype(np.uint16)
+    R[: h // 2, : w // 2], G[: h // 2, : w // 2], B[: h // 2, : w // 2] = 0, 0, 1023     # flat saturated blue block: max U
+    ref = S.SwsConverter(w, h, "gbrp10le", "yuv420p10le", src_matrix=matrix, dst_matrix=matrix).convert(
+        [G, B, R], S.alloc_planes("yuv420p10le", w, h))
+    for a, b in zip(O.gbrp10_to_yuv420p10(R, G, B, matrix), ref):
+        assert np.array_equal(a, b)
+
+
 def test_range_pass_tables_match_libswscale():
     tl, tc = O.range_tables()
     w, h = 256, 12
@@ -131,7 +148,8 @@ def test_composite_with_real_swscale_legs_equals_oracle_composite():
     from lut_renderer_b200 import synth
     from oracle import cpu_baseline as C
     for fmt, out_fmt, w, h, n in (("yuv422p10le", None, 640, 48, 33), ("yuv420p", None, 320, 36, 17), ("yuv420p", "yuv422p10le", 320, 36, 33),
-                                  ("yuv420p10le", "yuv422p10le", 320, 36, 33)):
+                                  ("yuv420p10le", "yuv422p10le", 320, 36, 33), ("yuv420p10le", "yuv420p10le", 320, 36, 33),
+                                  ("yuv422p10le", "yuv420p10le", 328, 30, 17)):
         lut = O.OracleLut.from_table(synth.look_lut(n).astype(np.float32))
         for frame in (synth.natural_frame(fmt, w, h, 2), synth.noise_frame(fmt, w, h, 4)):
             planes = [np.ascontiguousarray(p) for p in synth.split_planes(frame, fmt, w, h)]
