@@ -636,7 +636,7 @@ typedef struct rgbvec {
     float r, g, b;
 } rgbvec;
 
-enum { ORC_INTERP_NEAREST = 0, ORC_INTERP_TRILINEAR = 1, ORC_INTERP_TETRAHEDRAL = 2 };
+enum { ORC_INTERP_NEAREST = 0, ORC_INTERP_TRILINEAR = 1, ORC_INTERP_TETRAHEDRAL = 2, ORC_INTERP_PYRAMID = 3, ORC_INTERP_PRISM = 4 };
 
 #define LUTAT(l, ri, gi, bi) (*(const rgbvec *)((l)->rgb + 3 * ((size_t)(ri) * (l)->size * (l)->size + (gi) * (l)->size + (bi))))
 #define PREV(x) ((int)(x))
@@ -716,6 +716,64 @@ static inline rgbvec interp_tetrahedral(const OrcLut *l, const rgbvec *s)
     }
 }
 
+/* interp=pyramid / interp=prism (accepted by the reference's whitelist, ffmpeg.py:243; not offered by its GUI).  Restated from
+ * upstream vf_lut3d.c interp_pyramid / interp_prism: one expression per channel, evaluated left to right in float32. */
+#define PYR(ch, A1, A0, B1, B0, C1, C0, D3, D2, D1, D0, f1, f2, f3, g1, g2)                                                   \
+    (c000.ch + (A1.ch - A0.ch) * (f1) + (B1.ch - B0.ch) * (f2) + (C1.ch - C0.ch) * (f3) +                                      \
+     (D3.ch - D2.ch - D1.ch + D0.ch) * (g1) * (g2))
+
+static inline rgbvec interp_pyramid(const OrcLut *l, const rgbvec *s)
+{
+    const int p[3] = {PREV(s->r), PREV(s->g), PREV(s->b)};
+    const int n[3] = {NEXT(s->r, l), NEXT(s->g, l), NEXT(s->b, l)};
+    const rgbvec d = {s->r - p[0], s->g - p[1], s->b - p[2]};
+    const rgbvec c000 = LUTAT(l, p[0], p[1], p[2]), c111 = LUTAT(l, n[0], n[1], n[2]);
+    rgbvec c;
+    if (d.g > d.r && d.b > d.r) {
+        const rgbvec c001 = LUTAT(l, p[0], p[1], n[2]), c010 = LUTAT(l, p[0], n[1], p[2]), c011 = LUTAT(l, p[0], n[1], n[2]);
+        c.r = PYR(r, c111, c011, c010, c000, c001, c000, c011, c001, c010, c000, d.r, d.g, d.b, d.g, d.b);
+        c.g = PYR(g, c111, c011, c010, c000, c001, c000, c011, c001, c010, c000, d.r, d.g, d.b, d.g, d.b);
+        c.b = PYR(b, c111, c011, c010, c000, c001, c000, c011, c001, c010, c000, d.r, d.g, d.b, d.g, d.b);
+    } else if (d.r > d.g && d.b > d.g) {
+        const rgbvec c001 = LUTAT(l, p[0], p[1], n[2]), c100 = LUTAT(l, n[0], p[1], p[2]), c101 = LUTAT(l, n[0], p[1], n[2]);
+        c.r = PYR(r, c100, c000, c111, c101, c001, c000, c101, c001, c100, c000, d.r, d.g, d.b, d.r, d.b);
+        c.g = PYR(g, c100, c000, c111, c101, c001, c000, c101, c001, c100, c000, d.r, d.g, d.b, d.r, d.b);
+        c.b = PYR(b, c100, c000, c111, c101, c001, c000, c101, c001, c100, c000, d.r, d.g, d.b, d.r, d.b);
+    } else {
+        const rgbvec c010 = LUTAT(l, p[0], n[1], p[2]), c110 = LUTAT(l, n[0], n[1], p[2]), c100 = LUTAT(l, n[0], p[1], p[2]);
+        c.r = PYR(r, c100, c000, c010, c000, c111, c110, c110, c100, c010, c000, d.r, d.g, d.b, d.r, d.g);
+        c.g = PYR(g, c100, c000, c010, c000, c111, c110, c110, c100, c010, c000, d.r, d.g, d.b, d.r, d.g);
+        c.b = PYR(b, c100, c000, c010, c000, c111, c110, c110, c100, c010, c000, d.r, d.g, d.b, d.r, d.g);
+    }
+    return c;
+}
+
+#define PRISM(ch, A1, A0, B1, B0, D3, D2, D1, D0, E3, E2, E1, E0)                                                              \
+    (c000.ch + (A1.ch - A0.ch) * d.b + (B1.ch - B0.ch) * d.r + (c010.ch - c000.ch) * d.g +                                    \
+     (D3.ch - D2.ch - D1.ch + D0.ch) * d.b * d.g + (E3.ch - E2.ch - E1.ch + E0.ch) * d.r * d.g)
+
+static inline rgbvec interp_prism(const OrcLut *l, const rgbvec *s)
+{
+    const int p[3] = {PREV(s->r), PREV(s->g), PREV(s->b)};
+    const int n[3] = {NEXT(s->r, l), NEXT(s->g, l), NEXT(s->b, l)};
+    const rgbvec d = {s->r - p[0], s->g - p[1], s->b - p[2]};
+    const rgbvec c000 = LUTAT(l, p[0], p[1], p[2]), c010 = LUTAT(l, p[0], n[1], p[2]);
+    const rgbvec c101 = LUTAT(l, n[0], p[1], n[2]), c111 = LUTAT(l, n[0], n[1], n[2]);
+    rgbvec c;
+    if (d.b > d.r) {
+        const rgbvec c001 = LUTAT(l, p[0], p[1], n[2]), c011 = LUTAT(l, p[0], n[1], n[2]);
+        c.r = PRISM(r, c001, c000, c101, c001, c000, c010, c001, c011, c001, c011, c101, c111);
+        c.g = PRISM(g, c001, c000, c101, c001, c000, c010, c001, c011, c001, c011, c101, c111);
+        c.b = PRISM(b, c001, c000, c101, c001, c000, c010, c001, c011, c001, c011, c101, c111);
+    } else {
+        const rgbvec c110 = LUTAT(l, n[0], n[1], p[2]), c100 = LUTAT(l, n[0], p[1], p[2]);
+        c.r = PRISM(r, c101, c100, c100, c000, c100, c110, c101, c111, c000, c010, c100, c110);
+        c.g = PRISM(g, c101, c100, c100, c000, c100, c110, c101, c111, c000, c010, c100, c110);
+        c.b = PRISM(b, c101, c100, c100, c000, c100, c110, c101, c111, c000, c010, c100, c110);
+    }
+    return c;
+}
+
 static inline rgbvec interp_any(const OrcLut *l, int interp, const rgbvec *s)
 {
     switch (interp) {
@@ -723,6 +781,10 @@ static inline rgbvec interp_any(const OrcLut *l, int interp, const rgbvec *s)
         return interp_nearest(l, s);
     case ORC_INTERP_TRILINEAR:
         return interp_trilinear(l, s);
+    case ORC_INTERP_PYRAMID:
+        return interp_pyramid(l, s);
+    case ORC_INTERP_PRISM:
+        return interp_prism(l, s);
     default:
         return interp_tetrahedral(l, s);
     }
@@ -928,6 +990,267 @@ ORC_API int orc_stage_10bit(const OrcLut *l, int interp, int in_420, int out_420
         orc_gbrp10_to_yuv420p10(R, G, B, w, Yo, w, Uo, Vo, w / 2, w, h, out_matrix);
     else
         orc_gbrp10_to_yuv422p10(R, G, B, w, Yo, w, Uo, Vo, w / 2, w, h, out_matrix);
+    free(rgb);
+    return ORC_OK;
+}
+
+/* ================================================================================================ */
+/* The whole format matrix of the operator (reference ffmpeg.py:137-143 intermediate formats, :287-310 output formats,  */
+/* :213-223 output range): generic legs and one composite, orc_stage_any.  Every leg below is PINNED against libswscale   */
+/* 9.1.100 in tests/test_oracle_swscale.py (test_any_*).                                                                  */
+/* ================================================================================================ */
+
+/* pixel format ids (= lutr_pix_fmt in include/lutr.h) */
+enum { ORC_PIX_YUV420P = 0, ORC_PIX_YUV422P10 = 1, ORC_PIX_YUV420P10 = 2, ORC_PIX_YUV422P = 3, ORC_PIX_YUV444P = 4,
+       ORC_PIX_YUV444P10 = 5, ORC_PIX_COUNT = 6 };
+
+ORC_API int orc_pix_depth(int fmt) { return (fmt == ORC_PIX_YUV422P10 || fmt == ORC_PIX_YUV420P10 || fmt == ORC_PIX_YUV444P10) ? 10 : 8; }
+/* log2 chroma subsampling: sx | sy << 1 */
+ORC_API int orc_pix_sub(int fmt)
+{
+    switch (fmt) {
+    case ORC_PIX_YUV420P: case ORC_PIX_YUV420P10: return 1 | 2;
+    case ORC_PIX_YUV422P: case ORC_PIX_YUV422P10: return 1;
+    default: return 0;
+    }
+}
+
+/* libswscale >= 7.1 range conversion on the 15-bit intermediates (swscale.c lumRangeTo/FromJpeg_c with the constants of
+ * init_range_convert_constants / solve_range_convert), restated and PINNED: for an output of `depth` bits
+ *   coeff  = ceil(((dst_max - dst_min) << 14) / (src_max - src_min))
+ *   offset = (dst_max << (29 - depth)) - (src_max << (15 - depth)) * coeff + (1 << 13)
+ *   out15  = min((in15 * coeff + offset) >> 14, 32767)
+ * with mpeg = [16, 235 | 240] << (depth - 8) and jpeg = [0, 2^depth - 1].  which: 0 luma, 1 chroma. */
+ORC_API void orc_range_coeffs(int depth, int to_jpeg, int which, int64_t *coeff, int64_t *offset)
+{
+    const int ss = 15 - depth, ts = 14 + ss;
+    const int64_t mpeg_min = 16 << (depth - 8), mpeg_max = (which ? 240 : 235) << (depth - 8), jpeg_max = (1 << depth) - 1;
+    const int64_t smin = to_jpeg ? mpeg_min : 0, smax = to_jpeg ? mpeg_max : jpeg_max;
+    const int64_t dmin = to_jpeg ? 0 : mpeg_min, dmax = to_jpeg ? jpeg_max : mpeg_max;
+    const int64_t num = (dmax - dmin) << ts, den = (smax - smin) << ss;
+    *coeff = (num + den - 1) / den;
+    *offset = (dmax << ts) - (smax << ss) * *coeff + (1 << 13);
+}
+
+static inline int range_conv15(int v, int64_t coeff, int64_t offset)
+{
+    int64_t o = ((int64_t)v * coeff + offset) >> 14;
+    return (int)(o > 32767 ? 32767 : o);
+}
+
+/* 8-bit sources -> rgb24.  4:2:0 / 4:2:2: the x86 SIMD path of orc_yuv420p_to_rgb24 (chroma replicated);
+ * 4:4:4: swscale's C path (8-bit samples lifted to 15 bits, yuv2rgb_full: 30-bit clip, >> 22). */
+ORC_API void orc_yuv8_to_rgb24(int sub, const uint8_t *Y, int ys, const uint8_t *U, const uint8_t *V, int cs, uint8_t *rgb, int rs,
+                               int w, int h, int matrix_id, int full_range)
+{
+    OrcYuv2Rgb t;
+    orc_yuv2rgb_setup(matrix_id, full_range, &t);
+    const int sx = sub & 1, sy = sub >> 1;
+    for (int y = 0; y < h; y++) {
+        const uint8_t *yr = Y + y * ys, *ur = U + (y >> sy) * cs, *vr_ = V + (y >> sy) * cs;
+        uint8_t *o = rgb + y * rs;
+        for (int x = 0; x < w; x++) {
+            if (sx) {
+                int yy = ((yr[x] * 8 - t.yO8) * t.yC) >> 16;
+                int u = ur[x >> 1] * 8 - 1024, v = vr_[x >> 1] * 8 - 1024;
+                o[3 * x + 0] = (uint8_t)clip_u(yy + ((v * t.vr) >> 16), 255);
+                o[3 * x + 1] = (uint8_t)clip_u(yy + ((u * t.ug) >> 16) + ((v * t.vg) >> 16), 255);
+                o[3 * x + 2] = (uint8_t)clip_u(yy + ((u * t.ub) >> 16), 255);
+            } else {
+                uint32_t yy = (uint32_t)(yr[x] * 512 - t.yOff10) * (uint32_t)t.yC + (1u << 21);
+                uint32_t u = (uint32_t)((ur[x] - 128) * 512), v = (uint32_t)((vr_[x] - 128) * 512);
+                int32_t r = (int32_t)(yy + v * (uint32_t)t.vr), g = (int32_t)(yy + v * (uint32_t)t.vg + u * (uint32_t)t.ug);
+                int32_t b = (int32_t)(yy + u * (uint32_t)t.ub);
+                if ((r | g | b) & (int32_t)0xC0000000) {
+                    r = r & ~0x3FFFFFFF ? (~r) >> 31 & 0x3FFFFFFF : r;
+                    g = g & ~0x3FFFFFFF ? (~g) >> 31 & 0x3FFFFFFF : g;
+                    b = b & ~0x3FFFFFFF ? (~b) >> 31 & 0x3FFFFFFF : b;
+                }
+                o[3 * x + 0] = (uint8_t)(r >> 22), o[3 * x + 1] = (uint8_t)(g >> 22), o[3 * x + 2] = (uint8_t)(b >> 22);
+            }
+        }
+    }
+}
+
+/* yuv444p10le -> gbrp10le: orc_yuv422p10_to_gbrp10 without the chroma filter (c15 = C << 5, u17 = (C - 512) * 128) */
+ORC_API void orc_yuv444p10_to_gbrp10(const uint16_t *Y, const uint16_t *U, const uint16_t *V, int is, uint16_t *R, uint16_t *G,
+                                     uint16_t *B, int os, int w, int h, int matrix_id, int full_range)
+{
+    OrcYuv2Rgb t;
+    orc_yuv2rgb_setup(matrix_id, full_range, &t);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            uint32_t u17 = (uint32_t)((U[y * is + x] - 512) * 128), v17 = (uint32_t)((V[y * is + x] - 512) * 128);
+            uint32_t yy = (uint32_t)(Y[y * is + x] * 128 - t.yOff10) * (uint32_t)t.yC + (1u << 19);
+            R[y * os + x] = clip30_shift20((int32_t)(yy + v17 * (uint32_t)t.vr));
+            G[y * os + x] = clip30_shift20((int32_t)(yy + v17 * (uint32_t)t.vg + u17 * (uint32_t)t.ug));
+            B[y * os + x] = clip30_shift20((int32_t)(yy + u17 * (uint32_t)t.ub));
+        }
+}
+
+/* ff_dither_8x8_128: swscale's ordered dither for 8-bit outputs of > 8-bit sources (recovered bit-exactly from the binary) */
+static const uint8_t k_dither_8x8_128[8][8] = {
+    {36, 68, 60, 92, 34, 66, 58, 90},   {100, 4, 124, 28, 98, 2, 122, 26}, {52, 84, 44, 76, 50, 82, 42, 74},
+    {116, 20, 108, 12, 114, 18, 106, 10}, {32, 64, 56, 88, 38, 70, 62, 94},  {96, 0, 120, 24, 102, 6, 126, 30},
+    {48, 80, 40, 72, 54, 86, 46, 78},   {112, 16, 104, 8, 118, 22, 110, 14},
+};
+
+/* RGB (src_depth 8 = rgb24 values, 10 = gbrp10le values; planes of uint16, stride `is` elements) -> any supported YUV output.
+ *   15-bit intermediates:  src 8: y15 = 2*y14 (rgb24ToY), chroma rgb24ToUV (4:4:4) or rgb24ToUV_half pair sums (4:2:2 / 4:2:0);
+ *                          src 10: y15 = min(2*y14, 32767) (planar_rgb16_to_y), chroma per column, then for 4:2:2 / 4:2:0 the
+ *                          8-tap horizontal decimation (orc_gbrp10_to_yuv422p10), for 4:4:4 min(2*c14, 32767)
+ *   out_full:              range conversion of the 15-bit values (orc_range_coeffs with the OUTPUT depth)
+ *   output stage:          10 bit: (v + 16) >> 5;  8 bit: (v + d) >> 7 with d = 64, or ff_dither_8x8_128[y & 7][(x + off) & 7]
+ *                          (off = 3 for V) when the RGB source is deeper than 8 bit
+ *   4:2:0 vertical:        8-tap over luma rows 2j-3 .. 2j+4, edge taps folded; 10 bit: exact, (sum + (1 << 16)) >> 17;
+ *                          8 bit: x86 yuv2yuvX: ((d + 56) >> 4) + sum((c15 * tap) >> 16)) >> 3, except the last chroma row
+ *                          (C code): ((d << 12) + sum(c15 * tap)) >> 19 */
+ORC_API void orc_rgb_to_yuv_any(int src_depth, int out_fmt, int out_full, const uint16_t *R, const uint16_t *G, const uint16_t *B,
+                                int is, void *Yo, void *Uo, void *Vo, int w, int h, int matrix_id)
+{
+    int32_t c[9];
+    orc_rgb2yuv_setup(matrix_id, c);
+    const int od = orc_pix_depth(out_fmt), sub = orc_pix_sub(out_fmt), sx = sub & 1, sy = sub >> 1;
+    const int cw = w >> sx, ch = h >> sy, omax = (1 << od) - 1;
+    const int bayer = src_depth > 8 && od == 8;
+    int64_t lc, lo, cc, co;
+    orc_range_coeffs(od, 1, 0, &lc, &lo);
+    orc_range_coeffs(od, 1, 1, &cc, &co);
+    int32_t *u14 = (int32_t *)malloc(sizeof(int32_t) * (size_t)w), *v14 = (int32_t *)malloc(sizeof(int32_t) * (size_t)w);
+    int32_t *hu = (int32_t *)malloc(sizeof(int32_t) * (size_t)cw * h), *hv = (int32_t *)malloc(sizeof(int32_t) * (size_t)cw * h);
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            const int r = R[y * is + x], g = G[y * is + x], b = B[y * is + x];
+            int y15;
+            if (src_depth == 8) {
+                y15 = 2 * ((c[0] * r + c[1] * g + c[2] * b + (32 << 14) + (1 << 8)) >> 9);
+                u14[x] = (c[3] * r + c[4] * g + c[5] * b + (256 << 14) + (1 << 8)) >> 9;
+                v14[x] = (c[6] * r + c[7] * g + c[8] * b + (256 << 14) + (1 << 8)) >> 9;
+            } else {
+                y15 = 2 * ((c[0] * r + c[1] * g + c[2] * b + (16 << 17) + (1 << 10)) >> 11);
+                if (y15 > 32767)
+                    y15 = 32767;
+                u14[x] = (c[3] * r + c[4] * g + c[5] * b + (128 << 17) + (1 << 10)) >> 11;
+                v14[x] = (c[6] * r + c[7] * g + c[8] * b + (128 << 17) + (1 << 10)) >> 11;
+            }
+            if (out_full)
+                y15 = range_conv15(y15, lc, lo);
+            const int d = bayer ? k_dither_8x8_128[y & 7][x & 7] : 64;
+            if (od == 8)
+                ((uint8_t *)Yo)[(size_t)y * w + x] = (uint8_t)clip_u((y15 + d) >> 7, 255);
+            else
+                ((uint16_t *)Yo)[(size_t)y * w + x] = (uint16_t)clip_u((y15 + 16) >> 5, omax);
+        }
+        for (int i = 0; i < cw; i++) {
+            int64_t su, sv;
+            if (!sx) {
+                su = 2 * u14[i], sv = 2 * v14[i];
+            } else if (src_depth == 8) {
+                const int r = R[y * is + 2 * i] + R[y * is + 2 * i + 1], g = G[y * is + 2 * i] + G[y * is + 2 * i + 1];
+                const int b = B[y * is + 2 * i] + B[y * is + 2 * i + 1];
+                su = 2 * ((c[3] * r + c[4] * g + c[5] * b + (256 << 15) + (1 << 9)) >> 10);
+                sv = 2 * ((c[6] * r + c[7] * g + c[8] * b + (256 << 15) + (1 << 9)) >> 10);
+            } else {
+                su = sv = 0;
+                for (int k = 0; k < 8; k++) {
+                    const int x = clampi(2 * i - 3 + k, 0, w - 1);
+                    su += (int64_t)u14[x] * k_h422_taps[k];
+                    sv += (int64_t)v14[x] * k_h422_taps[k];
+                }
+                su >>= 13, sv >>= 13;
+            }
+            int a = (int)(su > 32767 ? 32767 : su), b_ = (int)(sv > 32767 ? 32767 : sv);
+            if (out_full)
+                a = range_conv15(a, cc, co), b_ = range_conv15(b_, cc, co);
+            hu[(size_t)y * cw + i] = a, hv[(size_t)y * cw + i] = b_;
+        }
+    }
+    for (int j = 0; j < ch; j++) {
+        int rows[8], coef[8], n = 0;
+        if (sy)
+            for (int k = 0; k < 8; k++) { /* fold taps whose source row lies outside the frame onto the edge row */
+                const int row = clampi(2 * j - 3 + k, 0, h - 1);
+                if (n && rows[n - 1] == row)
+                    coef[n - 1] += k_v420_taps[k];
+                else
+                    rows[n] = row, coef[n] = k_v420_taps[k], n++;
+            }
+        for (int i = 0; i < cw; i++) {
+            const int du = bayer ? k_dither_8x8_128[j & 7][i & 7] : 64, dv = bayer ? k_dither_8x8_128[j & 7][(i + 3) & 7] : 64;
+            int ou, ov;
+            if (!sy) {
+                const int a = hu[(size_t)j * cw + i], b_ = hv[(size_t)j * cw + i];
+                ou = od == 8 ? (a + du) >> 7 : (a + 16) >> 5, ov = od == 8 ? (b_ + dv) >> 7 : (b_ + 16) >> 5;
+            } else if (od == 10) {
+                int64_t su = 1 << 16, sv = 1 << 16;
+                for (int k = 0; k < n; k++)
+                    su += (int64_t)hu[(size_t)rows[k] * cw + i] * coef[k], sv += (int64_t)hv[(size_t)rows[k] * cw + i] * coef[k];
+                ou = (int)(su >> 17), ov = (int)(sv >> 17);
+            } else if (j == ch - 1) { /* swscale drops to the C vertical scaler for the last output rows */
+                int su = du << 12, sv = dv << 12;
+                for (int k = 0; k < n; k++)
+                    su += hu[(size_t)rows[k] * cw + i] * coef[k], sv += hv[(size_t)rows[k] * cw + i] * coef[k];
+                ou = su >> 19, ov = sv >> 19;
+            } else { /* x86 yuv2yuvX: per-tap truncation (pmulhw) */
+                int su = (du + 56) >> 4, sv = (dv + 56) >> 4;
+                for (int k = 0; k < n; k++)
+                    su += (hu[(size_t)rows[k] * cw + i] * coef[k]) >> 16, sv += (hv[(size_t)rows[k] * cw + i] * coef[k]) >> 16;
+                ou = su >> 3, ov = sv >> 3;
+            }
+            if (od == 8)
+                ((uint8_t *)Uo)[(size_t)j * cw + i] = (uint8_t)clip_u(ou, 255), ((uint8_t *)Vo)[(size_t)j * cw + i] = (uint8_t)clip_u(ov, 255);
+            else
+                ((uint16_t *)Uo)[(size_t)j * cw + i] = (uint16_t)clip_u(ou, omax), ((uint16_t *)Vo)[(size_t)j * cw + i] = (uint16_t)clip_u(ov, omax);
+        }
+    }
+    free(u14), free(v14), free(hu), free(hv);
+}
+
+/* Any supported source -> [8-bit pc->tv pass] -> RGB (rgb24 for 8-bit, gbrp10le for 10-bit sources) -> lut3d -> any supported
+ * output, one frame, tightly packed planes.  range_pass only for 8-bit sources (the reference's pass always lands on 8-bit
+ * yuv4xxp, ffmpeg.py:137-143); in_full_range = range of the samples the YUV->RGB step sees. */
+ORC_API int orc_stage_any(const OrcLut *l, int interp, int in_fmt, int out_fmt, int range_pass, int in_matrix, int in_full_range,
+                          int out_matrix, int out_full_range, const void *Y, const void *U, const void *V, void *Yo, void *Uo,
+                          void *Vo, int w, int h)
+{
+    if (in_fmt < 0 || in_fmt >= ORC_PIX_COUNT || out_fmt < 0 || out_fmt >= ORC_PIX_COUNT)
+        return ORC_EINVAL;
+    const int id = orc_pix_depth(in_fmt), sub = orc_pix_sub(in_fmt), cw = w >> (sub & 1), ch = h >> (sub >> 1);
+    const size_t n = (size_t)w * h, cn = (size_t)cw * ch;
+    uint16_t *rgb = (uint16_t *)malloc(3 * n * sizeof(uint16_t));
+    if (!rgb)
+        return ORC_ENOMEM;
+    uint16_t *R = rgb, *G = rgb + n, *B = rgb + 2 * n;
+    if (id == 8) {
+        uint8_t *p8 = (uint8_t *)malloc(3 * n), *tmp = NULL;
+        const uint8_t *y8 = (const uint8_t *)Y, *u8 = (const uint8_t *)U, *v8 = (const uint8_t *)V;
+        if (range_pass) {
+            tmp = (uint8_t *)malloc(n + 2 * cn);
+            orc_range_pc_to_tv_8(y8, w, tmp, w, w, h, 0);
+            orc_range_pc_to_tv_8(u8, cw, tmp + n, cw, cw, ch, 1);
+            orc_range_pc_to_tv_8(v8, cw, tmp + n + cn, cw, cw, ch, 1);
+            y8 = tmp, u8 = tmp + n, v8 = tmp + n + cn;
+        }
+        orc_yuv8_to_rgb24(sub, y8, w, u8, v8, cw, p8, 3 * w, w, h, in_matrix, in_full_range);
+        orc_lut3d_rgb24(l, interp, p8, 3 * w, p8, 3 * w, w, h);
+        for (size_t i = 0; i < n; i++)
+            R[i] = p8[3 * i], G[i] = p8[3 * i + 1], B[i] = p8[3 * i + 2];
+        free(p8), free(tmp);
+    } else {
+        if (range_pass) {
+            free(rgb);
+            return ORC_EINVAL;
+        }
+        const uint16_t *y16 = (const uint16_t *)Y, *u16 = (const uint16_t *)U, *v16 = (const uint16_t *)V;
+        if (in_fmt == ORC_PIX_YUV420P10)
+            orc_yuv420p10_to_gbrp10(y16, w, u16, v16, cw, R, G, B, w, w, h, in_matrix, in_full_range);
+        else if (in_fmt == ORC_PIX_YUV422P10)
+            orc_yuv422p10_to_gbrp10(y16, w, u16, v16, cw, R, G, B, w, w, h, in_matrix, in_full_range);
+        else
+            orc_yuv444p10_to_gbrp10(y16, u16, v16, w, R, G, B, w, w, h, in_matrix, in_full_range);
+        orc_lut3d_planar16(l, interp, 10, R, G, B, w, R, G, B, w, w, h);
+    }
+    orc_rgb_to_yuv_any(id, out_fmt, out_full_range, R, G, B, w, Yo, Uo, Vo, w, h, out_matrix);
     free(rgb);
     return ORC_OK;
 }

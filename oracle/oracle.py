@@ -16,7 +16,8 @@ _SO = os.path.join(_HERE, "liblutr_oracle.so")
 
 MATRIX_ID = {"bt709": 0, "bt601": 1, "smpte170m": 1, "bt470bg": 1, "default": 1, "bt2020nc": 2, "bt2020c": 2,
              "bt2020": 2, "fcc": 3, "smpte240m": 4}
-INTERP_ID = {"nearest": 0, "trilinear": 1, "tetrahedral": 2}
+INTERP_ID = {"nearest": 0, "trilinear": 1, "tetrahedral": 2, "pyramid": 3, "prism": 4}
+PIX_ID = {"yuv420p": 0, "yuv422p10le": 1, "yuv420p10le": 2, "yuv422p": 3, "yuv444p": 4, "yuv444p10le": 5}
 
 _lib = None
 
@@ -237,3 +238,59 @@ def stage_10bit(lut, Y, U, V, in_420=False, out_420=False, interp="tetrahedral",
     if r:
         raise RuntimeError(f"orc_stage_10bit: {r}")
     return Yo, Uo, Vo
+
+
+# ---- the whole format matrix (generic legs; lutr_oracle.c "orc_stage_any") -------------------------------------------------
+def pix_geometry(pix_fmt, w, h):
+    """[(rows, cols)] of the three planes and the sample dtype."""
+    L = lib()
+    sub, depth = L.orc_pix_sub(PIX_ID[pix_fmt]), L.orc_pix_depth(PIX_ID[pix_fmt])
+    cw, ch = w >> (sub & 1), h >> (sub >> 1)
+    return [(h, w), (ch, cw), (ch, cw)], (np.uint16 if depth > 8 else np.uint8)
+
+
+def range_coeffs(depth, to_jpeg, chroma):
+    c, o = ctypes.c_int64(), ctypes.c_int64()
+    lib().orc_range_coeffs(depth, int(to_jpeg), int(chroma), ctypes.byref(c), ctypes.byref(o))
+    return c.value, o.value
+
+
+def yuv8_to_rgb24(pix_fmt, Y, U, V, matrix="bt709", full_range=False):
+    h, w = Y.shape
+    rgb = np.empty((h, 3 * w), np.uint8)
+    L = lib()
+    L.orc_yuv8_to_rgb24(L.orc_pix_sub(PIX_ID[pix_fmt]), _p(Y), w, _p(U), _p(V), U.shape[1], _p(rgb), 3 * w, w, h,
+                        MATRIX_ID[matrix], int(full_range))
+    return rgb
+
+
+def yuv444p10_to_gbrp10(Y, U, V, matrix="bt709", full_range=False):
+    h, w = Y.shape
+    R, G, B = (np.empty((h, w), np.uint16) for _ in range(3))
+    lib().orc_yuv444p10_to_gbrp10(_p(Y), _p(U), _p(V), w, _p(R), _p(G), _p(B), w, w, h, MATRIX_ID[matrix], int(full_range))
+    return R, G, B
+
+
+def rgb_to_yuv_any(src_depth, out_fmt, R, G, B, matrix="bt709", out_full_range=False):
+    """R, G, B: uint16 planes holding rgb24 (src_depth 8) or gbrp10le (src_depth 10) values."""
+    h, w = R.shape
+    shapes, dt = pix_geometry(out_fmt, w, h)
+    out = [np.empty(s, dt) for s in shapes]
+    R, G, B = (np.ascontiguousarray(p, dtype=np.uint16) for p in (R, G, B))
+    lib().orc_rgb_to_yuv_any(src_depth, PIX_ID[out_fmt], int(out_full_range), _p(R), _p(G), _p(B), w, _p(out[0]), _p(out[1]),
+                             _p(out[2]), w, h, MATRIX_ID[matrix])
+    return out
+
+
+def stage_any(lut, in_fmt, out_fmt, Y, U, V, interp="tetrahedral", range_pass=False, in_matrix="bt709", in_full_range=False,
+              out_matrix="bt709", out_full_range=False):
+    """Any supported source -> [8-bit pc->tv pass] -> RGB -> lut3d -> any supported output (one frame, contiguous planes)."""
+    h, w = Y.shape
+    shapes, dt = pix_geometry(out_fmt, w, h)
+    out = [np.empty(s, dt) for s in shapes]
+    r = lib().orc_stage_any(lut._h, INTERP_ID[interp], PIX_ID[in_fmt], PIX_ID[out_fmt], int(range_pass), MATRIX_ID[in_matrix],
+                            int(in_full_range), MATRIX_ID[out_matrix], int(out_full_range), _p(Y), _p(U), _p(V), _p(out[0]),
+                            _p(out[1]), _p(out[2]), w, h)
+    if r:
+        raise RuntimeError(f"orc_stage_any: {r}")
+    return out

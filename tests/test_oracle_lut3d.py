@@ -86,3 +86,31 @@ def test_8bit_packed_path():
     out = O.lut3d_rgb24(lut, rgb, "tetrahedral")
     d = rgb.astype(int) - out.astype(int)
     assert d.min() >= 0 and d.max() <= 1
+
+
+@pytest.mark.parametrize("interp", ["pyramid", "prism"])
+def test_pyramid_prism_reproduce_corners_and_affine_luts(interp):
+    """interp=pyramid / prism (reference whitelist ffmpeg.py:243): both reproduce the LUT nodes, are exact on affine LUTs (every
+    difference term cancels) and agree with tetrahedral along the cube axes / grey diagonal of a 2-point LUT."""
+    rng = np.random.default_rng(5)
+    t = rng.random((2, 2, 2, 3)).astype(np.float32)
+    lut = O.OracleLut.from_table(t)
+    for r in (0, 1):
+        for g in (0, 1):
+            for b in (0, 1):
+                exp = tuple(int(np.float32(v) * np.float32(1023.0)) for v in t[r, g, b])
+                assert _px(lut, 1023 * r, 1023 * g, 1023 * b, interp=interp) == exp
+    # affine LUT: value = 0.1 + 0.5 r + 0.2 g + 0.15 b on a 9-point grid -> any cell interpolation returns the affine function
+    n = 9
+    ax = np.linspace(0, 1, n, dtype=np.float64)
+    aff = (0.1 + 0.5 * ax[:, None, None] + 0.2 * ax[None, :, None] + 0.15 * ax[None, None, :])
+    lut = O.OracleLut.from_table(np.repeat(aff[..., None], 3, -1).astype(np.float32))
+    pts = rng.integers(0, 1024, (1, 4096, 3)).astype(np.uint16)
+    R, G, B = O.lut3d_planar16(lut, pts[..., 0].copy(), pts[..., 1].copy(), pts[..., 2].copy(), 10, interp)
+    ideal = (0.1 + (0.5 * pts[..., 0] + 0.2 * pts[..., 1] + 0.15 * pts[..., 2]) / 1023.0) * 1023.0
+    assert np.abs(R.astype(np.float64) - np.floor(ideal)).max() <= 1 and np.array_equal(R, G) and np.array_equal(G, B)
+    # on a cube edge (two fractions zero) every interpolation is the same 1-D lerp up to float rounding of the blend order
+    lut = O.OracleLut.from_table(synth.look_lut(17).astype(np.float32))
+    for px in ((512, 0, 0), (0, 300, 0), (0, 0, 900)):
+        a, b = _px(lut, *px, interp=interp), _px(lut, *px, interp="trilinear")
+        assert max(abs(x - y) for x, y in zip(a, b)) <= 1

@@ -157,3 +157,87 @@ def test_composite_with_real_swscale_legs_equals_oracle_composite():
             b = C.CpuStage(fmt, w, h, lut, use_swscale=False, out_pix_fmt=out_fmt).run(planes)
             for x, y in zip(a, b):
                 assert np.array_equal(x, y)
+
+
+# ---- the whole format matrix: generic legs (orc_yuv8_to_rgb24, orc_yuv444p10_to_gbrp10, orc_rgb_to_yuv_any) ---------------------
+def _saturate(rng, planes, hi):
+    for P in planes:
+        sel = rng.random(P.shape) < 0.25
+        P[sel] = np.where(rng.random(int(sel.sum())) < 0.5, 0, hi).astype(P.dtype)
+
+
+@pytest.mark.parametrize("fmt", ["yuv420p", "yuv422p", "yuv444p"])
+@pytest.mark.parametrize("w,h", [(1920, 36), (64, 16), (328, 18), (16, 12)])
+def test_any_8bit_sources_match_libswscale(fmt, w, h):
+    """yuv4xxp -> rgb24 for every 8-bit layout the reference's range pass can leave (ffmpeg.py:137-143): 4:2:0 / 4:2:2 take the
+    SIMD path (replicated chroma), 4:4:4 swscale's C path; 3 matrices x 2 ranges, full code range."""
+    rng = np.random.default_rng(w + h)
+    shapes, dt = O.pix_geometry(fmt, w, h)
+    for matrix in ("bt709", "bt601", "bt2020"):
+        for full in (0, 1):
+            Y, U, V = (rng.integers(0, 256, s, dtype=np.uint8) for s in shapes)
+            ref = S.SwsConverter(w, h, fmt, "rgb24", src_range=full, src_matrix=matrix, dst_matrix=matrix).convert(
+                [Y, U, V], S.alloc_planes("rgb24", w, h))[0]
+            assert np.array_equal(O.yuv8_to_rgb24(fmt, Y, U, V, matrix, full), ref)
+
+
+@pytest.mark.parametrize("w,h", [(512, 32), (66, 14), (16, 2)])
+def test_any_yuv444p10_source_matches_libswscale(w, h):
+    rng = np.random.default_rng(w * 3 + h)
+    for matrix in ("bt709", "bt601", "bt2020"):
+        for full in (0, 1):
+            Y, U, V = (rng.integers(0, 1024, (h, w), dtype=np.uint16) for _ in range(3))
+            g, b, r = S.SwsConverter(w, h, "yuv444p10le", "gbrp10le", src_range=full, src_matrix=matrix, dst_matrix=matrix).convert(
+                [Y, U, V], S.alloc_planes("gbrp10le", w, h))
+            R, G, B = O.yuv444p10_to_gbrp10(Y, U, V, matrix, full)
+            assert np.array_equal(R, r) and np.array_equal(G, g) and np.array_equal(B, b)
+
+
+@pytest.mark.parametrize("src_depth", [8, 10])
+@pytest.mark.parametrize("out_fmt", ["yuv420p", "yuv422p", "yuv444p", "yuv420p10le", "yuv422p10le", "yuv444p10le"])
+@pytest.mark.parametrize("w,h", [(1920, 36), (64, 16), (328, 18), (22, 30)])
+def test_any_output_leg_matches_libswscale(src_depth, out_fmt, w, h):
+    """RGB -> every output layout / depth / range: rgb24 (8-bit sources) and gbrp10le (10-bit sources) in front; limited and full
+    range behind (swscale's 15-bit range conversion), ordered dither for the 10 -> 8 bit outputs, the 4:2:0 vertical scalers
+    (SIMD per-tap truncation for 8 bit incl. the C-path last row, exact for 10 bit)."""
+    rng = np.random.default_rng(w * 5 + h + src_depth)
+    hi = (1 << src_depth) - 1
+    src_fmt = "rgb24" if src_depth == 8 else "gbrp10le"
+    for matrix in ("bt709", "bt601", "bt2020"):
+        for full in (0, 1):
+            R, G, B = (rng.integers(0, hi + 1, (h, w), dtype=np.uint16) for _ in range(3))
+            _saturate(rng, (R, G, B), hi)
+            if src_depth == 8:
+                src = [np.stack([R, G, B], -1).astype(np.uint8).reshape(h, 3 * w)]
+            else:
+                src = [G, B, R]
+            ref = S.SwsConverter(w, h, src_fmt, out_fmt, dst_range=full, src_matrix=matrix, dst_matrix=matrix).convert(
+                src, S.alloc_planes(out_fmt, w, h))
+            got = O.rgb_to_yuv_any(src_depth, out_fmt, R, G, B, matrix, full)
+            for name, a, b in zip("YUV", got, ref):
+                assert np.array_equal(a, b), (name, matrix, full, int((a != b).sum()))
+
+
+def test_any_composite_equals_specialised_composites():
+    """orc_stage_any == the specialised composites on the formats both cover, and the range constants reproduce the pc->tv tables."""
+    from lut_renderer_b200 import synth
+    lut = O.OracleLut.from_table(synth.look_lut(17).astype(np.float32))
+    w, h = 96, 20
+    for fmt, out_fmt in (("yuv420p", "yuv420p"), ("yuv420p", "yuv422p10le"), ("yuv422p10le", "yuv422p10le"),
+                         ("yuv420p10le", "yuv422p10le"), ("yuv422p10le", "yuv420p10le"), ("yuv420p10le", "yuv420p10le")):
+        f = synth.noise_frame(fmt, w, h, 3)
+        Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(f, fmt, w, h)]
+        a = O.stage_any(lut, fmt, out_fmt, Y, U, V, range_pass=(fmt == "yuv420p"))
+        if fmt == "yuv420p" and out_fmt == "yuv420p":
+            b = O.stage_yuv420p(lut, Y, U, V, range_pass=True)
+        elif fmt == "yuv420p":
+            b = O.stage_yuv420p_to_yuv422p10(lut, Y, U, V, range_pass=True)
+        else:
+            b = O.stage_10bit(lut, Y, U, V, in_420=fmt == "yuv420p10le", out_420=out_fmt == "yuv420p10le")
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    tl, tc = O.range_tables()
+    x = np.arange(256, dtype=np.int64) << 7
+    for chroma, t in ((0, tl), (1, tc)):
+        c, o = O.range_coeffs(8, False, chroma)
+        assert np.array_equal(np.clip((np.minimum((x * c + o) >> 14, 32767) + 64) >> 7, 0, 255), t)
