@@ -44,13 +44,16 @@ CONFIGS = {
     "hevc10_422": dict(pix_fmt="yuv422p10le", out_pix_fmt="yuv420p10le", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv",
                        norm_range="tv", frames_per_step=64,
                        desc="4K UHD yuv422p10le source -> 65-point look .cube, tetrahedral -> yuv420p10le (libx265 preserve)"),
+    "deliver8": dict(pix_fmt="yuv420p10le", out_pix_fmt="yuv420p", w=3840, h=2160, lut=65, interp="tetrahedral", in_range="tv",
+                     norm_range="tv", frames_per_step=64,
+                     desc="4K UHD yuv420p10le source -> 65-point look .cube, tetrahedral -> yuv420p 8-bit delivery (ordered dither)"),
     "cfg4": dict(pix_fmt="yuv422p10le", w=7680, h=4320, lut=65, interp="tetrahedral", in_range="tv", norm_range="tv",
                  frames_per_step=16, desc="8K yuv422p10le, 65-point look .cube, tetrahedral, frame-range sharded"),
 }
 # BASELINE.json configs[4]: batch queue of 64 mixed clips with per-clip LUTs, sharded by clip (handled by run_cfg5)
 CFG5 = dict(clips=64, frames_per_clip=24,
             desc="batch queue of 64 mixed 1080p yuv420p (33-point) / 4K yuv422p10le (65-point) clips, per-clip .cube LUTs, sharded by clip")
-BYTES_PER_PIXEL = {"yuv420p": 1.5, "yuv422p10le": 4.0, "yuv420p10le": 3.0}  # per side; algorithmic bytes/frame = (in + out) * w * h
+BYTES_PER_PIXEL = {"yuv420p": 1.5, "yuv422p": 2.0, "yuv444p": 3.0, "yuv420p10le": 3.0, "yuv422p10le": 4.0, "yuv444p10le": 6.0}  # per side; algorithmic bytes/frame = (in + out) * w * h
 
 
 def measured_peak_hbm():
@@ -431,13 +434,8 @@ def main():
             first = src[:stage.in_frame_bytes].cpu().numpy()
             L = O.OracleLut.from_table(table)
             Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(first, cfg["pix_fmt"], cfg["w"], cfg["h"])]
-            if "10" in cfg["pix_fmt"]:
-                exp = O.stage_10bit(L, Y, U, V, in_420=cfg["pix_fmt"] == "yuv420p10le",
-                                    out_420=cfg.get("out_pix_fmt", cfg["pix_fmt"]) == "yuv420p10le", interp=cfg["interp"])
-            elif cfg.get("out_pix_fmt") == "yuv422p10le":
-                exp = O.stage_yuv420p_to_yuv422p10(L, Y, U, V, interp=cfg["interp"])
-            else:
-                exp = O.stage_yuv420p(L, Y, U, V, interp=cfg["interp"], range_pass=cfg["in_range"] == "pc" and cfg["norm_range"] == "tv")
+            exp = O.stage_any(L, cfg["pix_fmt"], cfg.get("out_pix_fmt", cfg["pix_fmt"]), Y, U, V, interp=cfg["interp"],
+                              range_pass=cfg["in_range"] == "pc" and cfg["norm_range"] == "tv")
             parity = "bit-exact" if np.array_equal(got, synth.pack_planes(exp)) else "MISMATCH"
         except Exception as exc:  # the checker is optional for the measurement
             parity = f"unchecked ({exc})"

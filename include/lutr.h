@@ -53,7 +53,10 @@ typedef enum lutr_status {
 typedef enum lutr_pix_fmt {
     LUTR_PIX_YUV420P = 0,     /* 8-bit 4:2:0 planar  (fast-delivery default / force_8bit)                 */
     LUTR_PIX_YUV422P10LE = 1, /* 10-bit 4:2:2 planar in LE u16 (pro-mode ProRes master, ffmpeg.py:417-433) */
-    LUTR_PIX_YUV420P10LE = 2  /* 10-bit 4:2:0 planar in LE u16 (10-bit camera / HEVC sources; libx265 'preserve' output, ffmpeg.py:297-298) */
+    LUTR_PIX_YUV420P10LE = 2, /* 10-bit 4:2:0 planar in LE u16 (10-bit camera / HEVC sources; libx265 'preserve' output, ffmpeg.py:297-298) */
+    LUTR_PIX_YUV422P = 3,     /* 8-bit 4:2:2 planar (GUI pix_fmt choice main_window.py:767-771; range-pass intermediate ffmpeg.py:137-143) */
+    LUTR_PIX_YUV444P = 4,     /* 8-bit 4:4:4 planar (same two uses) */
+    LUTR_PIX_YUV444P10LE = 5  /* 10-bit 4:4:4 planar in LE u16 (10-bit 4:4:4 sources) */
 } lutr_pix_fmt;
 
 typedef enum lutr_range { LUTR_RANGE_TV = 0, LUTR_RANGE_PC = 1 } lutr_range;
@@ -68,7 +71,13 @@ typedef enum lutr_matrix {
 } lutr_matrix;
 
 /* lut3d `interp=` (ffmpeg.py:242-246; GUI offers tetrahedral / trilinear, main_window.py:649-652). */
-typedef enum lutr_interp { LUTR_INTERP_NEAREST = 0, LUTR_INTERP_TRILINEAR = 1, LUTR_INTERP_TETRAHEDRAL = 2 } lutr_interp;
+typedef enum lutr_interp {
+    LUTR_INTERP_NEAREST = 0,
+    LUTR_INTERP_TRILINEAR = 1,
+    LUTR_INTERP_TETRAHEDRAL = 2,
+    LUTR_INTERP_PYRAMID = 3, /* accepted by the reference's whitelist (ffmpeg.py:243); generic kernel only */
+    LUTR_INTERP_PRISM = 4
+} lutr_interp;
 
 /* Float evaluation order of the LUT blend.  C = FFmpeg's C code (separate mul and add; what packed
  * rgb24 always uses and the documented semantics of this library).  FMA = contracted multiply-adds

@@ -14,11 +14,11 @@ LIB_PATH = os.path.join(_HERE, "liblutr.so")
 
 OK, ERR_INVALID_ARG, ERR_INVALID_DATA, ERR_LUT_SIZE, ERR_IO, ERR_NOMEM, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
 
-PIX_FMT = {"yuv420p": 0, "yuv422p10le": 1, "yuv420p10le": 2}
+PIX_FMT = {"yuv420p": 0, "yuv422p10le": 1, "yuv420p10le": 2, "yuv422p": 3, "yuv444p": 4, "yuv444p10le": 5}
 RANGE = {"tv": 0, "pc": 1}
 MATRIX = {"bt709": 0, "bt601": 1, "smpte170m": 1, "bt470bg": 1, "bt2020": 2, "bt2020nc": 2, "bt2020c": 2, "fcc": 3,
           "smpte240m": 4}
-INTERP = {"nearest": 0, "trilinear": 1, "tetrahedral": 2}
+INTERP = {"nearest": 0, "trilinear": 1, "tetrahedral": 2, "pyramid": 3, "prism": 4}
 FLOAT_MODE = {"c": 0, "fma": 1}
 
 

@@ -112,4 +112,19 @@ void build_index_table(int depth, int entries, float scale_times_lutmax, float l
     }
 }
 
+// libswscale >= 7.1 range conversion on the 15-bit intermediates (lumRangeTo/FromJpeg_c, chrRangeTo/FromJpeg_c with the
+// constants of solve_range_convert), pinned against libswscale 9.1.100 through oracle/lutr_oracle.c orc_range_coeffs:
+//   coeff = ceil(((dst_max - dst_min) << 14) / (src_max - src_min)),
+//   offset = (dst_max << (29 - depth)) - (src_max << (15 - depth)) * coeff + (1 << 13)
+void range_coeffs(int depth, bool to_jpeg, bool chroma, int32_t *coeff, int32_t *offset) {
+    const int ss = 15 - depth, ts = 14 + ss;
+    const int64_t mpeg_min = 16 << (depth - 8), mpeg_max = (chroma ? 240 : 235) << (depth - 8), jpeg_max = (1 << depth) - 1;
+    const int64_t smin = to_jpeg ? mpeg_min : 0, smax = to_jpeg ? mpeg_max : jpeg_max;
+    const int64_t dmin = to_jpeg ? 0 : mpeg_min, dmax = to_jpeg ? jpeg_max : mpeg_max;
+    const int64_t num = (dmax - dmin) << ts, den = (smax - smin) << ss;
+    const int64_t c = (num + den - 1) / den;
+    *coeff = (int32_t)c;
+    *offset = (int32_t)((dmax << ts) - (smax << ss) * c + (1 << 13));
+}
+
 }  // namespace lutr

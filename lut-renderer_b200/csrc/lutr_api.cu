@@ -57,6 +57,8 @@ struct lutr_stage {
     const lutr_lut *persist_lut = nullptr;
     std::vector<IdxTable> idx_tables;
     int use_fast = 1;      // 0 forces the generic kernels (testing)
+    bool any_only = false; // the combination exists in the generic tile kernel (k_any.cu) only
+    int force_any = 0;     // option "any_kernel": 1 routes every launch through the generic tile kernel (testing)
     int grid_ctas = 0;     // 0 = min_blocks CTAs per SM
     int idx_mode = 3;      // 0 = shared-memory index table, 1 = arithmetic index, 2 = arithmetic index + TMA-staged rows,
                            // 3 = warp-window kernel (k422_warp.cu)
@@ -81,10 +83,10 @@ namespace {
         }                                                                                  \
     } while (0)
 
-int plane_rows(int fmt, int h, int p) { return ((fmt == LUTR_PIX_YUV420P || fmt == LUTR_PIX_YUV420P10LE) && p > 0) ? h / 2 : h; }
+int plane_rows(int fmt, int h, int p) { return p > 0 ? h >> (pix_sub(fmt) >> 1) : h; }
 int plane_row_bytes(int fmt, int w, int p) {
-    const int bps = fmt == LUTR_PIX_YUV420P ? 1 : 2;
-    return (p == 0 ? w : w / 2) * bps;
+    const int bps = pix_depth(fmt) > 8 ? 2 : 1;
+    return (p == 0 ? w : w >> (pix_sub(fmt) & 1)) * bps;
 }
 size_t frame_bytes(int fmt, int w, int h) {
     size_t n = 0;
@@ -146,8 +148,8 @@ int check_planes(const lutr_stage *s, const lutr_planes *pl, int fmt, int nframe
             return LUTR_ERR_INVALID_ARG;
         }
         // vector accesses: one 8-pixel group of Y (16 B at 10 bit, 8 B at 8 bit), half of that for a chroma group
-        const int ya = fmt == LUTR_PIX_YUV420P ? 8 : 16;
-        const int a = p == 0 ? ya : ya / 2;
+        const int ya = pix_depth(fmt) > 8 ? 16 : 8;
+        const int a = p == 0 || !(pix_sub(fmt) & 1) ? ya : ya / 2;
         if (((uintptr_t)pl->data[p] % a) || (pl->stride[p] % a) || (nframes > 1 && (pl->frame_step % ya))) {
             set_error("%s plane %d: pointer and stride must be %d-byte aligned, frame_step %d-byte aligned", what, p, a, ya);
             return LUTR_ERR_UNSUPPORTED;
@@ -297,17 +299,35 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         }
     }
     k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : k.min_blocks * s->ctx->sm_count;
-    if (s->d.in_fmt == LUTR_PIX_YUV420P10LE || s->d.out_fmt == LUTR_PIX_YUV420P10LE) {
-        if (!warp_kernel) {
-            set_error("stage: 10-bit 4:2:0 input / output needs one LUT domain scale for all channels and the default kernel family");
-            return LUTR_ERR_UNSUPPORTED;
-        }
-        const bool in420 = s->d.in_fmt == LUTR_PIX_YUV420P10LE, out420 = s->d.out_fmt == LUTR_PIX_YUV420P10LE;
-        k.rows_per_cta = 0, k.bands = 1;
+    // generic tile kernel: combinations without a specialised kernel, and specialised combinations whose fast path does not apply
+    // (per-channel LUT domain scales, interp=nearest on the master stages, rows narrower than a window)
+    auto run_any = [&]() {
+        AnyK &a = k.any;
+        a.in_sub = pix_sub(s->d.in_fmt), a.in_depth = pix_depth(s->d.in_fmt);
+        a.out_sub = pix_sub(s->d.out_fmt), a.out_depth = pix_depth(s->d.out_fmt);
+        a.out_full = s->d.out_range == LUTR_RANGE_PC ? 1 : 0;
+        range_coeffs(8, false, false, &a.in_lc, &a.in_lo);
+        range_coeffs(8, false, true, &a.in_cc, &a.in_co);
+        range_coeffs(a.out_depth, true, false, &a.out_lc, &a.out_lo);
+        range_coeffs(a.out_depth, true, true, &a.out_cc, &a.out_co);
         k.grid_ctas = s->grid_ctas;
-        k.min_blocks = s->wk_minb;
-        rc = launch_k10_warp(k, in420, out420, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
-        s->last_kernel = !out420 ? "k10_warp<420,422>" : (in420 ? "k10_warp<420,420>" : "k10_warp<422,420>");
+        s->last_kernel = "k_any";
+        return launch_k_any(k, s->d.interp, s->d.float_mode, st);
+    };
+    const bool mixed = s->d.in_fmt != s->d.out_fmt;
+    if (s->any_only || s->force_any) {
+        rc = run_any();
+    } else if (s->d.in_fmt == LUTR_PIX_YUV420P10LE || s->d.out_fmt == LUTR_PIX_YUV420P10LE) {
+        if (!warp_kernel) {
+            rc = run_any();
+        } else {
+            const bool in420 = s->d.in_fmt == LUTR_PIX_YUV420P10LE, out420 = s->d.out_fmt == LUTR_PIX_YUV420P10LE;
+            k.rows_per_cta = 0, k.bands = 1;
+            k.grid_ctas = s->grid_ctas;
+            k.min_blocks = s->wk_minb;
+            rc = launch_k10_warp(k, in420, out420, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = !out420 ? "k10_warp<420,422>" : (in420 ? "k10_warp<420,420>" : "k10_warp<422,420>");
+        }
     } else if (s->d.in_fmt == LUTR_PIX_YUV422P10LE) {
         k.rows_per_cta = s->rows_per_cta > 0 ? s->rows_per_cta : 1;
         if (warp_kernel) {
@@ -326,21 +346,16 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         // 4:2:0 warp-window kernel (window width and grid are chosen in the launcher)
         k.wk_unroll = s->wk_nk_forced ? s->wk_unroll : 0;
         k.rows_per_cta = 0, k.bands = 1;
-        if (s->d.out_fmt == LUTR_PIX_YUV422P10LE) {
+        if (mixed) {
             rc = launch_k420_warp10(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
             s->last_kernel = "k420_warp10";
         } else {
             rc = launch_k420_warp(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
             s->last_kernel = "k420_warp";
         }
-        if (rc == LUTR_ERR_UNSUPPORTED) {
-            set_error("stage: this LUT / option combination needs a row of at least 256 columns");
-            return rc;
-        }
-    } else if (s->d.out_fmt != s->d.in_fmt) {
-        set_error("stage: yuv420p->yuv422p10le needs one LUT domain scale for all channels, width >= 256 (or 128 with a standard LUT) "
-                  "and the default kernel family");
-        return LUTR_ERR_UNSUPPORTED;
+        if (rc == LUTR_ERR_UNSUPPORTED) rc = run_any();  // this LUT / option combination needs a row of at least 256 columns
+    } else if (mixed) {
+        rc = run_any();
     } else {
         // bands per frame: enough CTAs to fill the device a few times over, but bands of >= 16 rows (7 halo rows each)
         int rows = s->band_rows;
@@ -563,60 +578,49 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
         return LUTR_ERR_INVALID_ARG;
     }
     const lutr_stage_desc &d = *desc;
-    if (d.width <= 0 || d.height <= 0 || d.interp < 0 || d.interp > 2 || d.float_mode < 0 || d.float_mode > 1 ||
+    if (d.width <= 0 || d.height <= 0 || d.interp < 0 || d.interp > LUTR_INTERP_PRISM || d.float_mode < 0 || d.float_mode > 1 ||
         d.in_matrix < 0 || d.in_matrix > 4 || d.out_matrix < 0 || d.out_matrix > 4 || d.in_range < 0 || d.in_range > 1 ||
-        d.norm_range < 0 || d.norm_range > 1 || d.out_range < 0 || d.out_range > 1) {
+        d.norm_range < 0 || d.norm_range > 1 || d.out_range < 0 || d.out_range > 1 || d.in_fmt < 0 ||
+        d.in_fmt > LUTR_PIX_YUV444P10LE || d.out_fmt < 0 || d.out_fmt > LUTR_PIX_YUV444P10LE) {
         set_error("stage: bad geometry or enum value");
         return LUTR_ERR_INVALID_ARG;
-    }
-    const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
-    const bool to_master = d.in_fmt == LUTR_PIX_YUV420P && d.out_fmt == LUTR_PIX_YUV422P10LE;  // pro-mode master from an 8-bit source
-    // 10-bit chains whose rows are walked in order (k10_warp.cu): 4:2:0 source -> master, and the 10-bit 4:2:0 outputs
-    const bool in10 = d.in_fmt == LUTR_PIX_YUV420P10LE || d.in_fmt == LUTR_PIX_YUV422P10LE;
-    const bool ordered10 = in10 && (d.in_fmt == LUTR_PIX_YUV420P10LE || d.out_fmt == LUTR_PIX_YUV420P10LE) &&
-                           (d.out_fmt == LUTR_PIX_YUV422P10LE || d.out_fmt == LUTR_PIX_YUV420P10LE);
-    if (!same_fmt && !to_master && !ordered10) {
-        set_error("stage: implemented are yuv420p->yuv420p, yuv420p->yuv422p10le and yuv420p10le|yuv422p10le->yuv420p10le|yuv422p10le");
-        return LUTR_ERR_UNSUPPORTED;
-    }
-    if (ordered10 && (d.interp == LUTR_INTERP_NEAREST || (d.height % 2) || d.height < 14 ||
-                      (d.in_range == LUTR_RANGE_PC && d.norm_range == LUTR_RANGE_TV))) {
-        // height: the vertical chroma filter models are pinned to libswscale for even heights >= 14 (tests/test_oracle_swscale.py)
-        set_error("stage: 10-bit 4:2:0 input / output needs an even height >= 14, interp trilinear / tetrahedral and no pc->tv pass");
-        return LUTR_ERR_UNSUPPORTED;
-    }
-    if (to_master && (d.width < 128 || d.interp == LUTR_INTERP_NEAREST)) {
-        set_error("stage: yuv420p->yuv422p10le needs width >= 128 and interp trilinear / tetrahedral");
-        return LUTR_ERR_UNSUPPORTED;
-    }
-    if (d.out_range != LUTR_RANGE_TV) {
-        set_error("stage: full-range output is not implemented (reference default tags=bt709 gives tv)");
-        return LUTR_ERR_UNSUPPORTED;
     }
     if (d.in_range == LUTR_RANGE_TV && d.norm_range != LUTR_RANGE_TV) {
         set_error("stage: norm_range must equal in_range for a tv source");
         return LUTR_ERR_INVALID_ARG;
     }
-    if (d.in_fmt == LUTR_PIX_YUV422P10LE && d.in_range == LUTR_RANGE_PC && d.norm_range == LUTR_RANGE_TV) {
-        // the reference's pc->tv pass always drops to 8-bit yuv4xxp (ffmpeg.py:137-143,233): a 10-bit in/out stage cannot express it
+    const bool range_pass = d.in_range == LUTR_RANGE_PC && d.norm_range == LUTR_RANGE_TV;
+    if (pix_depth(d.in_fmt) > 8 && range_pass) {
+        // the reference's pc->tv pass always drops to 8-bit yuv4xxp (ffmpeg.py:137-143,233): hand the stage that 8-bit format
         set_error("stage: pc->tv normalisation of a 10-bit source re-quantises to 8 bit in the reference; not implemented");
         return LUTR_ERR_UNSUPPORTED;
     }
-    // geometry the arithmetic model was pinned for against libswscale (tests/test_oracle_swscale.py)
+    // geometry the arithmetic models were pinned for against libswscale (tests/test_oracle_swscale.py)
     if ((d.width % 8) || d.width < 16 || d.width > 16384) {
         set_error("stage: width must be a multiple of 8 in [16, 16384]");
         return LUTR_ERR_UNSUPPORTED;
     }
-    if (d.in_fmt == LUTR_PIX_YUV420P && ((d.height % 2) || d.height < 12)) {
-        set_error("stage: yuv420p needs an even height >= 12");
+    const bool v420 = (pix_sub(d.in_fmt) | pix_sub(d.out_fmt)) & 2;  // a vertical chroma filter on either side
+    const int min_h = pix_depth(d.in_fmt) > 8 ? 14 : 12;
+    if (v420 && ((d.height % 2) || d.height < min_h)) {
+        set_error("stage: 4:2:0 input / output needs an even height >= %d", min_h);
         return LUTR_ERR_UNSUPPORTED;
     }
+    // combinations with a specialised warp-window kernel; everything else runs the generic tile kernel (k_any.cu)
+    const bool tri_tet = d.interp == LUTR_INTERP_TRILINEAR || d.interp == LUTR_INTERP_TETRAHEDRAL;
+    const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
+    const bool to_master = d.in_fmt == LUTR_PIX_YUV420P && d.out_fmt == LUTR_PIX_YUV422P10LE && d.width >= 128 && tri_tet;
+    const bool in10 = d.in_fmt == LUTR_PIX_YUV420P10LE || d.in_fmt == LUTR_PIX_YUV422P10LE;
+    const bool ordered10 = in10 && (d.in_fmt == LUTR_PIX_YUV420P10LE || d.out_fmt == LUTR_PIX_YUV420P10LE) &&
+                           (d.out_fmt == LUTR_PIX_YUV422P10LE || d.out_fmt == LUTR_PIX_YUV420P10LE) && tri_tet;
+    const bool specialised = d.out_range == LUTR_RANGE_TV && d.interp <= LUTR_INTERP_TETRAHEDRAL && (same_fmt || to_master || ordered10);
     CUDA_TRY(cudaSetDevice(ctx->device));
     lutr_stage *s = new (std::nothrow) lutr_stage;
     if (!s) return LUTR_ERR_NOMEM;
     s->ctx = ctx;
     s->d = d;
-    s->depth = d.in_fmt == LUTR_PIX_YUV420P ? 8 : 10;
+    s->depth = pix_depth(d.in_fmt);
+    s->any_only = !specialised;
     // YUV->RGB sees the range left by the normalisation pass
     make_yuv2rgb(d.in_matrix, d.norm_range == LUTR_RANGE_PC, s->f);
     make_rgb2yuv(d.out_matrix, s->b);
@@ -761,6 +765,7 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     if (!std::strcmp(name, "rows_per_cta")) s->rows_per_cta = value;
     else if (!std::strcmp(name, "band_rows")) s->band_rows = value;
     else if (!std::strcmp(name, "fast_path")) s->use_fast = value;
+    else if (!std::strcmp(name, "any_kernel")) s->force_any = value;
     else if (!std::strcmp(name, "grid_ctas")) s->grid_ctas = value;
     else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value < 0 || value > 3 ? 1 : value;
     else if (!std::strcmp(name, "host_chunk_mb")) {

@@ -75,6 +75,15 @@ struct FastK {
     int32_t maxv;                 // 2^depth - 1
 };
 
+// Parameters of the generic tile kernel (k_any.cu)
+struct AnyK {
+    int32_t in_sub, in_depth;    // log2 chroma subsampling (sx | sy << 1) and sample depth of the source
+    int32_t out_sub, out_depth;  // ... of the output
+    int32_t out_full;            // 1: full-range output (15-bit range conversion with the constants below)
+    int32_t in_lc, in_lo, in_cc, in_co;      // 8-bit pc -> tv pass: luma / chroma coefficient and offset
+    int32_t out_lc, out_lo, out_cc, out_co;  // tv -> pc on the output side (output depth)
+};
+
 struct StageK {
     int32_t w, h;
     int32_t nframes;
@@ -98,7 +107,20 @@ struct StageK {
     float wk_one;                // 1.0f the compiler cannot constant-fold (see addp2 in k422_warp.cu)
     int32_t wk_unroll;           // pass B double-iterations unrolled together (1, 2, 4)
     int32_t wk_nomin;            // 1: the clip of the LUT coordinate to lut_max can never bind (host-checked), drop it
+    AnyK any;                    // generic tile kernel only
 };
+
+// pixel format properties (lutr_pix_fmt ids)
+inline int pix_depth(int fmt) { return (fmt == LUTR_PIX_YUV422P10LE || fmt == LUTR_PIX_YUV420P10LE || fmt == LUTR_PIX_YUV444P10LE) ? 10 : 8; }
+inline int pix_sub(int fmt) {  // log2 chroma subsampling: sx | sy << 1
+    switch (fmt) {
+        case LUTR_PIX_YUV420P: case LUTR_PIX_YUV420P10LE: return 3;
+        case LUTR_PIX_YUV422P: case LUTR_PIX_YUV422P10LE: return 1;
+        default: return 0;
+    }
+}
+// swscale's 15-bit range conversion constants (colour_tables.cpp): out15 = min((in15 * coeff + offset) >> 14, 32767)
+void range_coeffs(int depth, bool to_jpeg, bool chroma, int32_t *coeff, int32_t *offset);
 
 // host-side construction of the index table (colour_tables.cpp): same float operations as lut3d's per-pixel prologue
 void build_index_table(int depth, int entries, float scale_times_lutmax, float lut_max, IdxEntry *out);
@@ -110,6 +132,7 @@ int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream);
 int launch_k420_warp(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);
 // 10-bit chains with a 4:2:0 side (k10_warp.cu): yuv420p10le in and / or yuv420p10le out
 int launch_k10_warp(const StageK &k, bool in420, bool out420, int interp, int float_mode, bool grid_forced, void *stream);
+int launch_k_any(const StageK &k, int interp, int float_mode, void *stream);  // generic tile kernel, the whole format matrix
 int launch_k420_warp10(const StageK &k, int interp, int float_mode, bool grid_forced, void *stream);  // yuv422p10le out
 
 }  // namespace lutr

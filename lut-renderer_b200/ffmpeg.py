@@ -21,7 +21,7 @@ from .media_info import VideoInfo
 from .models import ProcessingParams, Task
 
 LUT3D_INTERPS = ("nearest", "trilinear", "tetrahedral", "pyramid", "prism", "cubic")
-GPU_INTERPS = ("nearest", "trilinear", "tetrahedral")
+GPU_INTERPS = ("nearest", "trilinear", "tetrahedral", "pyramid", "prism")
 _TEN_BIT_ENCODERS = frozenset({"prores_ks", "libx265", "hevc_videotoolbox"})
 _FORCEABLE_MATRICES = ("bt709", "smpte170m", "bt470bg", "bt2020nc", "bt2020c")
 _BT709_TAGS = ["-color_primaries", "bt709", "-color_trc", "bt709", "-colorspace", "bt709", "-color_range", "tv"]

@@ -17,7 +17,7 @@ from typing import Dict, Optional, Tuple
 from . import _native as N
 from .ffmpeg import GPU_INTERPS, ColourStagePlan
 
-_FMT_BYTES_PER_PIXEL = {"yuv420p": 1.5, "yuv422p10le": 4.0, "yuv420p10le": 3.0}
+_FMT_BYTES_PER_PIXEL = {"yuv420p": 1.5, "yuv422p": 2.0, "yuv444p": 3.0, "yuv420p10le": 3.0, "yuv422p10le": 4.0, "yuv444p10le": 6.0}
 
 
 def frame_bytes(pix_fmt: str, width: int, height: int) -> int:

@@ -14,14 +14,15 @@ import numpy as np
 _KR, _KB = 0.2126, 0.0722  # BT.709 luma weights (content generation only; not part of the measured arithmetic)
 
 
+_SUBSAMPLING = {"yuv420p": (1, 1, 8), "yuv422p": (1, 0, 8), "yuv444p": (0, 0, 8),
+                "yuv420p10le": (1, 1, 10), "yuv422p10le": (1, 0, 10), "yuv444p10le": (0, 0, 10)}  # log2 sx, log2 sy, depth
+
+
 def plane_shapes(pix_fmt: str, w: int, h: int):
-    if pix_fmt == "yuv420p":
-        return [(h, w), (h // 2, w // 2), (h // 2, w // 2)], np.uint8
-    if pix_fmt == "yuv422p10le":
-        return [(h, w), (h, w // 2), (h, w // 2)], np.dtype("<u2")
-    if pix_fmt == "yuv420p10le":
-        return [(h, w), (h // 2, w // 2), (h // 2, w // 2)], np.dtype("<u2")
-    raise ValueError(pix_fmt)
+    if pix_fmt not in _SUBSAMPLING:
+        raise ValueError(pix_fmt)
+    sx, sy, depth = _SUBSAMPLING[pix_fmt]
+    return [(h, w), (h >> sy, w >> sx), (h >> sy, w >> sx)], (np.dtype("<u2") if depth > 8 else np.uint8)
 
 
 def split_planes(frame: np.ndarray, pix_fmt: str, w: int, h: int):
@@ -81,12 +82,9 @@ def _rgb_to_yuv_planes(rgb: np.ndarray, pix_fmt: str, full_range: bool):
         Y, U, V = yf * mx, uf * mx + 128 * s, vf * mx + 128 * s
     else:
         Y, U, V = (16 + 219 * yf) * s, (128 + 224 * uf) * s, (128 + 224 * vf) * s
-    if pix_fmt in ("yuv420p", "yuv420p10le"):
-        U = U.reshape(h // 2, 2, w // 2, 2).mean(axis=(1, 3))
-        V = V.reshape(h // 2, 2, w // 2, 2).mean(axis=(1, 3))
-    else:
-        U = U.reshape(h, w // 2, 2).mean(axis=2)
-        V = V.reshape(h, w // 2, 2).mean(axis=2)
+    sx, sy, _ = _SUBSAMPLING[pix_fmt]
+    U = U.reshape(h >> sy, 1 << sy, w >> sx, 1 << sx).mean(axis=(1, 3))
+    V = V.reshape(h >> sy, 1 << sy, w >> sx, 1 << sx).mean(axis=(1, 3))
     dt = np.dtype("<u2") if depth > 8 else np.uint8
     q = lambda a: np.clip(np.rint(a), 0, (1 << depth) - 1).astype(dt)  # noqa: E731
     return [q(Y), q(U), q(V)]

@@ -39,12 +39,7 @@ class CpuStage:
     def run(self, planes):
         Y, U, V = planes
         if not self.use_swscale:
-            if "10" in self.pix_fmt:
-                return O.stage_10bit(self.lut, Y, U, V, self.pix_fmt == "yuv420p10le", self.out_pix_fmt == "yuv420p10le", self.interp,
-                                     self.in_matrix, False, self.out_matrix)
-            if self.out_pix_fmt == "yuv422p10le":
-                return O.stage_yuv420p_to_yuv422p10(self.lut, Y, U, V, self.interp, False, self.in_matrix, False, self.out_matrix)
-            return O.stage_yuv420p(self.lut, Y, U, V, self.interp, False, self.in_matrix, False, self.out_matrix)
+            return O.stage_any(self.lut, self.pix_fmt, self.out_pix_fmt, Y, U, V, self.interp, False, self.in_matrix, False, self.out_matrix)
         self.fwd.convert([Y, U, V], self.mid)
         if "10" in self.pix_fmt:
             g, b, r = self.mid

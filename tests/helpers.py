@@ -7,20 +7,13 @@ from lut_renderer_b200 import synth
 
 
 def oracle_stage(pix_fmt, w, h, frame, lut, interp="tetrahedral", in_matrix="bt709", out_matrix="bt709",
-                 in_range="tv", norm_range=None, out_pix_fmt=None):
+                 in_range="tv", norm_range=None, out_pix_fmt=None, out_range="tv"):
     """Packed frame in -> packed frame out through oracle/ (CPU restatement of the FFmpeg chain)."""
     from oracle import oracle as O
     norm_range = norm_range or in_range
     Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(frame, pix_fmt, w, h)]
-    if pix_fmt == "yuv420p" and out_pix_fmt == "yuv422p10le":
-        out = O.stage_yuv420p_to_yuv422p10(lut, Y, U, V, interp=interp, range_pass=(in_range == "pc" and norm_range == "tv"),
-                                           in_matrix=in_matrix, in_full_range=(norm_range == "pc"), out_matrix=out_matrix)
-    elif pix_fmt in ("yuv420p10le", "yuv422p10le"):
-        out = O.stage_10bit(lut, Y, U, V, in_420=(pix_fmt == "yuv420p10le"), out_420=((out_pix_fmt or pix_fmt) == "yuv420p10le"),
-                            interp=interp, in_matrix=in_matrix, in_full_range=(norm_range == "pc"), out_matrix=out_matrix)
-    else:
-        out = O.stage_yuv420p(lut, Y, U, V, interp=interp, range_pass=(in_range == "pc" and norm_range == "tv"),
-                              in_matrix=in_matrix, in_full_range=(norm_range == "pc"), out_matrix=out_matrix)
+    out = O.stage_any(lut, pix_fmt, out_pix_fmt or pix_fmt, Y, U, V, interp=interp, range_pass=(in_range == "pc" and norm_range == "tv"),
+                      in_matrix=in_matrix, in_full_range=(norm_range == "pc"), out_matrix=out_matrix, out_full_range=(out_range == "pc"))
     return synth.pack_planes(out)
 
 

@@ -69,8 +69,11 @@ def test_no_cpu_fallback_without_a_device():
 def test_unsupported_requests_are_named_before_touching_the_device():
     from lut_renderer_b200.stage import ColourStage
     with pytest.raises(N.LutrError) as e:
-        ColourStage(64, 16, "yuv420p", interp="pyramid")
+        ColourStage(64, 16, "yuv420p", interp="cubic")        # in the reference's whitelist, not a lut3d mode (ffmpeg.py:243)
     assert e.value.status == N.ERR_UNSUPPORTED
     with pytest.raises(N.LutrError) as e:
-        ColourStage(64, 16, "yuv444p")
+        ColourStage(64, 16, "yuv440p")
     assert e.value.status == N.ERR_UNSUPPORTED
+    # every layout / interp of the operator maps to an enum of include/lutr.h
+    assert set(N.PIX_FMT) == {"yuv420p", "yuv422p", "yuv444p", "yuv420p10le", "yuv422p10le", "yuv444p10le"}
+    assert set(N.INTERP) == {"nearest", "trilinear", "tetrahedral", "pyramid", "prism"}

@@ -396,3 +396,79 @@ def test_fma_mode_is_within_one_code():
     for x, y in zip(a, b):
         d = np.abs(x.view("<u2").astype(int) - y.view("<u2").astype(int))
         assert d.max() <= 1 and (d == 0).mean() > 0.99
+
+
+# ---- the generic tile kernel (k_any.cu): the whole format matrix of the operator -------------------------------------------------
+ALL_FMTS = ["yuv420p", "yuv422p", "yuv444p", "yuv420p10le", "yuv422p10le", "yuv444p10le"]
+
+
+@pytest.mark.parametrize("in_fmt", ALL_FMTS)
+@pytest.mark.parametrize("out_fmt", ALL_FMTS)
+@pytest.mark.parametrize("out_range", ["tv", "pc"])
+def test_any_format_matrix(in_fmt, out_fmt, out_range):
+    """Every source layout x every output layout / depth x both output ranges through ONE launch of the generic tile kernel
+    (forced with any_kernel=1 where a specialised kernel exists): 8-bit sources go through rgb24, 10-bit through gbrp10le; the
+    10 -> 8 bit outputs carry swscale's ordered dither.  Geometry: two tile columns with a ragged right tile, three tile rows."""
+    w, h = 200, 70 if "420" not in in_fmt + out_fmt else 72
+    table = synth.look_lut(17).astype(np.float32)
+    frames = _frames(in_fmt, w, h, ["natural", "noise", "extremes"])
+    got = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt, out_range=out_range, options=dict(any_kernel=1))
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        exp = oracle_stage(in_fmt, w, h, f, L, out_pix_fmt=out_fmt, out_range=out_range)
+        assert_bit_exact(out_fmt, w, h, got[i], exp, f"{in_fmt}->{out_fmt} {out_range} frame {i}")
+
+
+@pytest.mark.parametrize("interp", ["nearest", "trilinear", "tetrahedral", "pyramid", "prism"])
+@pytest.mark.parametrize("in_fmt,out_fmt", [("yuv420p", "yuv444p"), ("yuv422p10le", "yuv420p"), ("yuv444p10le", "yuv422p10le")])
+def test_any_interps_and_domain_scales(interp, in_fmt, out_fmt):
+    """All five interpolation modes of the reference's whitelist (ffmpeg.py:243) incl. pyramid / prism, a LUT that leaves [0,1]
+    and per-channel DOMAIN scales (the fast kernels need one common scale)."""
+    w, h = 136, 36
+    table = (synth.random_lut(9, 4) * 1.6 - 0.3).astype(np.float32)
+    frames = _frames(in_fmt, w, h, ["noise", "ramp"])
+    for scale in ((1.0, 1.0, 1.0), (0.5, 1.0, 0.25)):
+        got = gpu_stage(in_fmt, w, h, frames, table, scale=scale, out_pix_fmt=out_fmt, interp=interp)
+        L = oracle_lut(table, scale)
+        for i, f in enumerate(frames):
+            exp = oracle_stage(in_fmt, w, h, f, L, out_pix_fmt=out_fmt, interp=interp)
+            assert_bit_exact(out_fmt, w, h, got[i], exp, f"{in_fmt}->{out_fmt} {interp} scale {scale} frame {i}")
+
+
+@pytest.mark.parametrize("in_fmt", ["yuv420p", "yuv422p", "yuv444p"])
+@pytest.mark.parametrize("kw", [dict(in_range="pc", norm_range="tv"), dict(in_range="pc", norm_range="pc", out_range="pc"),
+                                dict(in_range="pc", norm_range="tv", in_matrix="bt601", out_matrix="bt2020")])
+def test_any_range_pass_and_matrices(in_fmt, kw):
+    """The reference's full-range chains (ffmpeg.py:211-233): pc -> tv pass re-quantised to the 8-bit layout of the source
+    (tags=bt709), and the pass-through pc -> pc chain with a full-range output (tags=inherit / none)."""
+    w, h = 264, 40
+    table = synth.look_lut(33).astype(np.float32)
+    frames = _frames(in_fmt, w, h, ["natural", "extremes"])
+    got = gpu_stage(in_fmt, w, h, frames, table, options=dict(any_kernel=1), **kw)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        assert_bit_exact(in_fmt, w, h, got[i], oracle_stage(in_fmt, w, h, f, L, **kw), f"{in_fmt} {kw} frame {i}")
+
+
+@pytest.mark.parametrize("in_fmt,out_fmt,w,h", [("yuv422p10le", "yuv420p", 1920, 1080), ("yuv420p", "yuv444p", 1920, 1080),
+                                                ("yuv444p10le", "yuv420p10le", 1280, 720), ("yuv420p10le", "yuv420p", 3840, 2160)])
+def test_any_full_frames(in_fmt, out_fmt, w, h):
+    """Full delivery frames: e.g. a 10-bit camera source to 8-bit H.264 (yuv420p for non-10-bit codecs, ffmpeg.py:299-302)."""
+    table = synth.look_lut(33).astype(np.float32)
+    frames = [synth.natural_frame(in_fmt, w, h, t=2), synth.noise_frame(in_fmt, w, h, seed=8)]
+    got = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        assert_bit_exact(out_fmt, w, h, got[i], oracle_stage(in_fmt, w, h, f, L, out_pix_fmt=out_fmt), f"{in_fmt}->{out_fmt} frame {i}")
+
+
+def test_any_kernel_agrees_with_specialised_kernels():
+    """The generic tile kernel and the warp-window kernels are independent implementations of the same stage: identical bytes."""
+    table = synth.look_lut(65).astype(np.float32)
+    for in_fmt, out_fmt, w, h in (("yuv422p10le", "yuv422p10le", 496, 38), ("yuv420p", "yuv420p", 512, 40),
+                                  ("yuv420p", "yuv422p10le", 328, 22), ("yuv420p10le", "yuv420p10le", 488, 30)):
+        frames = _frames(in_fmt, w, h, ["natural", "noise"])
+        a = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt)
+        b = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt, options=dict(any_kernel=1))
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), (in_fmt, out_fmt)
