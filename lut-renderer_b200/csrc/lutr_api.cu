@@ -317,6 +317,16 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     const bool mixed = s->d.in_fmt != s->d.out_fmt;
     if (s->any_only || s->force_any) {
         rc = run_any();
+    } else if (s->depth == 10 && s->d.out_fmt == LUTR_PIX_YUV420P) {
+        if (!warp_kernel) {
+            rc = run_any();
+        } else {
+            k.rows_per_cta = 0, k.bands = 1;
+            k.grid_ctas = s->grid_ctas;
+            k.min_blocks = s->wk_minb;
+            rc = launch_k10_warp8(k, s->d.in_fmt == LUTR_PIX_YUV420P10LE, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = s->d.in_fmt == LUTR_PIX_YUV420P10LE ? "k10_warp8<420>" : "k10_warp8<422>";
+        }
     } else if (s->d.in_fmt == LUTR_PIX_YUV420P10LE || s->d.out_fmt == LUTR_PIX_YUV420P10LE) {
         if (!warp_kernel) {
             rc = run_any();
@@ -611,8 +621,9 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
     const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
     const bool to_master = d.in_fmt == LUTR_PIX_YUV420P && d.out_fmt == LUTR_PIX_YUV422P10LE && d.width >= 128 && tri_tet;
     const bool in10 = d.in_fmt == LUTR_PIX_YUV420P10LE || d.in_fmt == LUTR_PIX_YUV422P10LE;
-    const bool ordered10 = in10 && (d.in_fmt == LUTR_PIX_YUV420P10LE || d.out_fmt == LUTR_PIX_YUV420P10LE) &&
-                           (d.out_fmt == LUTR_PIX_YUV422P10LE || d.out_fmt == LUTR_PIX_YUV420P10LE) && tri_tet;
+    const bool ordered10 = in10 && tri_tet &&
+                           ((d.in_fmt == LUTR_PIX_YUV420P10LE && d.out_fmt == LUTR_PIX_YUV422P10LE) || d.out_fmt == LUTR_PIX_YUV420P10LE ||
+                            d.out_fmt == LUTR_PIX_YUV420P);  // (10-bit source -> 8-bit 4:2:0 delivery: k10_warp8.cu)
     const bool specialised = d.out_range == LUTR_RANGE_TV && d.interp <= LUTR_INTERP_TETRAHEDRAL && (same_fmt || to_master || ordered10);
     CUDA_TRY(cudaSetDevice(ctx->device));
     lutr_stage *s = new (std::nothrow) lutr_stage;

@@ -472,3 +472,23 @@ def test_any_kernel_agrees_with_specialised_kernels():
         b = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt, options=dict(any_kernel=1))
         for x, y in zip(a, b):
             assert np.array_equal(x, y), (in_fmt, out_fmt)
+
+
+@pytest.mark.parametrize("pix_fmt", ["yuv420p10le", "yuv422p10le"])
+@pytest.mark.parametrize("w,h,options", [(16, 14, dict()), (240, 16, dict()), (248, 18, dict()), (488, 30, dict(grid_ctas=1)),
+                                         (728, 54, dict(grid_ctas=2)), (1928, 22, dict()), (656, 38, dict(grid_ctas=7)),
+                                         (512, 64, dict(grid_ctas=5))])
+@pytest.mark.parametrize("interp,lut_name,kw", [("tetrahedral", "look65", dict()), ("tetrahedral", "rand64", dict(out_matrix="bt601")),
+                                                ("trilinear", "look33", dict(in_matrix="bt2020", out_matrix="bt2020")),
+                                                ("tetrahedral", "wide9", dict(in_range="pc", norm_range="pc"))])
+def test_10bit_to_yuv420p_8bit_delivery(pix_fmt, w, h, options, interp, lut_name, kw):
+    """A 10-bit source delivered as 8-bit yuv420p (the reference's choice for codecs without 10-bit support, e.g. the default
+    libx264: ffmpeg.py:299-302): gbrp10le intermediate, swscale's ordered dither on luma and chroma (V shifted by 3 columns),
+    per-tap truncating vertical scaler with folded edge taps and the exact C-path last row.  Warp-window kernel k10_warp8."""
+    table = (LUTS[lut_name]() if lut_name in LUTS else synth.random_lut(9, 4) * 1.6 - 0.3).astype(np.float32)
+    frames = _frames(pix_fmt, w, h, ["natural", "noise", "extremes", "ramp"])
+    got = gpu_stage(pix_fmt, w, h, frames, table, interp=interp, out_pix_fmt="yuv420p", options=options, **kw)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        exp = oracle_stage(pix_fmt, w, h, f, L, interp=interp, out_pix_fmt="yuv420p", **kw)
+        assert_bit_exact("yuv420p", w, h, got[i], exp, f"{pix_fmt}->420p8 {w}x{h} {options} {interp} {lut_name} frame {i}")
