@@ -346,10 +346,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--in-fmt", default="", help="override the source layout of --config (any layout of include/lutr.h)")
+    ap.add_argument("--out-fmt", default="", help="override the output layout of --config")
+    ap.add_argument("--interp", default="", help="override the interpolation mode of --config")
     args = ap.parse_args()
     if args.config == "cfg5":
         return run_cfg5(args)
     cfg = dict(CONFIGS[args.config])
+    if args.in_fmt or args.out_fmt or args.interp:  # other cells of the format matrix at this config's geometry
+        cfg["pix_fmt"] = args.in_fmt or cfg["pix_fmt"]
+        cfg["out_pix_fmt"] = args.out_fmt or cfg.get("out_pix_fmt", cfg["pix_fmt"])
+        cfg["interp"] = args.interp or cfg["interp"]
+        cfg["desc"] = f"{cfg['w']}x{cfg['h']} {cfg['pix_fmt']} -> {cfg['lut']}-point look .cube, {cfg['interp']} -> {cfg['out_pix_fmt']}"
+        args.config = f"{args.config}[{cfg['pix_fmt']}->{cfg['out_pix_fmt']},{cfg['interp']}]"
     if args.frames_per_step:
         cfg["frames_per_step"] = args.frames_per_step
     rank = int(os.environ.get("RANK", "0"))

@@ -492,3 +492,37 @@ def test_10bit_to_yuv420p_8bit_delivery(pix_fmt, w, h, options, interp, lut_name
     for i, f in enumerate(frames):
         exp = oracle_stage(pix_fmt, w, h, f, L, interp=interp, out_pix_fmt="yuv420p", **kw)
         assert_bit_exact("yuv420p", w, h, got[i], exp, f"{pix_fmt}->420p8 {w}x{h} {options} {interp} {lut_name} frame {i}")
+
+
+@pytest.mark.parametrize("in_fmt,out_fmt,w,h,options", [
+    ("yuv422p10le", "yuv422p10le", 488, 10, dict()), ("yuv420p", "yuv420p", 328, 22, dict(grid_ctas=2)),
+    ("yuv420p", "yuv422p10le", 328, 22, dict(grid_ctas=2)), ("yuv420p10le", "yuv422p10le", 488, 30, dict(grid_ctas=2)),
+    ("yuv420p10le", "yuv420p10le", 488, 30, dict(grid_ctas=2)), ("yuv422p10le", "yuv420p10le", 488, 30, dict(grid_ctas=3)),
+    ("yuv420p10le", "yuv420p", 488, 30, dict(grid_ctas=2)), ("yuv422p10le", "yuv420p", 496, 30, dict(grid_ctas=5)),
+    ("yuv444p", "yuv420p10le", 200, 36, dict()), ("yuv420p10le", "yuv444p", 200, 36, dict()),
+    ("yuv422p10le", "yuv422p10le", 256, 6, dict(fast_path=0)), ("yuv422p10le", "yuv422p10le", 256, 6, dict(idx_mode=2)),
+    ("yuv420p", "yuv420p", 64, 14, dict())])
+def test_no_kernel_writes_outside_its_frames(in_fmt, out_fmt, w, h, options):
+    """Guard bands around the output batch stay untouched for every kernel family (compute-sanitizer is not available on this
+    pool): the frames sit inside a larger buffer filled with a sentinel, 4 KB before and after."""
+    import torch
+    from lut_renderer_b200.stage import ColourStage
+    table = synth.look_lut(17).astype(np.float32)
+    frames = [synth.noise_frame(in_fmt, w, h, seed=s) for s in (1, 2, 3)]
+    st = ColourStage(w, h, in_fmt, out_pix_fmt=out_fmt)
+    for k, v in options.items():
+        st.set_option(k, v)
+    lut = st.ctx.lut_from_table(table)
+    guard, n = 4096, len(frames)
+    src = torch.from_numpy(np.concatenate(frames)).cuda()
+    buf = torch.full((guard + n * st.out_frame_bytes + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    st.run(lut, src, buf[guard:guard + n * st.out_frame_bytes], n, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    out = buf.cpu().numpy()
+    assert (out[:guard] == 0xA5).all() and (out[-guard:] == 0xA5).all()
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        got = out[guard + i * st.out_frame_bytes: guard + (i + 1) * st.out_frame_bytes]
+        assert_bit_exact(out_fmt, w, h, got, oracle_stage(in_fmt, w, h, f, L, out_pix_fmt=out_fmt), f"{in_fmt}->{out_fmt} frame {i}")
+    st.close()
+    lut.close()
