@@ -16,7 +16,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <thread>
 
 #include "lutr_internal.h"
 
@@ -41,6 +43,7 @@ class LineReader {
         buf[n] = 0;
         return true;
     }
+    const char *pos() const { return p_; }
 
   private:
     const char *p_, *end_;
@@ -99,6 +102,108 @@ float clip01_recip(float mn, float mx) {
     return m > 1.f ? 1.f : m;
 }
 
+// ---- parallel data section ---------------------------------------------------------------------------------------------------
+// A 65-point .cube is 7 MB of text (824 k numbers); one core parses it in ~20 ms, which is as long as the GPU needs for 24 4K frames
+// (BASELINE cfg 5: per-clip LUTs).  The data section is cut at line boundaries into one piece per thread; every piece applies the
+// sequential rules line by line.  Anything the sequential reader would treat specially in a position-dependent way (a line longer
+// than the 511-byte fgets window, a malformed or non-finite data line, too few entries) makes the caller fall back to the
+// sequential reader, so accepted files give identical tables and rejected files identical errors.
+struct DomainLine {
+    size_t entries_before;  // data entries of this piece in front of the line
+    bool is_max;
+    int count;
+    float v[3];
+};
+struct Piece {
+    const char *begin = nullptr, *end = nullptr;
+    std::vector<float> vals;  // 3 per entry, file order
+    std::vector<DomainLine> domains;
+    bool anomaly = false;
+};
+
+void parse_piece(Piece &pc) {
+    const char *p = pc.begin;
+    pc.vals.reserve((size_t)(pc.end - pc.begin) / 8);
+    char buf[512];
+    while (p < pc.end) {
+        const char *nl = (const char *)std::memchr(p, '\n', (size_t)(pc.end - p));
+        const char *le = nl ? nl + 1 : pc.end;
+        const size_t len = (size_t)(le - p);
+        if (len > 511) {
+            pc.anomaly = true;
+            return;
+        }
+        std::memcpy(buf, p, len);
+        buf[len] = 0;
+        p = le;
+        if (buf[0] == 'D' && starts_with(buf, "DOMAIN_")) {
+            DomainLine d{};
+            if (starts_with(buf + 7, "MIN ")) d.is_max = false;
+            else if (starts_with(buf + 7, "MAX ")) d.is_max = true;
+            else {
+                pc.anomaly = true;
+                return;
+            }
+            d.entries_before = pc.vals.size() / 3;
+            d.count = scan3(buf + 11, d.v);
+            pc.domains.push_back(d);
+            continue;
+        }
+        if (buf[0] == 'T' && starts_with(buf, "TITLE")) continue;
+        if (is_blank_or_comment(buf)) continue;
+        float v[3];
+        if (scan3(buf, v) != 3 || !std::isfinite(v[0]) || !std::isfinite(v[1]) || !std::isfinite(v[2])) {
+            pc.anomaly = true;
+            return;
+        }
+        pc.vals.push_back(v[0]), pc.vals.push_back(v[1]), pc.vals.push_back(v[2]);
+    }
+}
+
+// Fills file_order (n^3 entries, file order) and the domain from [begin, end); false = let the sequential reader decide.
+bool parse_data_parallel(const char *begin, const char *end, size_t entries, std::vector<float> &file_order, float dmin[3], float dmax[3]) {
+    const size_t bytes = (size_t)(end - begin);
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = hw > 8 ? 8 : hw;
+    if (bytes < (256u << 10) || nt < 2) return false;
+    std::vector<Piece> pieces(nt);
+    const char *p = begin;
+    for (unsigned i = 0; i < nt; ++i) {
+        pieces[i].begin = p;
+        const char *q = i + 1 == nt ? end : begin + bytes * (i + 1) / nt;
+        if (q < p) q = p;
+        if (q < end) {
+            const char *nl = (const char *)std::memchr(q, '\n', (size_t)(end - q));
+            q = nl ? nl + 1 : end;
+        }
+        pieces[i].end = q;
+        p = q;
+    }
+    std::vector<std::thread> threads;
+    for (unsigned i = 1; i < nt; ++i) threads.emplace_back(parse_piece, std::ref(pieces[i]));
+    parse_piece(pieces[0]);
+    for (std::thread &t : threads) t.join();
+    size_t total = 0;
+    for (const Piece &pc : pieces) {
+        if (pc.anomaly) return false;
+        total += pc.vals.size() / 3;
+    }
+    if (total < entries) return false;  // unexpected EOF: the sequential reader words the error
+    size_t base = 0;
+    for (const Piece &pc : pieces) {
+        // DOMAIN lines the sequential reader would still have read: those in front of the last entry it needs
+        for (const DomainLine &d : pc.domains)
+            if (base + d.entries_before < entries)
+                for (int k = 0; k < d.count; ++k) (d.is_max ? dmax : dmin)[k] = d.v[k];
+        if (base < entries) {
+            const size_t take = std::min(pc.vals.size() / 3, entries - base);
+            std::memcpy(&file_order[3 * base], pc.vals.data(), take * 3 * sizeof(float));
+        }
+        base += pc.vals.size() / 3;
+    }
+    return true;
+}
+
 }  // namespace
 
 void set_error(const char *fmt, ...) {
@@ -143,7 +248,11 @@ int parse_cube(const char *text, size_t len, CubeLut &out) {
     // entry costs a cache miss each on a 65-point table)
     std::vector<float> file_order(n2 * n * 3);
 
-    for (size_t b = 0; b < n; ++b)
+    float pmin[3] = {0.f, 0.f, 0.f}, pmax[3] = {1.f, 1.f, 1.f};
+    const bool parallel_ok = parse_data_parallel(rd.pos(), text + len, n2 * n, file_order, pmin, pmax);
+    if (parallel_ok)
+        for (int c = 0; c < 3; ++c) dmin[c] = pmin[c], dmax[c] = pmax[c];
+    for (size_t b = 0; b < n && !parallel_ok; ++b)
         for (size_t g = 0; g < n; ++g)
             for (size_t r = 0; r < n; ++r) {
                 for (;;) {

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "lutr_internal.h"
 
@@ -17,6 +19,10 @@ struct lutr_ctx {
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
     size_t l2_bytes = 0, persist_max = 0;
+    // freed LUT buffers, kept for the next upload of the same size (a batch queue with per-clip LUTs would otherwise pay a
+    // cudaMalloc + cudaFree per clip: 3-4 ms, as long as the GPU needs for five 4K frames)
+    std::mutex pool_mu;
+    std::vector<std::pair<size_t, void *>> pool;
 };
 
 struct lutr_lut {
@@ -125,7 +131,16 @@ int upload_lut(lutr_ctx *ctx, const CubeLut &c, lutr_lut **out) {
             if (c.rgb[3 * i + ch] < 0.f || c.rgb[3 * i + ch] > 1.f) l->needs_clamp = true;
     }
     l->dev_bytes = host.size() * sizeof(float4);
-    cudaError_t e = cudaMalloc((void **)&l->dev, l->dev_bytes);
+    {
+        std::lock_guard<std::mutex> lock(ctx->pool_mu);
+        for (size_t i = 0; i < ctx->pool.size(); ++i)
+            if (ctx->pool[i].first == l->dev_bytes) {
+                l->dev = (float4 *)ctx->pool[i].second;
+                ctx->pool.erase(ctx->pool.begin() + (long)i);
+                break;
+            }
+    }
+    cudaError_t e = l->dev ? cudaSuccess : cudaMalloc((void **)&l->dev, l->dev_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(l->dev, host.data(), l->dev_bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         set_error("lut upload: %s", cudaGetErrorString(e));
@@ -514,7 +529,14 @@ int lutr_ctx_create(int32_t device, lutr_ctx **out) {
     return LUTR_OK;
 }
 
-void lutr_ctx_destroy(lutr_ctx *ctx) { delete ctx; }
+void lutr_ctx_destroy(lutr_ctx *ctx) {
+    if (!ctx) return;
+    if (!ctx->pool.empty()) {
+        cudaSetDevice(ctx->device);
+        for (auto &b : ctx->pool) cudaFree(b.second);
+    }
+    delete ctx;
+}
 
 int lutr_ctx_info(const lutr_ctx *ctx, int32_t *device, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor) {
     if (!ctx) return LUTR_ERR_INVALID_ARG;
@@ -575,7 +597,11 @@ void lutr_lut_destroy(lutr_lut *lut) {
     if (!lut) return;
     if (lut->dev) {
         cudaSetDevice(lut->ctx->device);
-        cudaFree(lut->dev);
+        // like cudaFree, wait for whatever still reads the table; then keep the buffer for the next LUT of this size
+        cudaDeviceSynchronize();
+        std::lock_guard<std::mutex> lock(lut->ctx->pool_mu);
+        if (lut->ctx->pool.size() < 8) lut->ctx->pool.emplace_back(lut->dev_bytes, (void *)lut->dev);
+        else cudaFree(lut->dev);
     }
     delete lut;
 }

@@ -62,6 +62,22 @@ class DeviceContext:
                 self._luts[key] = lut
         return lut
 
+    def prefetch_lut(self, path, cached: bool = True):
+        """Start parsing + uploading a .cube on a background thread (the C calls release the GIL) and return a Future of the
+        DeviceLut: a batch queue loads the next clip's LUT while the GPU works on the current clip.  cached=False always
+        re-reads the file (a private LUT the caller closes itself)."""
+        with self._lock:
+            if getattr(self, "_pool", None) is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="lutr-lut")
+        if cached:
+            return self._pool.submit(self.lut_from_cube, path)
+
+        def load():
+            with open(path, "rb") as f:
+                return self.lut_from_text(f.read())
+        return self._pool.submit(load)
+
     def lut_from_text(self, text) -> "DeviceLut":
         data = text if isinstance(text, (bytes, bytearray)) else str(text).encode()
         h = c_void_p()

@@ -95,3 +95,34 @@ def test_parse_file(tmp_path):
     assert size.value == 5
     N.lib().lutr_free(tab)
     assert N.lib().lutr_cube_parse_file(str(tmp_path / "missing.cube").encode(), ctypes.byref(size), scale, ctypes.byref(tab)) == N.ERR_IO
+
+
+def test_large_files_take_the_parallel_reader_with_identical_results():
+    """Files above 256 KB are parsed by several threads (pieces cut at line boundaries); every dialect corner must come out as
+    from the sequential reader: DOMAIN lines in the middle of the data (also across pieces), a DOMAIN line / garbage behind the
+    last entry (never read), comments and blank lines, CRLF, and the error cases (which fall back to the sequential reader)."""
+    t = synth.random_lut(40, 6).astype(np.float32)              # 64 000 entries, ~1.7 MB of text
+    lines = synth.cube_text(t).split("\n")
+    k = len(lines) // 2
+    both("\n".join(lines))
+    mixed = lines[:]
+    mixed.insert(k, "DOMAIN_MAX 2.0 4.0 1.0")
+    mixed.insert(k + 5000, "# a comment in the data")
+    mixed.insert(k + 9000, "")
+    mixed.insert(30, "DOMAIN_MIN 0.5 0 0")
+    mixed.insert(k + 20000, 'TITLE "late title"')
+    size, scale, _ = both("\n".join(mixed) + "\nDOMAIN_MAX 9 9 9\nthis is not a data line\n")
+    assert size == 40 and [round(float(s), 6) for s in scale] == [0.666667, 0.25, 1.0]
+    both("\r\n".join(lines))
+    bad = lines[:]
+    bad[k + 100] = "0.1 oops 0.3"
+    fails("\n".join(bad), N.ERR_INVALID_DATA)
+    fails("\n".join(lines[:k]), N.ERR_INVALID_DATA)               # unexpected EOF
+    bad = lines[:]
+    bad[k] = "DOMAIN_MID 0 0 0"
+    fails("\n".join(bad), N.ERR_INVALID_DATA)
+    long_line = lines[:]
+    long_line[k] = " " * 600 + long_line[k]                       # crosses the 511-byte fgets window: sequential rules apply
+    size, scale, table = N.parse_cube_text("\n".join(long_line))
+    ref = O.OracleLut.from_text("\n".join(long_line))
+    assert np.array_equal(table, ref.table)

@@ -1,0 +1,81 @@
+"""Operator surface -> pixels: ProcessingParams + VideoInfo exactly as the reference's GUI / TaskRunner would hold them
+(reference models.py:19-56, media_info.py:12-36) -> plan_colour_stage -> ColourStage.from_plan -> GPU, checked against the
+oracle driven by the same plan.  One case per decision branch of build_command's colour block (ffmpeg.py:196-247, 287-310,
+348-383)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from lut_renderer_b200 import ProcessingParams, VideoInfo, plan_colour_stage, synth
+
+from helpers import assert_bit_exact, oracle_lut, oracle_stage
+
+pytestmark = pytest.mark.gpu
+
+W, H = 264, 40
+
+
+def _info(pix_fmt, depth, colorspace="bt709", color_range="tv"):
+    return VideoInfo(width=W, height=H, pix_fmt=pix_fmt, bit_depth=depth, colorspace=colorspace, color_range=color_range, fps=25.0)
+
+
+CASES = {
+    # fast delivery, defaults: 8-bit source, libx264, nothing forced -> the stage hands back the working layout
+    "default_8bit": (_info("yuv420p", 8), ProcessingParams(), ("yuv420p", "yuv420p", "tv", "tv", "tv", "tetrahedral")),
+    # BASELINE cfg 2: full-range source, forced bt709, trilinear, force_8bit
+    "cfg2_pc_to_tv": (_info("yuvj420p", 8, "bt470bg", "pc"),
+                      ProcessingParams(bit_depth_policy="force_8bit", lut_interp="trilinear", lut_input_matrix="bt709"),
+                      ("yuv420p", "yuv420p", "pc", "tv", "tv", "trilinear")),
+    # 4:2:2 full-range source: the range pass lands on yuv422p (ffmpeg.py:137-143); user asks for yuv444p out
+    "pc_422_to_444": (_info("yuvj422p", 8, "bt709", "pc"), ProcessingParams(pix_fmt="yuv444p"),
+                      ("yuv422p", "yuv444p", "pc", "tv", "tv", "tetrahedral")),
+    # tags=inherit keeps a pc source pc through the stage and out of it
+    "inherit_pc": (_info("yuvj420p", 8, "bt709", "pc"), ProcessingParams(lut_output_tags="inherit", pix_fmt="yuv420p"),
+                   ("yuv420p", "yuv420p", "pc", "pc", "pc", "tetrahedral")),
+    # 10-bit source through the default libx264: no 10-bit support -> yuv420p with swscale's ordered dither (ffmpeg.py:299-302)
+    "hevc10_to_x264": (_info("yuv420p10le", 10), ProcessingParams(), ("yuv420p10le", "yuv420p", "tv", "tv", "tv", "tetrahedral")),
+    # 10-bit source, libx265 preserve -> yuv420p10le (ffmpeg.py:297-298)
+    "hevc10_to_x265": (_info("yuv420p10le", 10), ProcessingParams(video_codec="libx265"),
+                       ("yuv420p10le", "yuv420p10le", "tv", "tv", "tv", "tetrahedral")),
+    "c422_10_to_x265": (_info("yuv422p10le", 10), ProcessingParams(video_codec="libx265"),
+                        ("yuv422p10le", "yuv420p10le", "tv", "tv", "tv", "tetrahedral")),
+    # pro-mode master parameters (ffmpeg.py:417-433) on 10-bit 4:2:2 and 4:4:4 sources
+    "master_422": (_info("yuv422p10le", 10), ProcessingParams(video_codec="prores_ks"),
+                   ("yuv422p10le", "yuv422p10le", "tv", "tv", "tv", "tetrahedral")),
+    "master_444": (_info("yuv444p10le", 10, "bt2020nc"), ProcessingParams(video_codec="prores_ks"),
+                   ("yuv444p10le", "yuv422p10le", "tv", "tv", "tv", "tetrahedral")),
+    # interp outside the GUI's two choices but inside the reference's whitelist (ffmpeg.py:243)
+    "prism_8bit": (_info("yuv420p", 8), ProcessingParams(lut_interp="prism", pix_fmt="yuv422p"),
+                   ("yuv420p", "yuv422p", "tv", "tv", "tv", "prism")),
+    # untagged output: swscale's default (BT.601) matrix behind the LUT
+    "tags_none": (_info("yuv420p", 8, "smpte170m"), ProcessingParams(lut_output_tags="none", pix_fmt="yuv420p"),
+                  ("yuv420p", "yuv420p", "tv", "tv", "tv", "tetrahedral")),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_reference_options_to_pixels(name, tmp_path):
+    from lut_renderer_b200.stage import ColourStage, DeviceContext
+    import torch
+    info, params, expect = CASES[name]
+    table = synth.look_lut(17).astype(np.float32)
+    cube = tmp_path / "look.cube"
+    synth.write_cube(cube, table)
+    plan = plan_colour_stage(params, Path(cube), info)
+    assert (plan.in_pix_fmt, plan.out_pix_fmt, plan.in_range, plan.norm_range, plan.out_range, plan.interp) == expect
+    st = ColourStage.from_plan(plan)
+    lut = DeviceContext.get(0).lut_from_cube(plan.lut_path)
+    frames = [synth.natural_frame(plan.in_pix_fmt, W, H, t=1, full_range=plan.in_range == "pc"), synth.noise_frame(plan.in_pix_fmt, W, H, 6)]
+    src = torch.from_numpy(np.concatenate(frames)).cuda()
+    dst = torch.zeros(len(frames) * st.out_frame_bytes, dtype=torch.uint8, device="cuda")
+    st.run(lut, src, dst, len(frames), stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    out = dst.cpu().numpy()
+    from oracle import oracle as O
+    L = O.OracleLut.from_path(cube)
+    for i, f in enumerate(frames):
+        exp = oracle_stage(plan.in_pix_fmt, W, H, f, L, interp=plan.interp, in_matrix=plan.in_matrix, out_matrix=plan.out_matrix,
+                           in_range=plan.in_range, norm_range=plan.norm_range, out_pix_fmt=plan.out_pix_fmt, out_range=plan.out_range)
+        assert_bit_exact(plan.out_pix_fmt, W, H, out[i * st.out_frame_bytes:(i + 1) * st.out_frame_bytes], exp, f"{name} frame {i}")
+    st.close()
