@@ -147,10 +147,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                     const int Rv = (int)(cvb * C.vr4 + (Y * C.yA + C.kR));
                     const int Gv = (int)(wv * C.ug4 + (cvb * C.vgx + (Y * C.yA + C.kG)));
                     const int Bv = (int)(cvb * C.ubx + (wv * C.ub4 + (Y * C.yA + C.kB)));
-                    // av_clip_uintp2(x, 30) >> 20, then 0x4B000000 + code: high word of x * 2^12 plus the magic bits
-                    mr[p] = (unsigned)__mulhi(__vimin_s32_relu(Rv, 0x3FFFFFFF), 4096) + kMagic;
-                    mg[p] = (unsigned)__mulhi(__vimin_s32_relu(Gv, 0x3FFFFFFF), 4096) + kMagic;
-                    mb[p] = (unsigned)__mulhi(__vimin_s32_relu(Bv, 0x3FFFFFFF), 4096) + kMagic;
+                    // av_clip_uintp2(x, 30) >> 20, then 0x4B000000 | code (one funnel shift)
+                    mr[p] = clip30_to_magic(Rv);
+                    mg[p] = clip30_to_magic(Gv);
+                    mb[p] = clip30_to_magic(Bv);
                 }
                 unsigned ro[2], go[2], bo[2];
                 lut3d_pair<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, PK>(LC, tab, mr, mg, mb, ro, go, bo);

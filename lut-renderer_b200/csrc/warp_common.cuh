@@ -38,6 +38,12 @@ __device__ __forceinline__ void stg_s16(void *p, uint4 v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// av_clip_uintp2(v, 30) >> 20 as the float 2^23 + code: 0x4B000000 | code.  The funnel shift (0x4B000 : clipped) >> 20 does the
+// shift and the OR in one instruction (code < 2^10 never reaches the constant's bits).
+__device__ __forceinline__ unsigned clip30_to_magic(int v) {
+    return __funnelshift_r((unsigned)__vimin_s32_relu(v, 0x3FFFFFFF), 0x4B000u, 20);
+}
+
 // The per-column words live in 4-word chunks; chunk c sits at c ^ bit3(c).  With that swizzle the 128-bit accesses of passes A
 // and C (8 lanes x 16 B, chunks 2 apart) and the 32-bit accesses of pass B (32 consecutive columns) are all bank-conflict free.
 __device__ __forceinline__ int swz_chunk(int c) { return c ^ ((c >> 3) & 1); }

@@ -13,6 +13,7 @@ Stages without a LUT (pro mode stage 2) still run as the reference's single ffmp
 """
 from __future__ import annotations
 
+import queue
 import shlex
 import subprocess
 import threading
@@ -141,21 +142,62 @@ class TaskRunner:
         colour = ColourStage.from_plan(gpu.plan, device=self.device)
         lut = colour.ctx.lut_from_cube(gpu.plan.lut_path)
         nb = self.frames_per_batch
-        pin_in = colour.ctx.pinned_buffer(nb * colour.in_frame_bytes)
-        pin_out = colour.ctx.pinned_buffer(nb * colour.out_frame_bytes)
+        # three batches in flight: a reader thread fills pinned input buffers from the decoder's pipe, this thread runs the GPU
+        # stage (H2D -> kernel -> D2H), a writer thread drains pinned output buffers into the encoder's pipe
+        nbuf = 3
+        pin_in = [colour.ctx.pinned_buffer(nb * colour.in_frame_bytes) for _ in range(nbuf)]
+        pin_out = [colour.ctx.pinned_buffer(nb * colour.out_frame_bytes) for _ in range(nbuf)]
         total = int(round(info.duration * info.fps)) if info and info.duration and info.fps else 0
         dec = self._spawn(gpu.decode_cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, bufsize=0)
         enc = self._spawn(gpu.encode_cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, bufsize=0)
+        free_q: "queue.Queue[int]" = queue.Queue()
+        filled_q: "queue.Queue" = queue.Queue()
+        write_q: "queue.Queue" = queue.Queue()
+        for i in range(nbuf):
+            free_q.put(i)
+        errors: List[BaseException] = []
+
+        def reader():
+            try:
+                while not self._cancelled:
+                    i = free_q.get()
+                    if i is None:
+                        break
+                    got = _read_exact(dec.stdout, memoryview(pin_in[i].array))
+                    filled_q.put((i, got))
+                    if got < len(pin_in[i].array):
+                        return
+            except BaseException as exc:  # noqa: BLE001 -- reported through the task status
+                errors.append(exc)
+            filled_q.put((None, 0))
+
+        def writer():
+            broken = False
+            while True:
+                item = write_q.get()
+                if item is None:
+                    return
+                i, nbytes = item
+                if not broken:
+                    try:
+                        enc.stdin.write(memoryview(pin_out[i].array)[:nbytes])
+                    except BaseException as exc:  # noqa: BLE001 -- the encoder went away: stop feeding it
+                        errors.append(exc)
+                        broken = True
+                free_q.put(i)
+
+        rt, wt = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
+        rt.start()
+        wt.start()
         done, last = 0, -1
         try:
-            src_view, dst_view = memoryview(pin_in.array), memoryview(pin_out.array)
-            while not self._cancelled:
-                got = _read_exact(dec.stdout, src_view)
-                n = got // colour.in_frame_bytes
+            while not self._cancelled and not errors:
+                i, got = filled_q.get()
+                n = got // colour.in_frame_bytes if i is not None else 0
                 if n == 0:
                     break
-                colour.run_host(lut, pin_in, pin_out, n)
-                enc.stdin.write(dst_view[:n * colour.out_frame_bytes])
+                colour.run_host(lut, pin_in[i], pin_out[i], n)
+                write_q.put((i, n * colour.out_frame_bytes))
                 done += n
                 if total:
                     pct = min(int(done / total * span), span - (0 if final else 1))
@@ -163,21 +205,27 @@ class TaskRunner:
                     if prog != last:
                         last = prog
                         self.signals.progress(self.task.task_id, prog)
-                if got < len(src_view):
+                if got < len(pin_in[i].array):
                     break
         finally:
+            write_q.put(None)
+            wt.join()
             try:
                 enc.stdin.close()
             except Exception:
                 pass
-            if self._cancelled:
+            if self._cancelled or errors:
                 for p in (dec, enc):
                     if p.poll() is None:
                         p.kill()
+            free_q.put(None)          # releases a reader that waits for a buffer; one blocked in read() ends with the decoder
             rc_dec, rc_enc = dec.wait(), enc.wait()
-            pin_in.close()
-            pin_out.close()
+            rt.join(timeout=5.0)
+            for b in pin_in + pin_out:
+                b.close()
             colour.close()
+        if errors and not self._cancelled:
+            raise RuntimeError(f"raw pipe failed: {errors[0]}")
         if self._cancelled:
             return None
         self._last_returncode = rc_enc or rc_dec

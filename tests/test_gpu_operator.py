@@ -79,3 +79,60 @@ def test_reference_options_to_pixels(name, tmp_path):
                            in_range=plan.in_range, norm_range=plan.norm_range, out_pix_fmt=plan.out_pix_fmt, out_range=plan.out_range)
         assert_bit_exact(plan.out_pix_fmt, W, H, out[i * st.out_frame_bytes:(i + 1) * st.out_frame_bytes], exp, f"{name} frame {i}")
     st.close()
+
+
+def test_task_runner_over_real_pipes(tmp_path):
+    """TaskRunner end to end over real OS pipes: a stand-in decoder process streams raw frames to stdout, the runner pushes them
+    through the GPU stage in pipelined batches (reader thread | GPU | writer thread) and a stand-in encoder process collects its
+    stdin.  (The image has no ffmpeg: the two child processes are python one-liners, everything between them is the product.)
+    The bytes that reach the 'encoder' must be the oracle's, frame for frame, and the reference's status / progress protocol holds."""
+    import subprocess
+    import sys
+    from lut_renderer_b200 import Task
+    from lut_renderer_b200.task_manager import TaskCallbacks, TaskRunner
+    from oracle import oracle as O
+    w, h, nframes = 328, 38, 21                       # 21 frames in batches of 4: a ragged last batch
+    info = VideoInfo(width=w, height=h, pix_fmt="yuv420p10le", bit_depth=10, colorspace="bt709", color_range="tv", fps=25.0,
+                     duration=nframes / 25.0)
+    cube = tmp_path / "look.cube"
+    synth.write_cube(cube, synth.look_lut(17).astype(np.float32))
+    frames = [synth.natural_frame("yuv420p10le", w, h, t=t) for t in range(nframes)]
+    raw_in, raw_out = tmp_path / "in.raw", tmp_path / "out.raw"
+    raw_in.write_bytes(np.concatenate(frames).tobytes())
+    task = Task("t1", tmp_path / "in.mov", tmp_path / "out.mp4", cube, None, ProcessingParams(), source_info=info)   # libx264 -> yuv420p
+    cmds = []
+
+    def popen(cmd, **kw):
+        cmds.append(list(cmd))
+        if "pipe:1" in cmd:      # decoder
+            fake = [sys.executable, "-c", f"import sys, shutil; shutil.copyfileobj(open({str(raw_in)!r}, 'rb'), sys.stdout.buffer)"]
+        else:                    # encoder
+            fake = [sys.executable, "-c", f"import sys, shutil; shutil.copyfileobj(sys.stdin.buffer, open({str(raw_out)!r}, 'wb'))"]
+        return subprocess.Popen(fake, **kw)
+
+    class Rec(TaskCallbacks):
+        events = []
+
+        def progress(self, tid, pct):
+            self.events.append(("progress", pct))
+
+        def status(self, tid, text):
+            self.events.append(("status", text))
+
+        def finished(self, tid, st):
+            self.events.append(("finished", st))
+
+    rec = Rec()
+    TaskRunner(task, callbacks=rec, frames_per_batch=4, popen=popen).run()
+    assert rec.events[-1] == ("finished", "completed"), rec.events[-5:]
+    assert ("progress", 100) in rec.events
+    dec_cmd = next(c for c in cmds if "pipe:1" in c)
+    enc_cmd = next(c for c in cmds if "pipe:0" in c)
+    assert dec_cmd[dec_cmd.index("-pix_fmt") + 1] == "yuv420p10le" and enc_cmd[enc_cmd.index("-pix_fmt") + 1] == "yuv420p"
+    out = np.frombuffer(raw_out.read_bytes(), np.uint8)
+    fb = w * h * 3 // 2
+    assert out.size == nframes * fb
+    L = O.OracleLut.from_path(cube)
+    for i in (0, 3, 4, 19, 20):
+        exp = oracle_stage("yuv420p10le", w, h, frames[i], L, out_pix_fmt="yuv420p")
+        assert_bit_exact("yuv420p", w, h, out[i * fb:(i + 1) * fb], exp, f"piped frame {i}")
