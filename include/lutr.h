@@ -161,9 +161,12 @@ LUTR_API int lutr_stage_sync(lutr_stage *stage);
 LUTR_API int64_t lutr_stage_launch_count(const lutr_stage *stage);
 /* name of the kernel family the most recent enqueue of this stage launched ("" before the first one); diagnostics */
 LUTR_API const char *lutr_stage_kernel_name(const lutr_stage *stage);
-/* run-time tunables, for benchmarking: "rows_per_cta", "band_rows", "l2_persist" (0/1), "fast_path" (0/1),
- * "grid_ctas" (persistent grid of the fast kernels), "idx_mode" (4:2:2 kernel family: 3 = warp-window kernel, 2 = TMA-staged rows,
- * 1 / 0 = earlier fast kernels), "min_blocks", "wk_minb" */
+/* run-time tunables, for benchmarking and testing: "grid_ctas" (persistent grid of the warp-window kernels), "host_chunk_mb" (input
+ * megabytes per slot of the host pipeline's 3-slot device ring, default 64), "l2_persist" (0/1: LUT in a persisting L2 window),
+ * "any_kernel" (1: route every launch through the generic tile kernel), "wk_minb" (CTAs per SM the warp-window kernels are built
+ * for: 2..4), "wk_unroll" (4:2:0 8-bit kernel: window width in 64-column steps), "fast_path" (0: generic kernels of the two
+ * original stage types), "idx_mode" (4:2:2 10-bit kernel family: 3 = warp-window kernel, 2 = TMA-staged rows, 1 / 0 = earlier fast
+ * kernels), "rows_per_cta", "band_rows", "min_blocks", "fast_threads" (geometry of those earlier kernels). */
 LUTR_API int lutr_stage_set_option(lutr_stage *stage, const char *name, int32_t value);
 
 /* ---- coefficient tables (exposed so the parity tests can pin them against libswscale) --------------- */

@@ -526,3 +526,37 @@ def test_no_kernel_writes_outside_its_frames(in_fmt, out_fmt, w, h, options):
         assert_bit_exact(out_fmt, w, h, got, oracle_stage(in_fmt, w, h, f, L, out_pix_fmt=out_fmt), f"{in_fmt}->{out_fmt} frame {i}")
     st.close()
     lut.close()
+
+
+def test_fuzz_geometries_formats_options():
+    """Seeded random sweep over layouts, geometries, grids, LUTs, interps, matrices and ranges: whatever kernel the library picks
+    (or is forced to pick) must match the oracle bit for bit.  Complements the hand-picked edge cases above."""
+    rng = np.random.default_rng(20261018)
+    luts = [synth.look_lut(17), synth.look_lut(33), synth.random_lut(9, 7) * 1.4 - 0.2, synth.random_lut(20, 8), synth.identity_lut(65)]
+    cases = 0
+    for trial in range(48):
+        in_fmt, out_fmt = rng.choice(ALL_FMTS), rng.choice(ALL_FMTS)
+        w = int(rng.choice([16, 24, 64, 120, 136, 240, 248, 256, 264, 376, 488, 512, 520, 736, 1032]))
+        h = int(rng.choice([14, 16, 18, 22, 30, 34, 46, 66]))
+        interp = str(rng.choice(["tetrahedral", "tetrahedral", "trilinear", "nearest", "pyramid", "prism"]))
+        kw = dict(in_matrix=str(rng.choice(["bt709", "bt601", "bt2020"])), out_matrix=str(rng.choice(["bt709", "bt601", "bt2020"])))
+        if rng.random() < 0.25:
+            kw.update(in_range="pc", norm_range="tv" if "10" not in in_fmt and rng.random() < 0.6 else "pc")
+        if rng.random() < 0.25:
+            kw.update(out_range="pc")
+        options = {}
+        if rng.random() < 0.5:
+            options["grid_ctas"] = int(rng.integers(1, 9))
+        if rng.random() < 0.2:
+            options["any_kernel"] = 1
+        scale = (1.0, 1.0, 1.0) if rng.random() < 0.8 else (0.5, 1.0, 0.75)
+        table = luts[int(rng.integers(len(luts)))].astype(np.float32)
+        frames = [synth.noise_frame(in_fmt, w, h, seed=int(rng.integers(1 << 30))),
+                  synth.natural_frame(in_fmt, w, h, t=trial, full_range=kw.get("in_range") == "pc")]
+        got = gpu_stage(in_fmt, w, h, frames, table, scale=scale, out_pix_fmt=out_fmt, interp=interp, options=options, **kw)
+        L = oracle_lut(table, scale)
+        for i, f in enumerate(frames):
+            exp = oracle_stage(in_fmt, w, h, f, L, out_pix_fmt=out_fmt, interp=interp, **kw)
+            assert_bit_exact(out_fmt, w, h, got[i], exp, f"fuzz {trial}: {in_fmt}->{out_fmt} {w}x{h} {interp} {kw} {options} scale {scale} frame {i}")
+        cases += 1
+    assert cases == 48
