@@ -17,7 +17,8 @@
 //            source leg straight from global memory (read-only path) -> lut3d -> luma out, per-pixel chroma terms to shared memory
 //   phase B  per chroma column: pair sum / horizontal 8-tap decimation, range conversion; 4:2:2 / 4:4:4 outputs are written here
 //   phase C  4:2:0 outputs: vertical 8-tap decimation of the rows phase B left in shared memory
-// This kernel favours coverage over speed (halo recomputation up to 29 %, no register-level pipelining); the headline
+// This kernel favours coverage over speed (halo recomputation up to 29 %, no register-level pipelining; its loads come straight
+// from global memory, so it is latency-bound and built for 4 CTAs per SM: 64 registers, measured +45 % over 2 CTAs); the headline
 // configurations never reach it.
 #include <cuda_runtime.h>
 
@@ -62,7 +63,7 @@ __device__ __forceinline__ int up422(const uint16_t *C, int cw, int x) {
 }
 
 template <int INTERP, bool FMA>
-__global__ void __launch_bounds__(kThreads, 2) k_any(const StageK K) {
+__global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
     __shared__ unsigned s_c[kCH][kCW];       // per luma pixel: (cu | cv << 16) chroma terms (c14, or c15 for 8-bit 4:4:4)
     __shared__ unsigned s_h[kCH][kTW / 2];   // 4:2:0 outputs: per chroma column and luma row, 15-bit (int16 | int16 << 16)
 
@@ -309,7 +310,7 @@ int launch_k_any(const StageK &k, int interp, int float_mode, void *stream) {
         default: return LUTR_ERR_INVALID_ARG;
     }
     const long tiles = (long)((k.w + kTW - 1) / kTW) * ((k.h + kTH - 1) / kTH) * k.nframes;
-    long grid = k.grid_ctas > 0 ? k.grid_ctas : 148l * 2 * 8;
+    long grid = k.grid_ctas > 0 ? k.grid_ctas : 148l * 4 * 4;  // 4 resident CTAs per SM, 4 waves of tiles
     if (grid > tiles) grid = tiles;
     fn<<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(k);
     return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;

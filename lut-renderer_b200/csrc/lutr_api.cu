@@ -163,9 +163,11 @@ int check_planes(const lutr_stage *s, const lutr_planes *pl, int fmt, int nframe
             set_error("%s stride[%d]=%d is smaller than the row (%d bytes)", what, p, pl->stride[p], plane_row_bytes(fmt, s->d.width, p));
             return LUTR_ERR_INVALID_ARG;
         }
-        // vector accesses: one 8-pixel group of Y (16 B at 10 bit, 8 B at 8 bit), half of that for a chroma group
-        const int ya = pix_depth(fmt) > 8 ? 16 : 8;
-        const int a = p == 0 || !(pix_sub(fmt) & 1) ? ya : ya / 2;
+        // vector accesses: one 8-pixel group of Y (16 B at 10 bit, 8 B at 8 bit), half of that for a chroma group; stages that only
+        // ever run the generic tile kernel (pixel pairs) need 4 B / 2 B for Y and one sample for chroma
+        const bool wide = pix_depth(fmt) > 8;
+        const int ya = s->any_only ? (wide ? 4 : 2) : (wide ? 16 : 8);
+        const int a = p == 0 || !(pix_sub(fmt) & 1) ? ya : (s->any_only ? (wide ? 2 : 1) : ya / 2);
         if (((uintptr_t)pl->data[p] % a) || (pl->stride[p] % a) || (nframes > 1 && (pl->frame_step % ya))) {
             set_error("%s plane %d: pointer and stride must be %d-byte aligned, frame_step %d-byte aligned", what, p, a, ya);
             return LUTR_ERR_UNSUPPORTED;
@@ -633,8 +635,8 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
         return LUTR_ERR_UNSUPPORTED;
     }
     // geometry the arithmetic models were pinned for against libswscale (tests/test_oracle_swscale.py)
-    if ((d.width % 8) || d.width < 16 || d.width > 16384) {
-        set_error("stage: width must be a multiple of 8 in [16, 16384]");
+    if ((d.width % 2) || d.width < 16 || d.width > 16384) {
+        set_error("stage: width must be even and in [16, 16384]");
         return LUTR_ERR_UNSUPPORTED;
     }
     const bool v420 = (pix_sub(d.in_fmt) | pix_sub(d.out_fmt)) & 2;  // a vertical chroma filter on either side
@@ -651,7 +653,10 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
     const bool ordered10 = in10 && tri_tet &&
                            ((d.in_fmt == LUTR_PIX_YUV420P10LE && d.out_fmt == LUTR_PIX_YUV422P10LE) || d.out_fmt == LUTR_PIX_YUV420P10LE ||
                             d.out_fmt == LUTR_PIX_YUV420P);  // (10-bit source -> 8-bit 4:2:0 delivery: k10_warp8.cu)
-    const bool specialised = d.out_range == LUTR_RANGE_TV && d.interp <= LUTR_INTERP_TETRAHEDRAL && (same_fmt || to_master || ordered10);
+    // (the warp-window kernels work on 8-column groups with 16-byte accesses: widths that are not a multiple of 8, e.g. 854x480,
+    // take the generic kernel)
+    const bool specialised = d.out_range == LUTR_RANGE_TV && d.interp <= LUTR_INTERP_TETRAHEDRAL && (d.width % 8) == 0 &&
+                             (same_fmt || to_master || ordered10);
     CUDA_TRY(cudaSetDevice(ctx->device));
     lutr_stage *s = new (std::nothrow) lutr_stage;
     if (!s) return LUTR_ERR_NOMEM;

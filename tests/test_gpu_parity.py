@@ -560,3 +560,18 @@ def test_fuzz_geometries_formats_options():
             assert_bit_exact(out_fmt, w, h, got[i], exp, f"fuzz {trial}: {in_fmt}->{out_fmt} {w}x{h} {interp} {kw} {options} scale {scale} frame {i}")
         cases += 1
     assert cases == 48
+
+
+@pytest.mark.parametrize("in_fmt,out_fmt,w,h", [("yuv420p", "yuv420p", 854, 480), ("yuv420p10le", "yuv420p", 854, 480),
+                                                ("yuv422p10le", "yuv422p10le", 1366, 18), ("yuv420p", "yuv422p10le", 18, 16),
+                                                ("yuv420p10le", "yuv420p10le", 22, 30), ("yuv444p", "yuv420p", 50, 14),
+                                                ("yuv422p", "yuv444p10le", 134, 12), ("yuv420p", "yuv420p", 130, 34)])
+def test_widths_that_are_not_multiples_of_8(in_fmt, out_fmt, w, h):
+    """Even widths that are not a multiple of 8 (854x480, 1366 wide, ...): the warp-window kernels work on 8-column groups, so the
+    generic tile kernel takes these frames -- same oracle, same bit-exact bar, ragged last tile / pair, odd-sized chroma planes."""
+    table = synth.look_lut(33).astype(np.float32)
+    frames = _frames(in_fmt, w, h, ["natural", "noise", "extremes"])
+    got = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        assert_bit_exact(out_fmt, w, h, got[i], oracle_stage(in_fmt, w, h, f, L, out_pix_fmt=out_fmt), f"{in_fmt}->{out_fmt} {w}x{h} frame {i}")
