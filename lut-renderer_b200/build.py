@@ -48,6 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     ]
     if verbose:
         common += ["-Xptxas", "-v"]
+    if os.environ.get("LUTR_NVCC_FLAGS"):  # experiment switches, e.g. LUTR_NVCC_FLAGS="-DLUTR_PACKED_BLEND=0"
+        common += os.environ["LUTR_NVCC_FLAGS"].split()
     if os.environ.get("LUTR_WK_EXPERIMENTS"):
         common += ["-DLUTR_WK_EXPERIMENTS"]
     # one nvcc per translation unit, in parallel (the template-heavy kernel files dominate the build time)

@@ -210,7 +210,12 @@ __device__ __forceinline__ LutC make_lutc(const StageK &K) {
 }
 
 // lut3d for NP (1 or 2) pixels of one lane.  m*: 0x4B000000 | code (i.e. the float 2^23 + code); outputs biased ints.
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK>
+// PKB: packed instructions also for the blend and the truncating store.  There only three of the four lanes of a float4 node
+// carry data and every per-pixel weight has to be duplicated into a register pair first, so the scalar form can win.
+#ifndef LUTR_PACKED_BLEND
+#define LUTR_PACKED_BLEND 1
+#endif
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, bool PKB = PK && (LUTR_PACKED_BLEND != 0)>
 __device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, const unsigned mr[2],
                                            const unsigned mg[2], const unsigned mb[2], unsigned ro[2], unsigned go[2], unsigned bo[2]) {
     const int N = NSZ ? NSZ : C.n, N2 = NSZ ? NSZ * NSZ : C.n2;
@@ -278,22 +283,22 @@ __device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, con
         const float w0s[2] = {w0.x, w0.y}, w1s[2] = {w1.x, w1.y}, w2s[2] = {w2.x, w2.y}, w3s[2] = {d3.x, d3.y};
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            f2 axy = mul2s<PK>(f2{v0[p].x, v0[p].y}, w0s[p]), azw = mul2s<PK>(f2{v0[p].z, v0[p].w}, w0s[p]);
-            axy = wacc<PK, FMA>(f2{vA[p].x, vA[p].y}, w1s[p], axy, C.one), azw = wacc<PK, FMA>(f2{vA[p].z, vA[p].w}, w1s[p], azw, C.one);
-            axy = wacc<PK, FMA>(f2{vB[p].x, vB[p].y}, w2s[p], axy, C.one), azw = wacc<PK, FMA>(f2{vB[p].z, vB[p].w}, w2s[p], azw, C.one);
-            axy = wacc<PK, FMA>(f2{v1[p].x, v1[p].y}, w3s[p], axy, C.one), azw = wacc<PK, FMA>(f2{v1[p].z, v1[p].w}, w3s[p], azw, C.one);
+            f2 axy = mul2s<PKB>(f2{v0[p].x, v0[p].y}, w0s[p]), azw = mul2s<PKB>(f2{v0[p].z, v0[p].w}, w0s[p]);
+            axy = wacc<PKB, FMA>(f2{vA[p].x, vA[p].y}, w1s[p], axy, C.one), azw = wacc<PKB, FMA>(f2{vA[p].z, vA[p].w}, w1s[p], azw, C.one);
+            axy = wacc<PKB, FMA>(f2{vB[p].x, vB[p].y}, w2s[p], axy, C.one), azw = wacc<PKB, FMA>(f2{vB[p].z, vB[p].w}, w2s[p], azw, C.one);
+            axy = wacc<PKB, FMA>(f2{v1[p].x, v1[p].y}, w3s[p], axy, C.one), azw = wacc<PKB, FMA>(f2{v1[p].z, v1[p].w}, w3s[p], azw, C.one);
             cxy[p] = axy, czw[p] = azw;
         }
     }
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        f2 fxy = mul2s<PK>(cxy[p], C.out_scale), fzw = mul2s<PK>(czw[p], C.out_scale);
+        f2 fxy = mul2s<PKB>(cxy[p], C.out_scale), fzw = mul2s<PKB>(czw[p], C.out_scale);
         if (CLAMP) {
             fxy.x = fminf(fmaxf(fxy.x, 0.f), C.out_scale), fxy.y = fminf(fmaxf(fxy.y, 0.f), C.out_scale);
             fzw.x = fminf(fmaxf(fzw.x, 0.f), C.out_scale);
         }
         // truncating store: + 2^23 toward zero leaves 0x4B000000 | (int)v in the bits
-        const f2 txy = addprz2s<PK>(fxy, 8388608.f, C.one), tzw = addprz2s<PK>(fzw, 8388608.f, C.one);
+        const f2 txy = addprz2s<PKB>(fxy, 8388608.f, C.one), tzw = addprz2s<PKB>(fzw, 8388608.f, C.one);
         ro[p] = __float_as_uint(txy.x), go[p] = __float_as_uint(txy.y), bo[p] = __float_as_uint(tzw.x);
     }
 }
