@@ -114,3 +114,58 @@ def test_pyramid_prism_reproduce_corners_and_affine_luts(interp):
     for px in ((512, 0, 0), (0, 300, 0), (0, 0, 900)):
         a, b = _px(lut, *px, interp=interp), _px(lut, *px, interp="trilinear")
         assert max(abs(x - y) for x, y in zip(a, b)) <= 1
+
+
+def test_trilinear_agrees_with_independent_implementations():
+    """The lut3d leg has no FFmpeg binary to pin against.  Two unrelated implementations at least confirm its
+    geometry -- which file column is which axis, node spacing, cell lookup, blend -- to within the rounding each of them uses:
+    scipy's RegularGridInterpolator (float64 multilinear) and Pillow's Color3DLUT filter (C, fixed point, 8 bit)."""
+    from scipy.interpolate import RegularGridInterpolator
+    from PIL import Image, ImageFilter
+    n = 17
+    t = synth.random_lut(n, 11).astype(np.float32)          # [r][g][b][3]
+    lut = O.OracleLut.from_text(synth.cube_text(t))           # through the .cube text: red fastest in the file
+    rng = np.random.default_rng(3)
+    h, w = 64, 96
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    got = O.lut3d_rgb24(lut, rgb.reshape(h, 3 * w).copy(), "trilinear").reshape(h, w, 3).astype(np.int32)
+    # scipy: float64 multilinear on the same grid; lut3d truncates, so floor() of the ideal value, +-1 for float32 rounding
+    ax = np.linspace(0.0, 1.0, n)
+    ideal = np.stack([RegularGridInterpolator((ax, ax, ax), t[..., c].astype(np.float64))(rgb.reshape(-1, 3) / 255.0) for c in range(3)], -1)
+    ref = np.floor(np.clip(ideal, 0.0, 1.0) * 255.0).reshape(h, w, 3)
+    assert np.abs(got - ref).max() <= 1 and (got == ref).mean() > 0.98
+    # Pillow: table flattened with the red index fastest (the .cube file order), 8-bit fixed-point blend, rounding to nearest
+    flat = np.ascontiguousarray(t.transpose(2, 1, 0, 3)).reshape(-1).tolist()
+    pil = np.asarray(Image.fromarray(rgb, "RGB").filter(ImageFilter.Color3DLUT(n, flat))).astype(np.int32)
+    assert np.abs(got - pil).max() <= 2
+    # a wrong axis order would be off by tens of codes on a random table:
+    swapped = np.asarray(Image.fromarray(rgb, "RGB").filter(ImageFilter.Color3DLUT(n, t.reshape(-1).tolist()))).astype(np.int32)
+    assert np.abs(got - swapped).max() > 20
+
+
+def test_tetrahedral_against_the_sorted_coordinate_definition():
+    """Tetrahedral interpolation from its mathematical definition (sort the three fractions, walk from c000 to c111 adding one axis
+    at a time, weights = successive differences), in float64 numpy: the oracle's six-branch float32 code must agree to the last
+    code value except where float32 rounding meets the truncating store (+-1)."""
+    n = 33
+    t = synth.random_lut(n, 12).astype(np.float32)
+    lut = O.OracleLut.from_table(t)
+    rng = np.random.default_rng(4)
+    pts = rng.integers(0, 1024, (20000, 3))
+    R, G, B = (np.ascontiguousarray(pts[:, c].reshape(1, -1).astype(np.uint16)) for c in range(3))
+    got = np.stack(O.lut3d_planar16(lut, R, G, B, 10, "tetrahedral"), -1).reshape(-1, 3).astype(np.int64)
+    s = pts / 1023.0 * (n - 1)
+    p = np.minimum(np.floor(s).astype(int), n - 1)
+    d = s - p
+    order = np.argsort(-d, axis=1, kind="stable")          # axis with the largest fraction first
+    ds = np.take_along_axis(d, order, 1)
+    w = np.stack([1 - ds[:, 0], ds[:, 0] - ds[:, 1], ds[:, 1] - ds[:, 2], ds[:, 2]], 1)
+    idx = p.copy()
+    acc = w[:, :1] * t[idx[:, 0], idx[:, 1], idx[:, 2]].astype(np.float64)
+    for k in range(3):
+        step = np.zeros_like(idx)
+        step[np.arange(len(idx)), order[:, k]] = 1
+        idx = np.minimum(idx + step, n - 1)
+        acc += w[:, k + 1:k + 2] * t[idx[:, 0], idx[:, 1], idx[:, 2]].astype(np.float64)
+    ref = np.floor(np.clip(acc, 0, 1) * 1023.0).astype(np.int64)
+    assert np.abs(got - ref).max() <= 1 and (got == ref).mean() > 0.99
