@@ -77,3 +77,39 @@ def test_unsupported_requests_are_named_before_touching_the_device():
     # every layout / interp of the operator maps to an enum of include/lutr.h
     assert set(N.PIX_FMT) == {"yuv420p", "yuv422p", "yuv444p", "yuv420p10le", "yuv422p10le", "yuv444p10le"}
     assert set(N.INTERP) == {"nearest", "trilinear", "tetrahedral", "pyramid", "prism"}
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/lutr.h compiles as C99 and a C program that uses the host-only entry points links against liblutr.so and runs
+    (no GPU needed: .cube parsing and the coefficient tables are host code)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "lutr.h"
+int main(void) {
+    const char *cube = "LUT_3D_SIZE 2\n0 0 0\n1 0 0\n0 1 0\n1 1 0\n0 0 1\n1 0 1\n0 1 1\n1 1 1\n";
+    int32_t size = 0, t[9];
+    float scale[3], *table = NULL;
+    lutr_stage_desc d;
+    memset(&d, 0, sizeof d);
+    d.struct_size = sizeof d;
+    if (lutr_version() != LUTR_VERSION) return 1;
+    if (lutr_cube_parse(cube, strlen(cube), &size, scale, &table) != LUTR_OK || size != 2) return 2;
+    if (table[3 * 4 + 0] != 1.0f) return 3;                  /* node r=1,g=0,b=0 holds the file's second line */
+    lutr_free(table);
+    if (lutr_cube_parse("LUT_3D_SIZE 1\n", 14, &size, scale, &table) != LUTR_ERR_LUT_SIZE) return 4;
+    if (lutr_tables_rgb2yuv(LUTR_MATRIX_BT709, t) != LUTR_OK || t[0] != 5983 || t[1] != 20127 || t[2] != 2032) return 5;
+    printf("%s\n", lutr_status_string(LUTR_ERR_UNSUPPORTED));
+    return 0;
+}
+''')
+    exe = tmp_path / "t"
+    lib_dir = os.path.join(root, "lut-renderer_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-llutr", f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == "unsupported configuration"
