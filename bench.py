@@ -76,6 +76,28 @@ def ncu_traffic(config_name, frames_per_launch):
         return None
 
 
+def pcie_simultaneous_gbs(device, nbytes=256 << 20, reps=6):
+    """Pinned host <-> device copy rate per direction with both directions busy (tools/pcie_peak.py, shortened)."""
+    import torch
+    h_in, h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(nbytes, dtype=torch.uint8, device=device), torch.empty(nbytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+    def run(n):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return nbytes * n / (time.perf_counter() - t0) / 1e9
+
+    run(2)
+    return run(reps)
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -466,7 +488,8 @@ def main():
     # end to end: the call a user makes (ColourStage.run_host) on pinned host frames, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        Fe = max(1, min(F, 16 if "10" in cfg["pix_fmt"] else 64))
+        # the same step as the device-resident measurement (F frames per call), bounded to 4 GB of pinned memory per direction
+        Fe = max(1, min(F, int(4e9 // max(stage.in_frame_bytes, stage.out_frame_bytes))))
         pin_in = stage.ctx.pinned_buffer(Fe * stage.in_frame_bytes)
         pin_out = stage.ctx.pinned_buffer(Fe * stage.out_frame_bytes)
         for i in range(Fe):
@@ -487,6 +510,14 @@ def main():
         e2e = {"value": round(world * Fe * e2e_steps / dt, 2), "unit": "frames/s", "h2d_bytes_per_step": Fe * stage.in_frame_bytes,
                "d2h_bytes_per_step": Fe * stage.out_frame_bytes, "frames_per_step": Fe, "steps": e2e_steps,
                "api": "ColourStage.run_host -> lutr_stage_run_host (pinned host buffers)"}
+        # what the bus allows: pinned copies in both directions at once (the path moves one frame in and one out per frame)
+        try:
+            pcie = pcie_simultaneous_gbs(device)
+            moved = max(stage.in_frame_bytes, stage.out_frame_bytes) * Fe * e2e_steps / dt / 1e9
+            e2e["pcie_each_direction_gbs"] = round(pcie, 1)
+            e2e["frac_of_pcie"] = round(moved / pcie, 3)
+        except Exception:
+            pass
         pin_in.close()
         pin_out.close()
 
