@@ -251,6 +251,8 @@ def run_cfg5(args):
         return
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
+    from lut_renderer_b200.sharding import bind_to_device_cpus
+    full_affinity = bind_to_device_cpus(local_rank)   # pinned host frames on the GPU's own NUMA node (one process per GPU)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(device))
@@ -414,6 +416,8 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
+    from lut_renderer_b200.sharding import bind_to_device_cpus
+    full_affinity = bind_to_device_cpus(local_rank)   # pinned host frames on the GPU's own NUMA node (one process per GPU)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(device))
@@ -509,7 +513,8 @@ def main():
             dt = float(t.item())
         e2e = {"value": round(world * Fe * e2e_steps / dt, 2), "unit": "frames/s", "h2d_bytes_per_step": Fe * stage.in_frame_bytes,
                "d2h_bytes_per_step": Fe * stage.out_frame_bytes, "frames_per_step": Fe, "steps": e2e_steps,
-               "api": "ColourStage.run_host -> lutr_stage_run_host (pinned host buffers)"}
+               "api": "ColourStage.run_host -> lutr_stage_run_host (pinned host buffers)",
+               "cpu_affinity": "cores local to the GPU (NVML)" if full_affinity else "unchanged"}
         # what the bus allows: pinned copies in both directions at once (the path moves one frame in and one out per frame)
         try:
             pcie = pcie_simultaneous_gbs(device)
@@ -533,6 +538,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_baseline as C
             from oracle import oracle as O
+            if full_affinity:
+                os.sched_setaffinity(0, full_affinity)   # the CPU chain gets every host core again
             r = C.time_cpu_path(cfg["pix_fmt"], cfg["w"], cfg["h"], O.OracleLut.from_table(table), base_frames,
                                 seconds=args.cpu_seconds, interp=cfg["interp"], out_pix_fmt=cfg.get("out_pix_fmt"))
             cpu = {"value": round(r["fps"], 3), "unit": "frames/s", "cores": r["threads"], "kind": "port",

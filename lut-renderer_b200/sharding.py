@@ -66,3 +66,26 @@ def luts_per_rank(clips: Sequence[Clip], plan: Sequence[Sequence[int]]) -> List[
             d[clips[i].lut] = d.get(clips[i].lut, 0) + 1
         out.append(d)
     return out
+
+
+def bind_to_device_cpus(device: int):
+    """Pin the calling process to the CPU cores local to GPU ``device`` (NVML's ideal-affinity mask) so that the pinned host buffers
+    it allocates afterwards land on that GPU's NUMA node: with one process per GPU, host frames otherwise cross the socket
+    interconnect on their way to PCIe.  Returns the previous affinity (restore it with ``os.sched_setaffinity(0, prev)``), or None
+    when NVML or the mask is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
