@@ -31,6 +31,10 @@ namespace lutr {
 namespace {
 
 constexpr int kORow = kWin / 2;  // words per row of the output ring (120 used)
+#ifndef LUTR_K10_WARPS
+#define LUTR_K10_WARPS 8
+#endif
+constexpr int kW10 = LUTR_K10_WARPS;  // warps per CTA (a CTA is only a container)
 
 // ff_dither_8x8_128: swscale's ordered dither of the 8-bit output stage for sources deeper than 8 bit (OUT8)
 __constant__ unsigned char c_dither10[8][8] = {
@@ -45,7 +49,7 @@ struct K10Smem {
 };
 
 template <bool IN420, bool OUT420, bool OUT8, int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int MINB>
-__global__ void __launch_bounds__(kWarps * 32, MINB) k10_warp(const StageK K) {
+__global__ void __launch_bounds__(kW10 * 32, MINB) k10_warp(const StageK K) {
     extern __shared__ __align__(16) unsigned s_dyn[];
     constexpr int NR = IN420 ? 4 : 1;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lane_odd = lane ^ 4;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k10_warp(const StageK K) {
     const unsigned c_kB = fk.kB - (unsigned)kCBias * fk.ub4;
 
     const unsigned total_c = (unsigned)K.nframes * (unsigned)tpr * (unsigned)ch;
-    const unsigned nwarps = gridDim.x * kWarps, gw = blockIdx.x * kWarps + wib;
+    const unsigned nwarps = gridDim.x * kW10, gw = blockIdx.x * kW10 + wib;
     const unsigned per = total_c / nwarps, rem = total_c % nwarps;
     unsigned c_pos = gw * per + min(gw, rem);
     const unsigned c_end = c_pos + per + (gw < rem ? 1u : 0u);
@@ -419,7 +423,7 @@ int launch_k10(const StageK &k, int interp, int float_mode, bool grid_forced, vo
     // 2 CTAs per SM with 128 registers by default (measured 5-10 % faster than 3 CTAs x 80 registers, which spill); min_blocks == 3
     // selects the 80-register build of the tetrahedral kernel.  Both rings together (IN420 && OUT420: 76 KB of shared memory per
     // CTA) leave room for two CTAs per SM only; trilinear keeps 16 gathers in flight per step and always gets 128 registers.
-    constexpr size_t smem = (size_t)kWarps * K10Smem<IN420, OUT420>::words * sizeof(unsigned);
+    constexpr size_t smem = (size_t)kW10 * K10Smem<IN420, OUT420>::words * sizeof(unsigned);
     constexpr bool two_only = 3 * smem > 200 * 1024;
     const int minb = interp == LUTR_INTERP_TRILINEAR || k.min_blocks != 3 || two_only ? 2 : 3;
     KernelFn fn = interp == LUTR_INTERP_TRILINEAR ? pick_sem<IN420, OUT420, OUT8, LUTR_INTERP_TRILINEAR, 2>(fma, clamp, fold_nomin, k.lut.n)
@@ -429,8 +433,8 @@ int launch_k10(const StageK &k, int interp, int float_mode, bool grid_forced, vo
     const long total_c = (long)k.nframes * k.tiles_per_row * (k.h / 2);
     long grid = grid_forced ? k.grid_ctas : 148 * minb;
     // small jobs: a smaller grid so that a share is at least 16 chroma rows and the ring warm-up / halo rows stay cheap
-    if (!grid_forced && total_c / (kWarps * grid) < 16) grid = total_c / (kWarps * 16) > 0 ? total_c / (kWarps * 16) : 1;
-    fn<<<(unsigned)grid, kWarps * 32, smem, (cudaStream_t)stream>>>(k);
+    if (!grid_forced && total_c / (kW10 * grid) < 16) grid = total_c / (kW10 * 16) > 0 ? total_c / (kW10 * 16) : 1;
+    fn<<<(unsigned)grid, kW10 * 32, smem, (cudaStream_t)stream>>>(k);
     return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
 }
 
