@@ -98,7 +98,11 @@ typedef struct lutr_stage_desc {
     int32_t out_range;    /* lutr_range of the output (LUTR_RANGE_TV for tags=bt709)                          */
     int32_t interp;       /* lutr_interp                                                                     */
     int32_t float_mode;   /* lutr_float_mode, 0 = C semantics                                                */
-    int32_t reserved[4];
+    int32_t via_8bit;     /* full-range (in_range = pc) source deeper than 8 bit: 1 = go through the 8-bit yuv4xxp intermediate the
+                             reference's `scale=in_range=pc:out_range=R,format=yuv4xxp` produces (ffmpeg.py:211-233; one swscale pass:
+                             range conversion + ordered dither for R = tv, dithered planar copy for R = pc), as plan_colour_stage
+                             asks for.  0 with norm_range = pc: the samples are used at their own depth (beyond the reference). */
+    int32_t reserved[3];
 } lutr_stage_desc;
 
 /* A batch of planar frames: plane p of frame f starts at data[p] + f * frame_step, rows `stride[p]` bytes apart. */

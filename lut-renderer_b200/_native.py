@@ -32,7 +32,7 @@ class LutrError(RuntimeError):
 class StageDesc(Structure):
     _fields_ = [("struct_size", c_uint32), ("width", c_int32), ("height", c_int32), ("in_fmt", c_int32), ("out_fmt", c_int32),
                 ("in_range", c_int32), ("norm_range", c_int32), ("in_matrix", c_int32), ("out_matrix", c_int32),
-                ("out_range", c_int32), ("interp", c_int32), ("float_mode", c_int32), ("reserved", c_int32 * 4)]
+                ("out_range", c_int32), ("interp", c_int32), ("float_mode", c_int32), ("via_8bit", c_int32), ("reserved", c_int32 * 3)]
 
 
 class Planes(Structure):

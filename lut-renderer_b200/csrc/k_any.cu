@@ -62,13 +62,25 @@ __device__ __forceinline__ int up422(const uint16_t *C, int cw, int x) {
     return min(s >> 9, 32767);
 }
 
+// One sample of a full-range 10-bit source through swscale's one-pass conversion to the 8-bit intermediate the reference inserts
+// (`scale=in_range=pc:out_range=R,format=yuv4xxp`, ffmpeg.py:211-233; oracle orc_prepass_10_to_8).  (py, px): position in the plane.
+__device__ __forceinline__ int pre10_sample(int v, int py, int px, int mode, int plane, int coeff, int offset) {
+    if (mode == 1)  // generic scaler: 15-bit sample, range conversion, ordered dither (V shifted by 3 columns)
+        return clamp_hi((range15(v << 5, coeff, offset) + c_dither[py & 7][(px + (plane == 2 ? 3 : 0)) & 7]) >> 7, 255);
+    const int d = (py & 1) ? ((px & 1) ? 0 : 3) : ((px & 1) ? 2 : 1);  // planar copy, 2x2 dither {{1,2},{3,0}}
+    if (plane == 0) return min((v + d - (v >> 8)) >> 2, 255);
+    const int t = (v + d) >> 2;
+    return t - (t >> 8);
+}
+
 template <int INTERP, bool FMA>
 __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
     __shared__ unsigned s_c[kCH][kCW];       // per luma pixel: (cu | cv << 16) chroma terms (c14, or c15 for 8-bit 4:4:4)
     __shared__ unsigned s_h[kCH][kTW / 2];   // 4:2:0 outputs: per chroma column and luma row, 15-bit (int16 | int16 << 16)
 
     const int w = K.w, h = K.h;
-    const int in_sx = K.any.in_sub & 1, in_sy = K.any.in_sub >> 1, sd = K.any.in_depth;
+    const int pre10 = K.any.pre10;  // != 0: 10-bit full-range samples enter through the reference's 8-bit intermediate
+    const int in_sx = K.any.in_sub & 1, in_sy = K.any.in_sub >> 1, sd = pre10 ? 8 : K.any.in_depth;
     const int o_sx = K.any.out_sub & 1, o_sy = K.any.out_sub >> 1, od = K.any.out_depth;
     const bool out_full = K.any.out_full != 0, bayer = sd > 8 && od == 8;
     const int hx = (sd > 8 && o_sx) ? 4 : 0;  // halo columns per side (the window stays pair-aligned)
@@ -104,10 +116,23 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
             if (sd == 8) {
                 const uint8_t *yr = inY + (long)y * K.p.in_stride[0];
                 const uint8_t *ur = inU + (long)(y >> in_sy) * K.p.in_stride[1], *vr = inV + (long)(y >> in_sy) * K.p.in_stride[2];
-                int Yv[2] = {(int)__ldg(yr + x), (int)__ldg(yr + x + 1)}, Uv[2], Vv[2];
-                if (in_sx) {
+                int Yv[2], Uv[2], Vv[2];
+                if (pre10) {  // 16-bit samples, re-quantised to the 8-bit intermediate at their own plane coordinates
+                    const uint16_t *y16 = reinterpret_cast<const uint16_t *>(yr), *u16 = reinterpret_cast<const uint16_t *>(ur);
+                    const uint16_t *v16 = reinterpret_cast<const uint16_t *>(vr);
+                    const int cy = y >> in_sy;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int cx = (x + q) >> in_sx;
+                        Yv[q] = pre10_sample((int)__ldg(y16 + x + q), y, x + q, pre10, 0, K.any.in_lc, K.any.in_lo);
+                        Uv[q] = pre10_sample((int)__ldg(u16 + cx), cy, cx, pre10, 1, K.any.in_cc, K.any.in_co);
+                        Vv[q] = pre10_sample((int)__ldg(v16 + cx), cy, cx, pre10, 2, K.any.in_cc, K.any.in_co);
+                    }
+                } else if (in_sx) {
+                    Yv[0] = (int)__ldg(yr + x), Yv[1] = (int)__ldg(yr + x + 1);
                     Uv[0] = Uv[1] = (int)__ldg(ur + (x >> 1)), Vv[0] = Vv[1] = (int)__ldg(vr + (x >> 1));
                 } else {
+                    Yv[0] = (int)__ldg(yr + x), Yv[1] = (int)__ldg(yr + x + 1);
                     Uv[0] = (int)__ldg(ur + x), Uv[1] = (int)__ldg(ur + x + 1), Vv[0] = (int)__ldg(vr + x), Vv[1] = (int)__ldg(vr + x + 1);
                 }
                 if (K.range_pass) {  // swscale's 8-bit pc -> tv pass: 15-bit range conversion, then the 8-bit output stage

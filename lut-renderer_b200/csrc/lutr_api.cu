@@ -64,6 +64,7 @@ struct lutr_stage {
     std::vector<IdxTable> idx_tables;
     int use_fast = 1;      // 0 forces the generic kernels (testing)
     bool any_only = false; // the combination exists in the generic tile kernel (k_any.cu) only
+    int pre10 = 0;         // full-range 10-bit source through the 8-bit intermediate: 1 = with pc -> tv, 2 = range kept
     int force_any = 0;     // option "any_kernel": 1 routes every launch through the generic tile kernel (testing)
     int grid_ctas = 0;     // 0 = min_blocks CTAs per SM
     int idx_mode = 3;      // 0 = shared-memory index table, 1 = arithmetic index, 2 = arithmetic index + TMA-staged rows,
@@ -324,6 +325,8 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         a.in_sub = pix_sub(s->d.in_fmt), a.in_depth = pix_depth(s->d.in_fmt);
         a.out_sub = pix_sub(s->d.out_fmt), a.out_depth = pix_depth(s->d.out_fmt);
         a.out_full = s->d.out_range == LUTR_RANGE_PC ? 1 : 0;
+        a.pre10 = s->pre10;
+        if (s->pre10) k.range_pass = 0;  // the pre-pass already delivers the normalised 8-bit samples
         range_coeffs(8, false, false, &a.in_lc, &a.in_lo);
         range_coeffs(8, false, true, &a.in_cc, &a.in_co);
         range_coeffs(a.out_depth, true, false, &a.out_lc, &a.out_lo);
@@ -629,9 +632,11 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
         return LUTR_ERR_INVALID_ARG;
     }
     const bool range_pass = d.in_range == LUTR_RANGE_PC && d.norm_range == LUTR_RANGE_TV;
-    if (pix_depth(d.in_fmt) > 8 && range_pass) {
+    // a full-range source deeper than 8 bit through the reference's 8-bit intermediate (desc.via_8bit, generic kernel)
+    const bool pre10 = pix_depth(d.in_fmt) > 8 && d.in_range == LUTR_RANGE_PC && d.via_8bit != 0;
+    if (pix_depth(d.in_fmt) > 8 && range_pass && !pre10) {
         // the reference's pc->tv pass always drops to 8-bit yuv4xxp (ffmpeg.py:137-143,233): hand the stage that 8-bit format
-        set_error("stage: pc->tv normalisation of a 10-bit source re-quantises to 8 bit in the reference; not implemented");
+        set_error("stage: pc->tv normalisation of a 10-bit source re-quantises to 8 bit in the reference: set lutr_stage_desc.via_8bit");
         return LUTR_ERR_UNSUPPORTED;
     }
     // geometry the arithmetic models were pinned for against libswscale (tests/test_oracle_swscale.py)
@@ -655,14 +660,15 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
                             d.out_fmt == LUTR_PIX_YUV420P);  // (10-bit source -> 8-bit 4:2:0 delivery: k10_warp8.cu)
     // (the warp-window kernels work on 8-column groups with 16-byte accesses: widths that are not a multiple of 8, e.g. 854x480,
     // take the generic kernel)
-    const bool specialised = d.out_range == LUTR_RANGE_TV && d.interp <= LUTR_INTERP_TETRAHEDRAL && (d.width % 8) == 0 &&
+    const bool specialised = !pre10 && d.out_range == LUTR_RANGE_TV && d.interp <= LUTR_INTERP_TETRAHEDRAL && (d.width % 8) == 0 &&
                              (same_fmt || to_master || ordered10);
     CUDA_TRY(cudaSetDevice(ctx->device));
     lutr_stage *s = new (std::nothrow) lutr_stage;
     if (!s) return LUTR_ERR_NOMEM;
     s->ctx = ctx;
     s->d = d;
-    s->depth = pix_depth(d.in_fmt);
+    s->depth = pre10 ? 8 : pix_depth(d.in_fmt);  // depth of the RGB intermediate the LUT works on
+    s->pre10 = pre10 ? (range_pass ? 1 : 2) : 0;
     s->any_only = !specialised;
     // YUV->RGB sees the range left by the normalisation pass
     make_yuv2rgb(d.in_matrix, d.norm_range == LUTR_RANGE_PC, s->f);

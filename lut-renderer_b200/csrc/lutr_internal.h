@@ -80,6 +80,7 @@ struct AnyK {
     int32_t in_sub, in_depth;    // log2 chroma subsampling (sx | sy << 1) and sample depth of the source
     int32_t out_sub, out_depth;  // ... of the output
     int32_t out_full;            // 1: full-range output (15-bit range conversion with the constants below)
+    int32_t pre10;               // full-range 10-bit source through the reference's 8-bit intermediate: 1 = pc -> tv, 2 = range kept
     int32_t in_lc, in_lo, in_cc, in_co;      // 8-bit pc -> tv pass: luma / chroma coefficient and offset
     int32_t out_lc, out_lo, out_cc, out_co;  // tv -> pc on the output side (output depth)
 };

@@ -393,6 +393,7 @@ class ColourStagePlan:
     interp: str
     lut_path: Optional[Path]
     rgb_intermediate: str            # "rgb24" (8-bit sources) | "gbrp10le" (10-bit sources): what FFmpeg negotiates for lut3d
+    via_8bit: bool = False   # full-range source deeper than 8 bit: the stage re-quantises it to the reference's 8-bit intermediate
     reference_filters: List[str] = field(default_factory=list)  # the -vf chain this plan replaces
     notes: List[str] = field(default_factory=list)
 
@@ -426,9 +427,14 @@ def plan_colour_stage(params: ProcessingParams, lut_path: Optional[Path], source
     src_fmt = str(info.pix_fmt or "yuv420p")
     src_depth = info.bit_depth or (10 if "10" in src_fmt else 8)
     full_range = _needs_full_range_normalization(info)
+    via_8bit = False
     if full_range:
         # the reference re-quantises to 8-bit yuv4xxp behind the range pass whatever the source depth (ffmpeg.py:137-143,233)
         in_pix_fmt, work_depth = _full_range_intermediate_pix_fmt(info), 8
+        deep = in_pix_fmt + "10le"
+        if src_depth == 10 and src_fmt.replace("yuvj", "yuv") == deep:
+            # hand the stage the 10-bit samples: it performs swscale's one-pass conversion to that 8-bit intermediate itself
+            in_pix_fmt, via_8bit = deep, True
         in_range, norm_range = "pc", _normalised_range(params, info)
         if norm_range not in ("tv", "pc"):
             norm_range = "pc"
@@ -459,7 +465,8 @@ def plan_colour_stage(params: ProcessingParams, lut_path: Optional[Path], source
         width=int(info.width), height=int(info.height), in_pix_fmt=in_pix_fmt, out_pix_fmt=out_pix_fmt,
         in_range=in_range, norm_range=norm_range, in_matrix=_effective_matrix(_forced_matrix(params, info), info.colorspace),
         out_matrix=out_matrix, out_range=out_range, interp=_resolve_interp(params), lut_path=Path(lut_path),
-        rgb_intermediate="gbrp10le" if work_depth >= 10 else "rgb24", reference_filters=reference_filters, notes=plan_notes)
+        rgb_intermediate="gbrp10le" if work_depth >= 10 else "rgb24", via_8bit=via_8bit, reference_filters=reference_filters,
+        notes=plan_notes)
 
 
 @dataclass
@@ -484,7 +491,9 @@ def build_gpu_stage(stage: CommandStage, source_info: Optional[VideoInfo], ffmpe
     params = stage.params
     _, fps_text = _resolve_fps(params, source_info)
     decode = [ffmpeg_bin, "-hide_banner", "-v", "error", "-i", str(stage.source_path), "-map", "0:v:0", "-f", "rawvideo",
-              "-pix_fmt", ("yuvj" + plan.in_pix_fmt[3:]) if plan.in_range == "pc" and plan.in_pix_fmt.startswith("yuv4") else plan.in_pix_fmt,
+              # untouched samples: 8-bit full-range sources are named yuvj4xxp; deeper ones keep their own name (no yuvj form exists)
+              "-pix_fmt", ("yuvj" + plan.in_pix_fmt[3:]) if plan.in_range == "pc" and plan.in_pix_fmt in ("yuv420p", "yuv422p", "yuv444p")
+              else plan.in_pix_fmt,
               "-fps_mode", "passthrough", "pipe:1"]
     encode = [ffmpeg_bin, "-hide_banner"]
     if params.overwrite:

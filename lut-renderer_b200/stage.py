@@ -153,7 +153,7 @@ class ColourStage:
 
     def __init__(self, width: int, height: int, pix_fmt: str = "yuv422p10le", out_pix_fmt: Optional[str] = None,
                  in_range: str = "tv", norm_range: Optional[str] = None, in_matrix: str = "bt709", out_matrix: str = "bt709",
-                 out_range: str = "tv", interp: str = "tetrahedral", float_mode: str = "c", device: int = 0):
+                 out_range: str = "tv", interp: str = "tetrahedral", float_mode: str = "c", device: int = 0, via_8bit: bool = False):
         out_pix_fmt = out_pix_fmt or pix_fmt
         if interp not in GPU_INTERPS:
             raise N.LutrError(N.ERR_UNSUPPORTED, f"interp={interp} is not implemented on the GPU stage (have {GPU_INTERPS})")
@@ -169,6 +169,7 @@ class ColourStage:
         d.in_range, d.norm_range = N.RANGE[in_range], N.RANGE[norm_range or in_range]
         d.in_matrix, d.out_matrix, d.out_range = N.MATRIX[in_matrix], N.MATRIX[out_matrix], N.RANGE[out_range]
         d.interp, d.float_mode = N.INTERP[interp], N.FLOAT_MODE[float_mode]
+        d.via_8bit = 1 if via_8bit else 0
         h = c_void_p()
         N.check(N.lib().lutr_stage_create(self.ctx._h, byref(d), byref(h)))
         self._h = h
@@ -179,7 +180,7 @@ class ColourStage:
     @classmethod
     def from_plan(cls, plan: ColourStagePlan, device: int = 0, float_mode: str = "c") -> "ColourStage":
         return cls(plan.width, plan.height, plan.in_pix_fmt, plan.out_pix_fmt, plan.in_range, plan.norm_range,
-                   plan.in_matrix, plan.out_matrix, plan.out_range, plan.interp, float_mode, device)
+                   plan.in_matrix, plan.out_matrix, plan.out_range, plan.interp, float_mode, device, via_8bit=plan.via_8bit)
 
     # -- device-resident frames ------------------------------------------------------------------------------
     def run(self, lut: DeviceLut, src, dst, nframes: int = 1, stream=None) -> None:

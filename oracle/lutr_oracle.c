@@ -1206,9 +1206,45 @@ ORC_API void orc_rgb_to_yuv_any(int src_depth, int out_fmt, int out_full, const 
     free(u14), free(v14), free(hu), free(hv);
 }
 
+/* Full-range sources deeper than 8 bit: the reference's range pass always lands on 8-bit yuv4xxp (`scale=in_range=pc:out_range=R,
+ * format=yuv4xxp`, ffmpeg.py:211-233), i.e. swscale converts yuv4xxp10le(pc) -> yuv4xxp 8 bit in one pass.  PINNED against
+ * libswscale 9.1.100 (tests/test_oracle_swscale.py test_any_10bit_full_range_prepass):
+ *   mode 1 (out_range tv): generic scaler path: 15-bit sample (v << 5) -> range conversion (8-bit constants, from jpeg) -> 8-bit
+ *          output stage with the ordered dither ff_dither_8x8_128[y & 7][(x + off) & 7], off = 3 for the V plane
+ *   mode 2 (out_range pc): swscale's planar copy with its 2x2 dither {{1,2},{3,0}}: chroma t = (v + d) >> 2, t - (t >> 8);
+ *          full-range luma min((v + d - (v >> 8)) >> 2, 255)        (recovered exhaustively from the binary)
+ * plane: 0 Y, 1 U, 2 V; coordinates are those of the plane itself. */
+ORC_API void orc_prepass_10_to_8(int mode, int plane, const uint16_t *src, int ss, uint8_t *dst, int ds, int w, int h)
+{
+    static const int d2[2][2] = {{1, 2}, {3, 0}};
+    int64_t c, o;
+    orc_range_coeffs(8, 0, plane > 0, &c, &o);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const int v = src[y * ss + x];
+            int r;
+            if (mode == 1) {
+                const int v15 = range_conv15(v << 5, c, o);
+                r = clip_u((v15 + k_dither_8x8_128[y & 7][(x + (plane == 2 ? 3 : 0)) & 7]) >> 7, 255);
+            } else {
+                const int d = d2[y & 1][x & 1];
+                if (plane == 0) {
+                    r = (v + d - (v >> 8)) >> 2;
+                    if (r > 255)
+                        r = 255;
+                } else {
+                    const int t = (v + d) >> 2;
+                    r = t - (t >> 8);
+                }
+            }
+            dst[y * ds + x] = (uint8_t)r;
+        }
+}
+
 /* Any supported source -> [8-bit pc->tv pass] -> RGB (rgb24 for 8-bit, gbrp10le for 10-bit sources) -> lut3d -> any supported
- * output, one frame, tightly packed planes.  range_pass only for 8-bit sources (the reference's pass always lands on 8-bit
- * yuv4xxp, ffmpeg.py:137-143); in_full_range = range of the samples the YUV->RGB step sees. */
+ * output, one frame, tightly packed planes.  range_pass: 8-bit sources: 1 = pc -> tv pass; 10-bit sources: 1 / 2 = the reference's
+ * 8-bit re-quantisation of a full-range source with / without the range conversion (orc_prepass_10_to_8), then the 8-bit chain.
+ * in_full_range = range of the samples the YUV->RGB step sees. */
 ORC_API int orc_stage_any(const OrcLut *l, int interp, int in_fmt, int out_fmt, int range_pass, int in_matrix, int in_full_range,
                           int out_matrix, int out_full_range, const void *Y, const void *U, const void *V, void *Yo, void *Uo,
                           void *Vo, int w, int h)
@@ -1221,7 +1257,17 @@ ORC_API int orc_stage_any(const OrcLut *l, int interp, int in_fmt, int out_fmt, 
     if (!rgb)
         return ORC_ENOMEM;
     uint16_t *R = rgb, *G = rgb + n, *B = rgb + 2 * n;
-    if (id == 8) {
+    uint8_t *pre = NULL;
+    int wd = id; /* working depth: 8 = rgb24 intermediate, 10 = gbrp10le */
+    if (id == 10 && range_pass) { /* full-range 10-bit source: the reference's pass re-quantises to 8-bit yuv4xxp first */
+        pre = (uint8_t *)malloc(n + 2 * cn);
+        orc_prepass_10_to_8(range_pass, 0, (const uint16_t *)Y, w, pre, w, w, h);
+        orc_prepass_10_to_8(range_pass, 1, (const uint16_t *)U, cw, pre + n, cw, cw, ch);
+        orc_prepass_10_to_8(range_pass, 2, (const uint16_t *)V, cw, pre + n + cn, cw, cw, ch);
+        Y = pre, U = pre + n, V = pre + n + cn;
+        wd = 8, range_pass = 0;
+    }
+    if (wd == 8) {
         uint8_t *p8 = (uint8_t *)malloc(3 * n), *tmp = NULL;
         const uint8_t *y8 = (const uint8_t *)Y, *u8 = (const uint8_t *)U, *v8 = (const uint8_t *)V;
         if (range_pass) {
@@ -1237,10 +1283,6 @@ ORC_API int orc_stage_any(const OrcLut *l, int interp, int in_fmt, int out_fmt, 
             R[i] = p8[3 * i], G[i] = p8[3 * i + 1], B[i] = p8[3 * i + 2];
         free(p8), free(tmp);
     } else {
-        if (range_pass) {
-            free(rgb);
-            return ORC_EINVAL;
-        }
         const uint16_t *y16 = (const uint16_t *)Y, *u16 = (const uint16_t *)U, *v16 = (const uint16_t *)V;
         if (in_fmt == ORC_PIX_YUV420P10)
             orc_yuv420p10_to_gbrp10(y16, w, u16, v16, cw, R, G, B, w, w, h, in_matrix, in_full_range);
@@ -1250,7 +1292,8 @@ ORC_API int orc_stage_any(const OrcLut *l, int interp, int in_fmt, int out_fmt, 
             orc_yuv444p10_to_gbrp10(y16, u16, v16, w, R, G, B, w, w, h, in_matrix, in_full_range);
         orc_lut3d_planar16(l, interp, 10, R, G, B, w, R, G, B, w, w, h);
     }
-    orc_rgb_to_yuv_any(id, out_fmt, out_full_range, R, G, B, w, Yo, Uo, Vo, w, h, out_matrix);
+    orc_rgb_to_yuv_any(wd, out_fmt, out_full_range, R, G, B, w, Yo, Uo, Vo, w, h, out_matrix);
     free(rgb);
+    free(pre);
     return ORC_OK;
 }

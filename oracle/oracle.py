@@ -282,9 +282,20 @@ def rgb_to_yuv_any(src_depth, out_fmt, R, G, B, matrix="bt709", out_full_range=F
     return out
 
 
+def prepass_10_to_8(mode, plane, src):
+    """swscale's yuv4xxp10le(pc) -> yuv4xxp 8-bit re-quantisation of one plane (mode 1: with pc->tv, 2: range kept)."""
+    h, w = src.shape
+    dst = np.empty((h, w), np.uint8)
+    src = np.ascontiguousarray(src, dtype=np.uint16)
+    lib().orc_prepass_10_to_8(int(mode), int(plane), _p(src), w, _p(dst), w, w, h)
+    return dst
+
+
 def stage_any(lut, in_fmt, out_fmt, Y, U, V, interp="tetrahedral", range_pass=False, in_matrix="bt709", in_full_range=False,
               out_matrix="bt709", out_full_range=False):
-    """Any supported source -> [8-bit pc->tv pass] -> RGB -> lut3d -> any supported output (one frame, contiguous planes)."""
+    """Any supported source -> [range pass] -> RGB -> lut3d -> any supported output (one frame, contiguous planes).
+    range_pass: 8-bit sources True = pc->tv pass; 10-bit sources 1 / 2 = the reference's 8-bit re-quantisation of a full-range
+    source with / without the range conversion (the rest of the chain is then the 8-bit one)."""
     h, w = Y.shape
     shapes, dt = pix_geometry(out_fmt, w, h)
     out = [np.empty(s, dt) for s in shapes]

@@ -575,3 +575,22 @@ def test_widths_that_are_not_multiples_of_8(in_fmt, out_fmt, w, h):
     L = oracle_lut(table)
     for i, f in enumerate(frames):
         assert_bit_exact(out_fmt, w, h, got[i], oracle_stage(in_fmt, w, h, f, L, out_pix_fmt=out_fmt), f"{in_fmt}->{out_fmt} {w}x{h} frame {i}")
+
+
+@pytest.mark.parametrize("in_fmt", ["yuv420p10le", "yuv422p10le", "yuv444p10le"])
+@pytest.mark.parametrize("norm_range,out_fmt,out_range", [("tv", "yuv420p", "tv"), ("tv", "yuv420p10le", "tv"), ("pc", "yuv422p", "pc"),
+                                                           ("pc", "yuv444p10le", "tv")])
+def test_full_range_10bit_source_via_8bit_intermediate(in_fmt, norm_range, out_fmt, out_range):
+    """Full-range 10-bit sources as the reference treats them (ffmpeg.py:211-233): one swscale pass to 8-bit yuv4xxp (with the
+    pc->tv conversion and ordered dither, or as a dithered planar copy when the range is kept), then the 8-bit chain through rgb24."""
+    w, h = 264, 40
+    table = synth.look_lut(33).astype(np.float32)
+    frames = [synth.natural_frame(in_fmt, w, h, t=2, full_range=True), synth.noise_frame(in_fmt, w, h, 9), synth.ramp_frame(in_fmt, w, h)]
+    got = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt, in_range="pc", norm_range=norm_range, out_range=out_range, via_8bit=True)
+    L = oracle_lut(table)
+    from oracle import oracle as O
+    for i, f in enumerate(frames):
+        Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(f, in_fmt, w, h)]
+        exp = synth.pack_planes(O.stage_any(L, in_fmt, out_fmt, Y, U, V, range_pass=1 if norm_range == "tv" else 2,
+                                            in_full_range=(norm_range == "pc"), out_full_range=(out_range == "pc")))
+        assert_bit_exact(out_fmt, w, h, got[i], exp, f"{in_fmt} pc->{norm_range} via 8 bit -> {out_fmt} {out_range} frame {i}")

@@ -241,3 +241,27 @@ def test_any_composite_equals_specialised_composites():
     for chroma, t in ((0, tl), (1, tc)):
         c, o = O.range_coeffs(8, False, chroma)
         assert np.array_equal(np.clip((np.minimum((x * c + o) >> 14, 32767) + 64) >> 7, 0, 255), t)
+
+
+@pytest.mark.parametrize("fmt", ["yuv420p10le", "yuv422p10le", "yuv444p10le"])
+@pytest.mark.parametrize("w,h", [(256, 32), (66, 18), (1920, 36)])
+def test_any_10bit_full_range_prepass(fmt, w, h):
+    """A full-range source deeper than 8 bit: the reference's `scale=in_range=pc:out_range=R,format=yuv4xxp` is ONE swscale pass
+    from yuv4xxp10le(pc) to 8-bit yuv4xxp (ffmpeg.py:211-233).  Both forms (R = tv: range conversion + ordered dither; R = pc: planar
+    copy with the 2x2 dither and the full-range luma correction) bit-exact, plus the exhaustive luma ramp for the pc form."""
+    rng = np.random.default_rng(w + 3 * h)
+    shapes, _ = O.pix_geometry(fmt, w, h)
+    P = [rng.integers(0, 1024, s, dtype=np.uint16) for s in shapes]
+    dst_fmt = fmt.replace("10le", "")
+    for mode, dst_range in ((1, 0), (2, 1)):
+        ref = S.SwsConverter(w, h, fmt, dst_fmt, src_range=1, dst_range=dst_range).convert(P, S.alloc_planes(dst_fmt, w, h))
+        for plane in range(3):
+            assert np.array_equal(O.prepass_10_to_8(mode, plane, P[plane]), ref[plane]), (mode, plane)
+    if fmt == "yuv444p10le" and w == 256:
+        ramp = np.tile((np.arange(8192) >> 3).astype(np.uint16)[None, :], (16, 1))      # every code value at every dither phase
+        mid = np.full((16, 8192), 512, np.uint16)
+        ref = S.SwsConverter(8192, 16, fmt, dst_fmt, src_range=1, dst_range=1).convert([ramp, mid, mid], S.alloc_planes(dst_fmt, 8192, 16))
+        assert np.array_equal(O.prepass_10_to_8(2, 0, ramp), ref[0])
+        ref = S.SwsConverter(8192, 16, fmt, dst_fmt, src_range=1, dst_range=0).convert([ramp, ramp, ramp], S.alloc_planes(dst_fmt, 8192, 16))
+        for plane in range(3):
+            assert np.array_equal(O.prepass_10_to_8(1, plane, ramp), ref[plane])
