@@ -1,22 +1,24 @@
-// Instantiations and launcher of the 4:2:0 warp-window kernel (k420_warp.cuh).  LUTR_K420_OUT10 selects the output side this
-// translation unit builds: yuv420p (k420_warp.cu) or yuv422p10le (k420_warp10.cu) -- two files so that they compile in parallel.
+// Instantiations and launcher of the 4:2:0 warp-window kernel (k420_warp.cuh).  LUTR_K420_OUT selects the output side this
+// translation unit builds: 0 yuv420p (k420_warp.cu), 1 yuv422p10le (k420_warp10.cu), 2 yuv422p, 3 yuv444p (k420_warp422.cu,
+// k420_warp444.cu) -- separate files so that they compile in parallel.
 #include "k420_warp.cuh"
 
-#ifndef LUTR_K420_OUT10
-#define LUTR_K420_OUT10 0
+#ifndef LUTR_K420_OUT
+#define LUTR_K420_OUT 0
 #endif
 
 namespace lutr {
 
 namespace {
 
-constexpr bool kOut10 = LUTR_K420_OUT10 != 0;
+constexpr int kOutSide = LUTR_K420_OUT;
+constexpr bool kRowLocal = kOutSide != 0;  // no vertical chroma filter on the output side
 
 using KernelFn = void (*)(const StageK);
 
 template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int NK, int MINB>
 KernelFn pick_range420(bool range) {
-    return range ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, true, kOut10, MINB> : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, false, kOut10, MINB>;
+    return range ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, true, kOutSide, MINB> : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, false, kOutSide, MINB>;
 }
 
 // Window widths of 128 / 192 / 256 columns (NK = 2 / 3 / 4) and the 33-point specialisation exist for the default semantics
@@ -24,7 +26,7 @@ KernelFn pick_range420(bool range) {
 template <int INTERP, int MINB>
 KernelFn pick420(bool fma, bool clamp, bool fold_nomin, bool range, int n, int nk) {
     if (!fma && !clamp && fold_nomin) {
-        if constexpr (!kOut10) {
+        if constexpr (kOutSide == 0) {
             if (n == 33) {
                 if (nk == 2) return pick_range420<INTERP, false, false, 1, true, 33, 2, MINB>(range);
                 if (nk == 3) return pick_range420<INTERP, false, false, 1, true, 33, 3, MINB>(range);
@@ -50,8 +52,12 @@ KernelFn pick420(bool fma, bool clamp, bool fold_nomin, bool range, int n, int n
 // (frame, window) columns and recomputes 6 halo luma rows per share.  Wide windows amortise the per-row overhead, narrow ones
 // may tile the row without a (recomputing) shifted last window and give longer shares: estimate each.  Small jobs use a smaller
 // grid so that a share is at least 16 chroma rows.  k.wk_unroll (2, 3, 4) forces the window width; k.grid_ctas > 0 the grid.
-#if LUTR_K420_OUT10
+#if LUTR_K420_OUT == 1
 int launch_k420_warp10(const StageK &k_in, int interp, int float_mode, bool grid_forced, void *stream) {
+#elif LUTR_K420_OUT == 2
+int launch_k420_warp422(const StageK &k_in, int interp, int float_mode, bool grid_forced, void *stream) {
+#elif LUTR_K420_OUT == 3
+int launch_k420_warp444(const StageK &k_in, int interp, int float_mode, bool grid_forced, void *stream) {
 #else
 int launch_k420_warp(const StageK &k_in, int interp, int float_mode, bool grid_forced, void *stream) {
 #endif
@@ -71,7 +77,7 @@ int launch_k420_warp(const StageK &k_in, int interp, int float_mode, bool grid_f
         long grid = k.grid_ctas;
         if (!grid_forced && total_c / (kWarps420 * grid) < 16) grid = total_c / (kWarps420 * 16) > 0 ? total_c / (kWarps420 * 16) : 1;
         const double share = (double)total_c / (double)(kWarps420 * grid);  // chroma rows per warp
-        const double cost = (2.0 * share + (kOut10 ? 0.0 : 6.0)) * (W + 24);
+        const double cost = (2.0 * share + (kRowLocal ? 0.0 : 6.0)) * (W + 24);
         if (cost < best) best = cost, best_nk = nk, best_grid = grid;
     }
     if (!best_nk) return LUTR_ERR_UNSUPPORTED;  // row narrower than the narrowest window: the caller uses the band kernel

@@ -27,6 +27,9 @@ constexpr int kWarps420 = 8;
 __device__ __forceinline__ void stg_u16(void *p, unsigned v) {
     asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
 }
+__device__ __forceinline__ void stg_u8(void *p, unsigned v) {
+    asm volatile("st.global.L1::no_allocate.u8 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
+}
 __device__ __forceinline__ void stg_u32(void *p, unsigned v) {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -36,11 +39,13 @@ __device__ __forceinline__ void stg_u32(void *p, unsigned v) {
 __device__ __forceinline__ int pc2tv_y(int v) { return __vimin_s32_relu(((((v << 7) * 14071 + 33561947) >> 14) + 64) >> 7, 255); }
 __device__ __forceinline__ int pc2tv_c(int v) { return __vimin_s32_relu(((((v << 7) * 7197 + 16762880) >> 13) + 64) >> 7, 255); }
 
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int NK, bool RANGE, bool OUT10, int MINB>
+// OUT: 0 = yuv420p, 1 = yuv422p10le, 2 = yuv422p, 3 = yuv444p (the last three are row-local: no vertical filter, no halo rows)
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int NK, bool RANGE, int OUT, int MINB>
 __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K) {
     constexpr int W = 64 * NK, CW = W / 2;  // luma / chroma columns per window
+    constexpr bool ROWLOCAL = OUT != 0, OUT10 = OUT == 1;
     // per warp: (2*u14 | 2*v14 << 16) of the last 8 luma rows, and one staged input row (W luma + CW + CW chroma bytes)
-    __shared__ __align__(16) unsigned s_ring[kWarps420][OUT10 ? 1 : 8][CW];  // unused for 4:2:2 output
+    __shared__ __align__(16) unsigned s_ring[kWarps420][ROWLOCAL ? 1 : 8][CW];  // unused for the row-local outputs
     __shared__ __align__(16) unsigned char s_in[kWarps420][2 * W];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned(*ring)[CW] = s_ring[wib];
@@ -57,6 +62,9 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
     const int taps[8] = {-58, -172, 492, 1786, 1786, 492, -172, -58};
     // output constants of the 10-bit 4:2:2 leg, derived from the 8-bit ones (same sums, different rounding term and shift)
     const unsigned kY10 = fk.kY - (24u << 9), kU10 = fk.kU + (8u << 10), kV10 = fk.kV + (8u << 10);
+    // yuv444p: per-pixel chroma, rounding (256 << 14) + (1 << 8), one float bias per channel, output rounding (32 << 9)
+    const unsigned kU444 = (unsigned)((256 << 14) + (1 << 8) + (32 << 9)) - kMagic * (unsigned)(b.ru + b.gu + b.bu);
+    const unsigned kV444 = (unsigned)((256 << 14) + (1 << 8) + (32 << 9)) - kMagic * (unsigned)(b.rv + b.gv + b.bv);
     // staging loads: NK == 2: every lane brings 4 luma + 2 + 2 chroma bytes; NK == 3, 4: the first W / 8 lanes bring 8 + 4 + 4
     constexpr int YB = NK == 2 ? 4 : 8, CB = YB / 2;
     using YLoad = typename std::conditional<NK == 2, unsigned, uint2>::type;
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
         const int x0 = min((int)win * W, w - W);
         const int y_begin = 2 * (int)j0, y_end = 2 * (int)j1;
         // 4:2:2 output has no vertical filter: no halo rows
-        const int r_first = OUT10 ? y_begin : max(0, y_begin - 3), r_last = OUT10 ? y_end - 1 : min(h - 1, y_end + 2);
+        const int r_first = ROWLOCAL ? y_begin : max(0, y_begin - 3), r_last = ROWLOCAL ? y_end - 1 : min(h - 1, y_end + 2);
         // this lane's share of a row for the staging loads, and its outputs
         const uint8_t *pY = K.p.in[0] + (long)frame * K.p.in_step + (long)r_first * K.p.in_stride[0] + x0 + YB * lane;
         const uint8_t *bU = K.p.in[1] + (long)frame * K.p.in_step + (x0 >> 1) + CB * lane;
@@ -90,10 +98,10 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
         // outputs: yuv420p: luma pair (2 B) per step, 4 chroma bytes per lane and chroma row; yuv422p10le: luma pair (4 B) and one
         // chroma sample per plane (2 B) per step and luma row
         uint8_t *oY = K.p.out[0] + (long)frame * K.p.out_step + (long)r_first * K.p.out_stride[0] + (OUT10 ? 2 : 1) * (x0 + 2 * lane);
-        uint8_t *oU = K.p.out[1] + (long)frame * K.p.out_step + (OUT10 ? (long)r_first * K.p.out_stride[1] + 2 * ((x0 >> 1) + lane)
-                                                                          : (long)(y_begin >> 1) * K.p.out_stride[1] + (x0 >> 1) + 4 * lane);
-        uint8_t *oV = K.p.out[2] + (long)frame * K.p.out_step + (OUT10 ? (long)r_first * K.p.out_stride[2] + 2 * ((x0 >> 1) + lane)
-                                                                          : (long)(y_begin >> 1) * K.p.out_stride[2] + (x0 >> 1) + 4 * lane);
+        // chroma bytes of this lane per step: yuv422p10le 2 (one sample), yuv422p 1, yuv444p 2 (two samples); yuv420p: 4 per chroma row
+        const long c_off = OUT == 1 ? 2 * ((x0 >> 1) + lane) : (OUT == 2 ? (x0 >> 1) + lane : (OUT == 3 ? x0 + 2 * lane : (x0 >> 1) + 4 * lane));
+        uint8_t *oU = K.p.out[1] + (long)frame * K.p.out_step + (long)(ROWLOCAL ? r_first : (y_begin >> 1)) * K.p.out_stride[1] + c_off;
+        uint8_t *oV = K.p.out[2] + (long)frame * K.p.out_step + (long)(ROWLOCAL ? r_first : (y_begin >> 1)) * K.p.out_stride[2] + c_off;
 
         auto load_y = [&](const uint8_t *p) { return *reinterpret_cast<const YLoad *>(p); };
         auto load_c = [&](const uint8_t *base, int y, int cstride) {
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
 
         int y = r_first;
         for (int j = y_begin >> 1; j < (y_end >> 1); ++j) {
-            const int last_needed = OUT10 ? 2 * j + 1 : min(h - 1, 2 * j + 4);
+            const int last_needed = ROWLOCAL ? 2 * j + 1 : min(h - 1, 2 * j + 4);
             for (; y <= last_needed; ++y) {
                 __syncwarp();  // everybody is done with the previous row's staged samples
                 if (loader) {
@@ -156,6 +164,29 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
                         stg_u32(oY + 128 * kk, yq0 | (yq1 << 16));
                         stg_u16(oU + 64 * kk, (unsigned)__vimin_s32_relu((int)(su + kU10) >> 14, 1023));
                         stg_u16(oV + 64 * kk, (unsigned)__vimin_s32_relu((int)(sv + kV10) >> 14, 1023));
+                    } else if (OUT == 2 || OUT == 3) {
+                        // 8-bit row-local outputs: luma as for yuv420p; chroma clip8((2*c14 + 64) >> 7) with
+                        //   yuv422p: c14 = S_pair >> 10 (rgb24ToUV_half)  ==  (S_pair + kU + (32 << 10)) >> 16
+                        //   yuv444p: c14 = S_pixel >> 9 (rgb24ToUV)       ==  (S_pixel + kU444 + (32 << 9)) >> 15
+                        const unsigned yq0 = (unsigned)((int)(sy0 + fk.kY) >> 15), yq1 = (unsigned)((int)(sy1 + fk.kY) >> 15);
+                        stg_u16(oY + 64 * kk, yq0 | (yq1 << 8));
+                        if (OUT == 2) {
+                            stg_u8(oU + 32 * kk, (unsigned)__vimin_s32_relu((int)(su + fk.kU + (32u << 10)) >> 16, 255));
+                            stg_u8(oV + 32 * kk, (unsigned)__vimin_s32_relu((int)(sv + fk.kV + (32u << 10)) >> 16, 255));
+                        } else {
+                            // per-pixel sums carry ONE 0x4B000000 bias per channel: half of the pair constants' bias term
+                            const unsigned kU1 = kU444, kV1 = kV444;
+                            unsigned uq[2], vq[2];
+#pragma unroll
+                            for (int p = 0; p < 2; ++p) {
+                                const unsigned s1u = (unsigned)b.ru * ro[p] + (unsigned)b.gu * go[p] + (unsigned)b.bu * bo[p];
+                                const unsigned s1v = (unsigned)b.rv * ro[p] + (unsigned)b.gv * go[p] + (unsigned)b.bv * bo[p];
+                                uq[p] = (unsigned)__vimin_s32_relu((int)(s1u + kU1) >> 15, 255);
+                                vq[p] = (unsigned)__vimin_s32_relu((int)(s1v + kV1) >> 15, 255);
+                            }
+                            stg_u16(oU + 64 * kk, uq[0] | (uq[1] << 8));
+                            stg_u16(oV + 64 * kk, vq[0] | (vq[1] << 8));
+                        }
                     } else {
                         // rgb24ToY: clip8((2*y14 + 64) >> 7), y14 = S >> 9  ==  (S + (32 << 9)) >> 15; no clip can bind (host-checked)
                         const unsigned yq0 = (unsigned)((int)(sy0 + fk.kY) >> 15), yq1 = (unsigned)((int)(sy1 + fk.kY) >> 15);
@@ -164,10 +195,10 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
                         ring[y & 7][32 * kk + lane] = ((2u * v14) << 16) + 2u * u14;
                     }
                 }
-                if (OUT10) oU += K.p.out_stride[1], oV += K.p.out_stride[2];
+                if (ROWLOCAL) oU += K.p.out_stride[1], oV += K.p.out_stride[2];
                 oY += K.p.out_stride[0];
             }
-            if (OUT10) continue;
+            if (ROWLOCAL) continue;
             __syncwarp();
             // vertical 8-tap decimation for chroma row j over luma rows 2j-3 .. 2j+4; lane = chroma columns 4*lane .. +3
             if (8 * lane < W) {

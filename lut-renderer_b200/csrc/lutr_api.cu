@@ -377,9 +377,15 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         // 4:2:0 warp-window kernel (window width and grid are chosen in the launcher)
         k.wk_unroll = s->wk_nk_forced ? s->wk_unroll : 0;
         k.rows_per_cta = 0, k.bands = 1;
-        if (mixed) {
+        if (s->d.out_fmt == LUTR_PIX_YUV422P10LE) {
             rc = launch_k420_warp10(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
             s->last_kernel = "k420_warp10";
+        } else if (s->d.out_fmt == LUTR_PIX_YUV422P) {
+            rc = launch_k420_warp422(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = "k420_warp422";
+        } else if (s->d.out_fmt == LUTR_PIX_YUV444P) {
+            rc = launch_k420_warp444(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = "k420_warp444";
         } else {
             rc = launch_k420_warp(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
             s->last_kernel = "k420_warp";
@@ -653,7 +659,9 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
     // combinations with a specialised warp-window kernel; everything else runs the generic tile kernel (k_any.cu)
     const bool tri_tet = d.interp == LUTR_INTERP_TRILINEAR || d.interp == LUTR_INTERP_TETRAHEDRAL;
     const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
-    const bool to_master = d.in_fmt == LUTR_PIX_YUV420P && d.out_fmt == LUTR_PIX_YUV422P10LE && d.width >= 128 && tri_tet;
+    // yuv420p source with a row-local output side: the pro-mode master, and the GUI's 8-bit yuv422p / yuv444p choices
+    const bool to_master = d.in_fmt == LUTR_PIX_YUV420P && d.width >= 128 && tri_tet &&
+                           (d.out_fmt == LUTR_PIX_YUV422P10LE || d.out_fmt == LUTR_PIX_YUV422P || d.out_fmt == LUTR_PIX_YUV444P);
     const bool in10 = d.in_fmt == LUTR_PIX_YUV420P10LE || d.in_fmt == LUTR_PIX_YUV422P10LE;
     const bool ordered10 = in10 && tri_tet &&
                            ((d.in_fmt == LUTR_PIX_YUV420P10LE && d.out_fmt == LUTR_PIX_YUV422P10LE) || d.out_fmt == LUTR_PIX_YUV420P10LE ||

@@ -594,3 +594,22 @@ def test_full_range_10bit_source_via_8bit_intermediate(in_fmt, norm_range, out_f
         exp = synth.pack_planes(O.stage_any(L, in_fmt, out_fmt, Y, U, V, range_pass=1 if norm_range == "tv" else 2,
                                             in_full_range=(norm_range == "pc"), out_full_range=(out_range == "pc")))
         assert_bit_exact(out_fmt, w, h, got[i], exp, f"{in_fmt} pc->{norm_range} via 8 bit -> {out_fmt} {out_range} frame {i}")
+
+
+@pytest.mark.parametrize("out_fmt", ["yuv422p", "yuv444p"])
+@pytest.mark.parametrize("w,h,options", [(128, 12, dict()), (256, 14, dict()), (328, 22, dict()), (448, 38, dict(wk_unroll=2)),
+                                         (640, 30, dict(grid_ctas=3)), (1920, 36, dict()), (200, 16, dict(grid_ctas=1))])
+@pytest.mark.parametrize("interp,lut_name,kw", [("tetrahedral", "look33", dict()), ("tetrahedral", "rand64", dict(out_matrix="bt601")),
+                                                ("trilinear", "look33", dict(in_range="pc", norm_range="tv")),
+                                                ("tetrahedral", "wide9", dict(in_range="pc", norm_range="pc"))])
+def test_yuv420p_to_8bit_422_444(out_fmt, w, h, options, interp, lut_name, kw):
+    """The GUI's pix_fmt choices yuv422p / yuv444p on an 8-bit 4:2:0 source (reference main_window.py:767-771): the 4:2:0 warp-window
+    kernel with its row-local 8-bit output sides (pair-sum chroma for 4:2:2, per-pixel chroma for 4:4:4); window widths, tiny grids,
+    range pass, a LUT that leaves [0,1]."""
+    table = (LUTS[lut_name]() if lut_name in LUTS else synth.random_lut(9, 4) * 1.6 - 0.3).astype(np.float32)
+    frames = _frames("yuv420p", w, h, ["natural", "noise", "extremes"])
+    got = gpu_stage("yuv420p", w, h, frames, table, interp=interp, out_pix_fmt=out_fmt, options=options, **kw)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        exp = oracle_stage("yuv420p", w, h, f, L, interp=interp, out_pix_fmt=out_fmt, **kw)
+        assert_bit_exact(out_fmt, w, h, got[i], exp, f"420p->{out_fmt} {w}x{h} {options} {interp} {lut_name} frame {i}")
