@@ -17,33 +17,37 @@ constexpr bool kRowLocal = kOutSide != 0;  // no vertical chroma filter on the o
 using KernelFn = void (*)(const StageK);
 
 template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int NK, int MINB>
-KernelFn pick_range420(bool range) {
-    return range ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, true, kOutSide, MINB> : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, false, kOutSide, MINB>;
+KernelFn pick_range420(bool range, bool in422) {
+    if (in422)
+        return range ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, true, kOutSide, true, MINB>
+                     : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, false, kOutSide, true, MINB>;
+    return range ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, true, kOutSide, false, MINB>
+                 : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, false, kOutSide, false, MINB>;
 }
 
 // Window widths of 128 / 192 / 256 columns (NK = 2 / 3 / 4) and the 33-point specialisation exist for the default semantics
 // with the folded index only (C float order, LUT inside [0,1], size-1 a power of two); everything else runs NK = 4, generic size.
 template <int INTERP, int MINB>
-KernelFn pick420(bool fma, bool clamp, bool fold_nomin, bool range, int n, int nk) {
+KernelFn pick420(bool fma, bool clamp, bool fold_nomin, bool range, bool in422, int n, int nk) {
     if (!fma && !clamp && fold_nomin) {
         if constexpr (kOutSide == 0) {
             if (n == 33) {
-                if (nk == 2) return pick_range420<INTERP, false, false, 1, true, 33, 2, MINB>(range);
-                if (nk == 3) return pick_range420<INTERP, false, false, 1, true, 33, 3, MINB>(range);
-                return pick_range420<INTERP, false, false, 1, true, 33, 4, MINB>(range);
+                if (nk == 2) return pick_range420<INTERP, false, false, 1, true, 33, 2, MINB>(range, in422);
+                if (nk == 3) return pick_range420<INTERP, false, false, 1, true, 33, 3, MINB>(range, in422);
+                return pick_range420<INTERP, false, false, 1, true, 33, 4, MINB>(range, in422);
             }
         }
-        if (nk == 2) return pick_range420<INTERP, false, false, 1, true, 0, 2, MINB>(range);
-        if (nk == 3) return pick_range420<INTERP, false, false, 1, true, 0, 3, MINB>(range);
-        return pick_range420<INTERP, false, false, 1, true, 0, 4, MINB>(range);
+        if (nk == 2) return pick_range420<INTERP, false, false, 1, true, 0, 2, MINB>(range, in422);
+        if (nk == 3) return pick_range420<INTERP, false, false, 1, true, 0, 3, MINB>(range, in422);
+        return pick_range420<INTERP, false, false, 1, true, 0, 4, MINB>(range, in422);
     }
-    if (!fma && !clamp) return pick_range420<INTERP, false, false, 2, false, 0, 4, MINB>(range);
+    if (!fma && !clamp) return pick_range420<INTERP, false, false, 2, false, 0, 4, MINB>(range, in422);
     if (fold_nomin) {
-        if (!fma) return pick_range420<INTERP, false, true, 1, true, 0, 4, MINB>(range);
-        return clamp ? pick_range420<INTERP, true, true, 1, true, 0, 4, MINB>(range) : pick_range420<INTERP, true, false, 1, true, 0, 4, MINB>(range);
+        if (!fma) return pick_range420<INTERP, false, true, 1, true, 0, 4, MINB>(range, in422);
+        return clamp ? pick_range420<INTERP, true, true, 1, true, 0, 4, MINB>(range, in422) : pick_range420<INTERP, true, false, 1, true, 0, 4, MINB>(range, in422);
     }
-    if (!fma) return pick_range420<INTERP, false, true, 2, false, 0, 4, MINB>(range);
-    return clamp ? pick_range420<INTERP, true, true, 2, false, 0, 4, MINB>(range) : pick_range420<INTERP, true, false, 2, false, 0, 4, MINB>(range);
+    if (!fma) return pick_range420<INTERP, false, true, 2, false, 0, 4, MINB>(range, in422);
+    return clamp ? pick_range420<INTERP, true, true, 2, false, 0, 4, MINB>(range, in422) : pick_range420<INTERP, true, false, 2, false, 0, 4, MINB>(range, in422);
 }
 
 }  // namespace
@@ -53,13 +57,13 @@ KernelFn pick420(bool fma, bool clamp, bool fold_nomin, bool range, int n, int n
 // may tile the row without a (recomputing) shifted last window and give longer shares: estimate each.  Small jobs use a smaller
 // grid so that a share is at least 16 chroma rows.  k.wk_unroll (2, 3, 4) forces the window width; k.grid_ctas > 0 the grid.
 #if LUTR_K420_OUT == 1
-int launch_k420_warp10(const StageK &k_in, int interp, int float_mode, bool grid_forced, void *stream) {
+int launch_k420_warp10(const StageK &k_in, bool in422, int interp, int float_mode, bool grid_forced, void *stream) {
 #elif LUTR_K420_OUT == 2
-int launch_k420_warp422(const StageK &k_in, int interp, int float_mode, bool grid_forced, void *stream) {
+int launch_k420_warp422(const StageK &k_in, bool in422, int interp, int float_mode, bool grid_forced, void *stream) {
 #elif LUTR_K420_OUT == 3
-int launch_k420_warp444(const StageK &k_in, int interp, int float_mode, bool grid_forced, void *stream) {
+int launch_k420_warp444(const StageK &k_in, bool in422, int interp, int float_mode, bool grid_forced, void *stream) {
 #else
-int launch_k420_warp(const StageK &k_in, int interp, int float_mode, bool grid_forced, void *stream) {
+int launch_k420_warp(const StageK &k_in, bool in422, int interp, int float_mode, bool grid_forced, void *stream) {
 #endif
     StageK k = k_in;
     const bool fma = float_mode == LUTR_FLOAT_FMA, clamp = k.clamp_out != 0;
@@ -82,8 +86,8 @@ int launch_k420_warp(const StageK &k_in, int interp, int float_mode, bool grid_f
     }
     if (!best_nk) return LUTR_ERR_UNSUPPORTED;  // row narrower than the narrowest window: the caller uses the band kernel
     k.tiles_per_row = (k.w + 64 * best_nk - 1) / (64 * best_nk);
-    KernelFn fn = interp == LUTR_INTERP_TRILINEAR ? pick420<LUTR_INTERP_TRILINEAR, 2>(fma, clamp, fold_nomin, k.range_pass != 0, k.lut.n, best_nk)
-                                                  : pick420<LUTR_INTERP_TETRAHEDRAL, 3>(fma, clamp, fold_nomin, k.range_pass != 0, k.lut.n, best_nk);
+    KernelFn fn = interp == LUTR_INTERP_TRILINEAR ? pick420<LUTR_INTERP_TRILINEAR, 2>(fma, clamp, fold_nomin, k.range_pass != 0, in422, k.lut.n, best_nk)
+                                                  : pick420<LUTR_INTERP_TETRAHEDRAL, 3>(fma, clamp, fold_nomin, k.range_pass != 0, in422, k.lut.n, best_nk);
     fn<<<(unsigned)best_grid, kWarps420 * 32, 0, (cudaStream_t)stream>>>(k);
     return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
 }

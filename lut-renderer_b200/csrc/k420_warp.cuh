@@ -40,7 +40,8 @@ __device__ __forceinline__ int pc2tv_y(int v) { return __vimin_s32_relu(((((v <<
 __device__ __forceinline__ int pc2tv_c(int v) { return __vimin_s32_relu(((((v << 7) * 7197 + 16762880) >> 13) + 64) >> 7, 255); }
 
 // OUT: 0 = yuv420p, 1 = yuv422p10le, 2 = yuv422p, 3 = yuv444p (the last three are row-local: no vertical filter, no halo rows)
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int NK, bool RANGE, int OUT, int MINB>
+// IN422: the source is yuv422p (one chroma row per luma row) instead of yuv420p; same SIMD-path arithmetic (chroma replicated)
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int NK, bool RANGE, int OUT, bool IN422, int MINB>
 __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K) {
     constexpr int W = 64 * NK, CW = W / 2;  // luma / chroma columns per window
     constexpr bool ROWLOCAL = OUT != 0, OUT10 = OUT == 1;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
 
         auto load_y = [&](const uint8_t *p) { return *reinterpret_cast<const YLoad *>(p); };
         auto load_c = [&](const uint8_t *base, int y, int cstride) {
-            return *reinterpret_cast<const CLoad *>(base + (long)(y >> 1) * cstride);
+            return *reinterpret_cast<const CLoad *>(base + (long)(IN422 ? y : (y >> 1)) * cstride);
         };
         YLoad ny{};
         CLoad nu{}, nv{};
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
                 __syncwarp();  // everybody is done with the previous row's staged samples
                 if (loader) {
                     *reinterpret_cast<YLoad *>(sY + YB * lane) = ny;
-                    if (!(y & 1) || y == r_first) {  // an odd row re-uses the chroma row its even neighbour staged
+                    if (IN422 || !(y & 1) || y == r_first) {  // 4:2:0: an odd row re-uses the chroma row its even neighbour staged
                         *reinterpret_cast<CLoad *>(sU + CB * lane) = nu;
                         *reinterpret_cast<CLoad *>(sV + CB * lane) = nv;
                     }
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
                 if (loader && y < r_last) {  // prefetch the next row into registers
                     pY += K.p.in_stride[0];
                     ny = load_y(pY);
-                    if (y & 1) nu = load_c(bU, y + 1, K.p.in_stride[1]), nv = load_c(bV, y + 1, K.p.in_stride[2]);
+                    if (IN422 || (y & 1)) nu = load_c(bU, y + 1, K.p.in_stride[1]), nv = load_c(bV, y + 1, K.p.in_stride[2]);
                 }
                 __syncwarp();
                 const bool own_row = y >= y_begin && y < y_end;

@@ -374,24 +374,25 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         rc = warp_kernel ? launch_k422_warp(k, s->d.interp, s->d.float_mode, st) : launch_yuv422p10(k, s->d.interp, s->d.float_mode, st);
         s->last_kernel = warp_kernel ? "k422_warp" : (k.idx_mode == 2 ? "k_yuv422p10_tma" : (k.idx_mode >= 0 ? "k_yuv422p10_fast" : "k_yuv422p10"));
     } else if (warp_kernel) {
-        // 4:2:0 warp-window kernel (window width and grid are chosen in the launcher)
+        // 4:2:0 / 4:2:2 8-bit source warp-window kernel (window width and grid are chosen in the launcher)
+        const bool in422 = s->d.in_fmt == LUTR_PIX_YUV422P;
         k.wk_unroll = s->wk_nk_forced ? s->wk_unroll : 0;
         k.rows_per_cta = 0, k.bands = 1;
         if (s->d.out_fmt == LUTR_PIX_YUV422P10LE) {
-            rc = launch_k420_warp10(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
-            s->last_kernel = "k420_warp10";
+            rc = launch_k420_warp10(k, in422, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = in422 ? "k420_warp10<422>" : "k420_warp10";
         } else if (s->d.out_fmt == LUTR_PIX_YUV422P) {
-            rc = launch_k420_warp422(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
-            s->last_kernel = "k420_warp422";
+            rc = launch_k420_warp422(k, in422, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = in422 ? "k420_warp422<422>" : "k420_warp422";
         } else if (s->d.out_fmt == LUTR_PIX_YUV444P) {
-            rc = launch_k420_warp444(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
-            s->last_kernel = "k420_warp444";
+            rc = launch_k420_warp444(k, in422, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = in422 ? "k420_warp444<422>" : "k420_warp444";
         } else {
-            rc = launch_k420_warp(k, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
-            s->last_kernel = "k420_warp";
+            rc = launch_k420_warp(k, in422, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
+            s->last_kernel = in422 ? "k420_warp<422>" : "k420_warp";
         }
         if (rc == LUTR_ERR_UNSUPPORTED) rc = run_any();  // this LUT / option combination needs a row of at least 256 columns
-    } else if (mixed) {
+    } else if (mixed || s->d.in_fmt != LUTR_PIX_YUV420P) {
         rc = run_any();
     } else {
         // bands per frame: enough CTAs to fill the device a few times over, but bands of >= 16 rows (7 halo rows each)
@@ -659,9 +660,11 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
     // combinations with a specialised warp-window kernel; everything else runs the generic tile kernel (k_any.cu)
     const bool tri_tet = d.interp == LUTR_INTERP_TRILINEAR || d.interp == LUTR_INTERP_TETRAHEDRAL;
     const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
+    const bool in8 = d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P;  // 8-bit sources of the SIMD-path arithmetic
     // yuv420p source with a row-local output side: the pro-mode master, and the GUI's 8-bit yuv422p / yuv444p choices
-    const bool to_master = d.in_fmt == LUTR_PIX_YUV420P && d.width >= 128 && tri_tet &&
-                           (d.out_fmt == LUTR_PIX_YUV422P10LE || d.out_fmt == LUTR_PIX_YUV422P || d.out_fmt == LUTR_PIX_YUV444P);
+    const bool to_master = in8 && d.width >= 128 && tri_tet && (d.height % 2) == 0 &&  // (the kernel walks pairs of luma rows)
+                           (d.out_fmt == LUTR_PIX_YUV422P10LE || d.out_fmt == LUTR_PIX_YUV422P || d.out_fmt == LUTR_PIX_YUV444P ||
+                            (d.in_fmt == LUTR_PIX_YUV422P && d.out_fmt == LUTR_PIX_YUV420P));
     const bool in10 = d.in_fmt == LUTR_PIX_YUV420P10LE || d.in_fmt == LUTR_PIX_YUV422P10LE;
     const bool ordered10 = in10 && tri_tet &&
                            ((d.in_fmt == LUTR_PIX_YUV420P10LE && d.out_fmt == LUTR_PIX_YUV422P10LE) || d.out_fmt == LUTR_PIX_YUV420P10LE ||

@@ -613,3 +613,26 @@ def test_yuv420p_to_8bit_422_444(out_fmt, w, h, options, interp, lut_name, kw):
     for i, f in enumerate(frames):
         exp = oracle_stage("yuv420p", w, h, f, L, interp=interp, out_pix_fmt=out_fmt, **kw)
         assert_bit_exact(out_fmt, w, h, got[i], exp, f"420p->{out_fmt} {w}x{h} {options} {interp} {lut_name} frame {i}")
+
+
+@pytest.mark.parametrize("out_fmt", ["yuv422p", "yuv420p", "yuv444p", "yuv422p10le"])
+@pytest.mark.parametrize("w,h,options", [(128, 12, dict()), (256, 14, dict()), (328, 22, dict()), (448, 38, dict(wk_unroll=2)),
+                                         (640, 31, dict(grid_ctas=3)), (1920, 36, dict()), (200, 16, dict(grid_ctas=1))])
+@pytest.mark.parametrize("interp,lut_name,kw", [("tetrahedral", "look33", dict()), ("trilinear", "look33", dict(in_range="pc", norm_range="tv")),
+                                                ("tetrahedral", "wide9", dict(in_range="pc", norm_range="pc", out_matrix="bt601")),
+                                                ("tetrahedral", "look33", dict(scale=(0.5, 1.0, 0.75)))])
+def test_yuv422p_8bit_source(out_fmt, w, h, options, interp, lut_name, kw):
+    """8-bit 4:2:2 sources (yuv422p / yuvj422p: MJPEG cameras, the 4:2:2 range-pass intermediate of ffmpeg.py:137-143) through the
+    warp-window kernel's IN422 side -- one chroma row per luma row, otherwise the 4:2:0 arithmetic -- to every row-local output and
+    to yuv420p; odd heights for the 4:2:2 -> 4:2:2 case; per-channel DOMAIN scales fall back to the generic kernel."""
+    kw = dict(kw)
+    scale = kw.pop("scale", (1.0, 1.0, 1.0))
+    if out_fmt == "yuv420p" and h % 2:
+        h += 1
+    table = (LUTS[lut_name]() if lut_name in LUTS else synth.random_lut(9, 4) * 1.6 - 0.3).astype(np.float32)
+    frames = _frames("yuv422p", w, h, ["natural", "noise", "extremes"])
+    got = gpu_stage("yuv422p", w, h, frames, table, scale=scale, interp=interp, out_pix_fmt=out_fmt, options=options, **kw)
+    L = oracle_lut(table, scale)
+    for i, f in enumerate(frames):
+        exp = oracle_stage("yuv422p", w, h, f, L, interp=interp, out_pix_fmt=out_fmt, **kw)
+        assert_bit_exact(out_fmt, w, h, got[i], exp, f"422p->{out_fmt} {w}x{h} {options} {interp} {lut_name} {kw} frame {i}")
