@@ -169,3 +169,22 @@ def test_tetrahedral_against_the_sorted_coordinate_definition():
         acc += w[:, k + 1:k + 2] * t[idx[:, 0], idx[:, 1], idx[:, 2]].astype(np.float64)
     ref = np.floor(np.clip(acc, 0, 1) * 1023.0).astype(np.int64)
     assert np.abs(got - ref).max() <= 1 and (got == ref).mean() > 0.99
+
+
+def test_composite_outputs_match_the_committed_hashes():
+    """The oracle composite (swscale legs + restated lut3d) reproduces the committed SHA-256 digests for 80 seeded cases
+    (tests/golden/oracle_hashes.json, written by tests/golden/gen_oracle_hashes.py): edits to oracle/, another compiler or libm
+    cannot silently move the yardstick the GPU is held to."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("gen_oracle_hashes", os.path.join(here, "gen_oracle_hashes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(here, "oracle_hashes.json")) as f:
+        want = json.load(f)
+    got = mod.compute()
+    assert set(got) == set(want) and len(want) == 80
+    bad = [k for k in want if got[k] != want[k]]
+    assert not bad, bad[:5]
