@@ -636,3 +636,29 @@ def test_yuv422p_8bit_source(out_fmt, w, h, options, interp, lut_name, kw):
     for i, f in enumerate(frames):
         exp = oracle_stage("yuv422p", w, h, f, L, interp=interp, out_pix_fmt=out_fmt, **kw)
         assert_bit_exact(out_fmt, w, h, got[i], exp, f"422p->{out_fmt} {w}x{h} {options} {interp} {lut_name} {kw} frame {i}")
+
+
+def test_gpu_against_committed_golden_digests():
+    """The CUDA path against the COMMITTED golden digests (tests/golden/oracle_hashes.json, 80 seeded cases over layouts, interps,
+    range handling, per-channel DOMAIN scales) -- no oracle code runs here, only its frozen outputs."""
+    import hashlib
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(here, "oracle_hashes.json")) as f:
+        want = json.load(f)
+    luts = {"look17": (synth.look_lut(17), (1.0, 1.0, 1.0)), "rand9": (synth.random_lut(9, 4) * 1.4 - 0.2, (0.5, 1.0, 0.75))}
+    w, h = 200, 36
+    for key, digest in sorted(want.items()):
+        lut_name, fmts, interp, rp, ofr = key.split("|")
+        in_fmt, out_fmt = fmts.split("->")
+        rp, ofr = int(rp.split("=")[1]), int(ofr.split("=")[1])
+        table, scale = luts[lut_name]
+        kw = dict(out_range="pc" if ofr else "tv")
+        if rp == 1:
+            kw.update(in_range="pc", norm_range="tv", via_8bit="10" in in_fmt)
+        elif rp == 2:
+            kw.update(in_range="pc", norm_range="pc", via_8bit=True)
+        frame = synth.noise_frame(in_fmt, w, h, seed=17)
+        got = gpu_stage(in_fmt, w, h, [frame], table.astype(np.float32), scale=scale, out_pix_fmt=out_fmt, interp=interp, **kw)[0]
+        assert hashlib.sha256(got.tobytes()).hexdigest() == digest, key
