@@ -662,3 +662,18 @@ def test_gpu_against_committed_golden_digests():
         frame = synth.noise_frame(in_fmt, w, h, seed=17)
         got = gpu_stage(in_fmt, w, h, [frame], table.astype(np.float32), scale=scale, out_pix_fmt=out_fmt, interp=interp, **kw)[0]
         assert hashlib.sha256(got.tobytes()).hexdigest() == digest, key
+
+
+@pytest.mark.parametrize("n", [129, 256])
+def test_largest_lut_sizes(n):
+    """LUT_3D_SIZE up to lut3d's maximum of 256 (16.7 M nodes, a 268 MB device table): node index arithmetic of every kernel family
+    near its 32-bit limits, noise frames so that the whole table is addressed."""
+    rng = np.random.default_rng(n)
+    table = rng.random((n, n, n, 3), dtype=np.float32)
+    L = oracle_lut(table)
+    for in_fmt, out_fmt, w, h, opts in (("yuv422p10le", "yuv422p10le", 496, 6, dict()), ("yuv420p", "yuv420p", 256, 16, dict()),
+                                        ("yuv420p10le", "yuv420p", 256, 16, dict()), ("yuv444p", "yuv444p10le", 136, 8, dict()),
+                                        ("yuv422p10le", "yuv422p10le", 256, 4, dict(idx_mode=2))):
+        frames = [synth.noise_frame(in_fmt, w, h, seed=n)]
+        got = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt, options=opts)
+        assert_bit_exact(out_fmt, w, h, got[0], oracle_stage(in_fmt, w, h, frames[0], L, out_pix_fmt=out_fmt), f"n={n} {in_fmt}->{out_fmt} {opts}")
