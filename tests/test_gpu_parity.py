@@ -55,7 +55,7 @@ def test_yuv422p10_interp_luts(lut_name, interp):
         assert_bit_exact("yuv422p10le", w, h, got[i], exp, f"422p10 {lut_name} {interp} frame {i}")
 
 
-@pytest.mark.parametrize("w,h", [(16, 2), (24, 1), (64, 3), (1920, 4), (3840, 2), (7680, 2), (4104, 1)])
+@pytest.mark.parametrize("w,h", [(16, 2), (24, 1), (64, 3), (1920, 4), (3840, 2), (7680, 2), (4104, 1), (16384, 2)])
 def test_yuv422p10_geometries(w, h):
     table = LUTS["look33"]().astype(np.float32)
     frames = _frames("yuv422p10le", w, h, ["noise", "natural"])
@@ -249,7 +249,7 @@ def test_yuv420p_interp_luts(lut_name, interp):
         assert_bit_exact("yuv420p", w, h, got[i], oracle_stage("yuv420p", w, h, f, L, interp=interp), f"420p {lut_name} {interp} frame {i}")
 
 
-@pytest.mark.parametrize("w,h", [(16, 12), (64, 14), (200, 18), (1920, 32), (4096, 16), (8192, 12)])
+@pytest.mark.parametrize("w,h", [(16, 12), (64, 14), (200, 18), (1920, 32), (4096, 16), (8192, 12), (16384, 12)])
 def test_yuv420p_geometries(w, h):
     table = LUTS["look33"]().astype(np.float32)
     frames = _frames("yuv420p", w, h, ["noise", "natural"])
