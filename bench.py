@@ -162,6 +162,10 @@ def make_host_frames(cfg, content, count):
         shapes, dt = synth.plane_shapes(cfg["pix_fmt"], cfg["w"], cfg["h"])
         mid = 128 << (np.dtype(dt).itemsize - 1) * 2
         return [synth.pack_planes([np.full(sh, mid + 37 * i + 11 * p, dt) for p, sh in enumerate(shapes)]) for i in range(count)]
+    if content.startswith("grain"):  # "grain0.02": the natural scene with that much per-channel noise (fraction of full scale)
+        g = float(content[5:])
+        return [synth.natural_frame(cfg["pix_fmt"], cfg["w"], cfg["h"], t=7 * i, seed=0, full_range=cfg["in_range"] == "pc", grain=g,
+                                    chroma_grain=g) for i in range(count)]
     return [synth.natural_frame(cfg["pix_fmt"], cfg["w"], cfg["h"], t=7 * i, seed=0, full_range=cfg["in_range"] == "pc")
             for i in range(count)]
 
@@ -375,7 +379,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS) + ["cfg5"])
-    ap.add_argument("--content", default="natural", choices=["natural", "noise", "flat"])
+    ap.add_argument("--content", default="natural", help="natural | noise | flat | grain<sigma> (e.g. grain0.02)")
     ap.add_argument("--float-mode", default="c", choices=["c", "fma"])
     ap.add_argument("--frames-per-step", type=int, default=0)
     ap.add_argument("--rows-per-cta", type=int, default=0)

@@ -41,7 +41,7 @@ def pack_planes(planes) -> np.ndarray:
     return np.concatenate([np.ascontiguousarray(p).view(np.uint8).reshape(-1) for p in planes])
 
 
-def _rgb_scene(w: int, h: int, t: int, seed: int) -> np.ndarray:
+def _rgb_scene(w: int, h: int, t: int, seed: int, grain: float = 0.004, chroma_grain: float = 0.0) -> np.ndarray:
     """float32 RGB in [0,1], (h, w, 3): colour bars, ramps, a moving gradient and disc, mild noise."""
     rng = np.random.default_rng(seed * 7919 + t)
     x = np.linspace(0.0, 1.0, w, dtype=np.float32)[None, :]
@@ -65,7 +65,9 @@ def _rgb_scene(w: int, h: int, t: int, seed: int) -> np.ndarray:
     cx, cy = 0.5 + 0.3 * np.cos(0.05 * t), 0.65 + 0.2 * np.sin(0.07 * t)
     disc = ((x - cx) ** 2 * (w / h) ** 2 + (y - cy) ** 2) < 0.02
     img[disc] = np.array([0.9, 0.4, 0.1], np.float32)
-    img += rng.normal(0.0, 0.004, size=(h, w, 1)).astype(np.float32)  # luma-ish grain
+    img += rng.normal(0.0, grain, size=(h, w, 1)).astype(np.float32)  # luma-ish grain
+    if chroma_grain > 0.0:  # independent per channel: the kind of noise that spreads neighbouring pixels over LUT cells
+        img += rng.normal(0.0, chroma_grain, size=(h, w, 3)).astype(np.float32)
     return np.clip(img, 0.0, 1.0)
 
 
@@ -90,9 +92,11 @@ def _rgb_to_yuv_planes(rgb: np.ndarray, pix_fmt: str, full_range: bool):
     return [q(Y), q(U), q(V)]
 
 
-def natural_frame(pix_fmt: str, w: int, h: int, t: int = 0, seed: int = 0, full_range: bool = False) -> np.ndarray:
-    """Content class A ("natural", testsrc2-like).  One packed frame."""
-    return pack_planes(_rgb_to_yuv_planes(_rgb_scene(w, h, t, seed), pix_fmt, full_range))
+def natural_frame(pix_fmt: str, w: int, h: int, t: int = 0, seed: int = 0, full_range: bool = False, grain: float = 0.004,
+                  chroma_grain: float = 0.0) -> np.ndarray:
+    """Content class A ("natural", testsrc2-like).  One packed frame.  grain / chroma_grain: standard deviation (fraction of full
+    scale) of the luma-like and of the per-channel noise added to the scene."""
+    return pack_planes(_rgb_to_yuv_planes(_rgb_scene(w, h, t, seed, grain, chroma_grain), pix_fmt, full_range))
 
 
 def noise_frame(pix_fmt: str, w: int, h: int, seed: int = 1) -> np.ndarray:
