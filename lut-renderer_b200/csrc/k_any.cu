@@ -32,6 +32,7 @@ namespace {
 constexpr int kTW = 128, kTH = 32;            // luma tile
 constexpr int kCW = kTW + 8, kCH = kTH + 7;   // with halo: columns X0-4 .. X0+TW+3, rows Y0-3 .. Y0+TH+3
 constexpr int kThreads = 256;
+constexpr int kUpRows = (kCH + 1) / 2 + 4;     // chroma rows the 4-tap vertical upsample of a tile's luma rows can touch
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int clamp_hi(int v, int hi) { return __vimin_s32_relu(v, hi); }
@@ -77,6 +78,7 @@ template <int INTERP, bool FMA>
 __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
     __shared__ unsigned s_c[kCH][kCW];       // per luma pixel: (cu | cv << 16) chroma terms (c14, or c15 for 8-bit 4:4:4)
     __shared__ unsigned s_h[kCH][kTW / 2];   // 4:2:0 outputs: per chroma column and luma row, 15-bit (int16 | int16 << 16)
+    __shared__ unsigned s_up[kUpRows][kCW];  // 10-bit 4:2:0 sources: horizontally upsampled chroma rows of the tile, (int16 | int16 << 16)
 
     const int w = K.w, h = K.h;
     const int pre10 = K.any.pre10;  // != 0: 10-bit full-range samples enter through the reference's 8-bit intermediate
@@ -108,6 +110,22 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
         uint8_t *outV = K.p.out[2] + (long)frame * K.p.out_step;
 
         __syncthreads();  // the previous tile's phases B / C have finished reading shared memory
+        // ------------------------------------------------ phase 0 ---------------------------------------------------------
+        // 10-bit 4:2:0 source: swscale upsamples chroma horizontally first (per chroma row, to 15 bits) and vertically afterwards, so
+        // every chroma row the tile needs is upsampled ONCE here instead of four times per pixel in phase A
+        const bool stage_up = sd > 8 && in_sx && in_sy;
+        const int chi = h >> 1;
+        const int uc0 = max((WY0 >> 1) - 2, 0), uc1 = min(((WY1 - 1) >> 1) + 2, chi - 1);
+        if (stage_up) {
+            const int ncols = WX1 - px0;
+            for (int idx = threadIdx.x; idx < (uc1 - uc0 + 1) * ncols; idx += kThreads) {
+                const int cr = idx / ncols, xx = px0 + (idx - cr * ncols);
+                const int cu = up422(reinterpret_cast<const uint16_t *>(inU + (long)(uc0 + cr) * K.p.in_stride[1]), cwi, xx);
+                const int cv = up422(reinterpret_cast<const uint16_t *>(inV + (long)(uc0 + cr) * K.p.in_stride[2]), cwi, xx);
+                s_up[cr][xx - WX0] = ((unsigned)cu & 0xFFFFu) | ((unsigned)cv << 16);
+            }
+            __syncthreads();
+        }
         // ------------------------------------------------ phase A ---------------------------------------------------------
         for (int idx = threadIdx.x; idx < npairs * nrows; idx += kThreads) {
             const int r = idx / npairs, pc = idx - r * npairs;
@@ -172,8 +190,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
                         const uint16_t *ur = reinterpret_cast<const uint16_t *>(inU + (long)y * K.p.in_stride[1]);
                         const uint16_t *vr = reinterpret_cast<const uint16_t *>(inV + (long)y * K.p.in_stride[2]);
                         u17 = 4 * up422(ur, cwi, xx) - 65536, v17 = 4 * up422(vr, cwi, xx) - 65536;
-                    } else {              // yuv420p10le: horizontal upsample of 4 chroma rows, then the 4-tap vertical filter
-                        const int chi = h >> 1, j = y >> 1;
+                    } else {              // yuv420p10le: the staged horizontally upsampled rows, then the 4-tap vertical filter
+                        const int j = y >> 1;
                         int r0, t0, t1, t2, t3;
                         if (y & 1) {
                             r0 = j - 1, t0 = -346, t1 = 3572, t2 = 985, t3 = -115;
@@ -188,9 +206,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (tp[k] == 0) continue;
-                            const int cr = clampi(r0 + k, 0, chi - 1);
-                            su += tp[k] * up422(reinterpret_cast<const uint16_t *>(inU + (long)cr * K.p.in_stride[1]), cwi, xx);
-                            sv += tp[k] * up422(reinterpret_cast<const uint16_t *>(inV + (long)cr * K.p.in_stride[2]), cwi, xx);
+                            const unsigned pk = s_up[clampi(r0 + k, 0, chi - 1) - uc0][xx - WX0];
+                            su += tp[k] * (int)(short)(pk & 0xFFFFu);
+                            sv += tp[k] * ((int)pk >> 16);
                         }
                         u17 = su >> 10, v17 = sv >> 10;
                     }

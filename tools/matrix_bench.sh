@@ -4,6 +4,8 @@ out=gpurun_out/bench_matrix.jsonl; : > $out
 run() { python bench.py --config cfg3 --steps 5 --warmup 3 --frames-per-step 16 --no-cpu-baseline --no-e2e "$@" >> $out 2>> gpurun_out/bench_matrix.err; }
 run --in-fmt yuv444p10le --out-fmt yuv444p10le
 run --in-fmt yuv422p10le --out-fmt yuv422p
+run --in-fmt yuv444p --out-fmt yuv444p
+run --in-fmt yuv420p --out-fmt yuv420p10le
 run --in-fmt yuv420p --out-fmt yuv444p
 run --in-fmt yuv422p --out-fmt yuv422p
 run --in-fmt yuv420p10le --out-fmt yuv420p --opt any_kernel=1
