@@ -501,8 +501,10 @@ def main():
     # end to end: the call a user makes (ColourStage.run_host) on pinned host frames, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        # the same step as the device-resident measurement (F frames per call), bounded to 4 GB of pinned memory per direction
-        Fe = max(1, min(F, int(4e9 // max(stage.in_frame_bytes, stage.out_frame_bytes))))
+        # the same step as the device-resident measurement (F frames per call), bounded to 4 GB of pinned memory per direction and
+        # 16 GB over all ranks of the box
+        budget = min(4e9, 8e9 / world)
+        Fe = max(1, min(F, int(budget // max(stage.in_frame_bytes, stage.out_frame_bytes))))
         pin_in = stage.ctx.pinned_buffer(Fe * stage.in_frame_bytes)
         pin_out = stage.ctx.pinned_buffer(Fe * stage.out_frame_bytes)
         for i in range(Fe):
