@@ -514,3 +514,96 @@ def build_gpu_stage(stage: CommandStage, source_info: Optional[VideoInfo], ffmpe
     _audio_and_mux_args(encode, params)
     encode.append(str(stage.output_path))
     return GpuCommandStage(stage=stage, plan=plan, decode_cmd=decode, encode_cmd=encode)
+
+
+# ---- one clip over several GPUs: contiguous, GOP-aligned frame ranges (BASELINE.json north_star item 4) -----------------------------
+@dataclass
+class ShardCommand:
+    """One frame range of a LUT-carrying stage: its own decoder and encoder process around the GPU stage of ``device``."""
+    index: int
+    device: int
+    start_frame: int
+    frames: int
+    decode_cmd: List[str]
+    encode_cmd: List[str]
+    part_path: Path
+
+
+@dataclass
+class ShardedGpuStage:
+    base: GpuCommandStage
+    shards: List[ShardCommand]
+    concat_list_path: Path
+    concat_list_text: str
+    concat_cmd: List[str]      # stitches the parts (stream copy) and brings audio / metadata over from the source
+
+
+def build_sharded_gpu_stage(stage: CommandStage, source_info: Optional[VideoInfo], devices: List[int],
+                            ffmpeg_bin: str = "ffmpeg") -> Optional[ShardedGpuStage]:
+    """Split a LUT-carrying stage into one (decode, GPU, encode) chain per device over contiguous frame ranges.
+
+    Frames are independent in every filter of the reference's chain, so the ranges need no exchange: each device uploads the LUT
+    once and works through its range.  Range boundaries fall on multiples of the encoder's GOP length (every part starts on a
+    keyframe; the GOP is the one ``build_command`` would set: ``-g``, else round(fps)), parts are stitched with the concat demuxer
+    and stream copy, audio and metadata come from the source in that last step.  Returns None when the clip cannot be cut
+    reliably -- unknown duration / frame rate, variable frame rate, fewer GOPs than devices -- and the caller falls back to
+    ``build_gpu_stage``."""
+    from .sharding import gop_aligned_ranges
+    base = build_gpu_stage(stage, source_info, ffmpeg_bin)
+    info = source_info
+    if base is None or len(devices) < 2 or not info or not info.duration or not info.fps or info.is_vfr:
+        return None
+    params = stage.params
+    fps = float(info.fps)
+    total = int(round(info.duration * fps))
+    try:
+        gop = int(params.gop) if params.gop else max(1, round(fps))
+    except (TypeError, ValueError):
+        gop = max(1, round(fps))
+    if total < gop * len(devices):
+        return None
+    out = Path(stage.output_path)
+    shards: List[ShardCommand] = []
+    lines = []
+    for k, (a, b) in enumerate(gop_aligned_ranges(total, len(devices), gop)):
+        if b <= a:
+            continue
+        part = out.with_name(f"{out.stem}.part{k:02d}{out.suffix}")
+        dec = list(base.decode_cmd)
+        i_at = dec.index("-i")
+        dec[i_at:i_at] = ["-ss", f"{a / fps:.6f}"]           # input seek: frame-accurate for constant-frame-rate sources
+        o_at = dec.index("-f")
+        dec[o_at:o_at] = ["-frames:v", str(b - a)]
+        enc = []
+        skip = 0
+        src_inputs = 0
+        for j, tok in enumerate(base.encode_cmd[:-1]):
+            if skip:
+                skip -= 1
+                continue
+            if tok == "-i":
+                src_inputs += 1
+                if src_inputs == 2:                           # the source as second input (audio / metadata): parts are video only
+                    skip = 1
+                    continue
+            if tok in ("-map", "-map_metadata", "-c:a", "-b:a", "-ar", "-ac", "-movflags"):
+                skip = 1
+                continue
+            enc.append(tok)
+        enc += ["-map", "0:v:0", "-an", str(part)]
+        shards.append(ShardCommand(index=k, device=devices[k % len(devices)], start_frame=a, frames=b - a, decode_cmd=dec,
+                                   encode_cmd=enc, part_path=part))
+        lines.append("file '" + str(part).replace("'", "'\\''") + "'")
+    list_path = out.with_name(f"{out.stem}.parts.txt")
+    concat = [ffmpeg_bin, "-hide_banner"] + (["-y"] if params.overwrite else []) + \
+             ["-f", "concat", "-safe", "0", "-i", str(list_path), "-i", str(stage.source_path), "-map", "0:v:0", "-map", "1:a?",
+              "-map_metadata", "1", "-c:v", "copy"]
+    if params.audio_codec:
+        concat += ["-c:a", params.audio_codec]
+    quiet: List[str] = []
+    _output_tag_args(concat, params, source_info, True, quiet)
+    if getattr(params, "faststart", False):
+        concat += ["-movflags", "+faststart"]
+    concat.append(str(out))
+    return ShardedGpuStage(base=base, shards=shards, concat_list_path=list_path, concat_list_text="\n".join(lines) + "\n",
+                           concat_cmd=concat)

@@ -20,7 +20,7 @@ import threading
 import time
 from typing import Callable, List, Optional
 
-from .ffmpeg import CommandStage, build_command, build_gpu_stage, build_pipeline
+from .ffmpeg import CommandStage, build_command, build_gpu_stage, build_pipeline, build_sharded_gpu_stage
 from .media_info import VideoInfo, probe_video
 from .models import Task, TaskStatus
 
@@ -57,8 +57,11 @@ def _read_exact(pipe, view) -> int:
 
 class TaskRunner:
     def __init__(self, task: Task, ffmpeg_bin: str = "ffmpeg", device: int = 0, callbacks: Optional[TaskCallbacks] = None,
-                 frames_per_batch: int = 8, popen: Callable = subprocess.Popen, probe: Callable = probe_video):
+                 frames_per_batch: int = 8, popen: Callable = subprocess.Popen, probe: Callable = probe_video,
+                 devices: Optional[List[int]] = None):
         self.task, self.ffmpeg_bin, self.device = task, ffmpeg_bin, device
+        # more than one entry: every LUT stage of the task is cut into GOP-aligned frame ranges, one per listed GPU
+        self.devices = list(devices) if devices else [device]
         self.signals = callbacks or TaskCallbacks()
         self.frames_per_batch = max(1, frames_per_batch)
         self._popen, self._probe = popen, probe
@@ -143,23 +146,85 @@ class TaskRunner:
     def _run_stage(self, stage: CommandStage, info: Optional[VideoInfo], base: int, span: int, final: bool) -> Optional[bool]:
         if not stage.lut_path:
             return self._run_plain(stage, info, base, span, final)
-        gpu = build_gpu_stage(stage, info, self.ffmpeg_bin)
+        total = int(round(info.duration * info.fps)) if info and info.duration and info.fps else 0
+        done_lock = threading.Lock()
+        state = {"done": 0, "last": -1}
+
+        def on_frames(n: int) -> None:   # progress over all shards of the stage
+            with done_lock:
+                state["done"] += n
+                if not total:
+                    return
+                pct = min(int(state["done"] / total * span), span - (0 if final else 1))
+                prog = min(base + pct, 100 if final else 99)
+                if prog == state["last"]:
+                    return
+                state["last"] = prog
+            self.signals.progress(self.task.task_id, prog)
+
+        sharded = build_sharded_gpu_stage(stage, info, self.devices, self.ffmpeg_bin) if len(self.devices) > 1 else None
         for note in stage.notes:
             self._log(note)
-        self._log(f"解码: {shlex.join(gpu.decode_cmd)}")
-        self._log(f"编码: {shlex.join(gpu.encode_cmd)}")
+        if sharded is None:
+            gpu = build_gpu_stage(stage, info, self.ffmpeg_bin)
+            self._log(f"解码: {shlex.join(gpu.decode_cmd)}")
+            self._log(f"编码: {shlex.join(gpu.encode_cmd)}")
+            rc = self._pump(gpu.plan, gpu.decode_cmd, gpu.encode_cmd, self.device, on_frames)
+        else:
+            # one clip over several GPUs: contiguous GOP-aligned frame ranges, one decoder / GPU stage / encoder chain per range,
+            # no exchange between them; the parts are stitched by stream copy afterwards
+            results: List[Optional[int]] = [None] * len(sharded.shards)
+
+            def work(k: int, sh) -> None:
+                self._log(f"分片 {sh.index} (GPU {sh.device}, 帧 {sh.start_frame}..{sh.start_frame + sh.frames - 1}): {shlex.join(sh.decode_cmd)}")
+                try:
+                    results[k] = self._pump(sharded.base.plan, sh.decode_cmd, sh.encode_cmd, sh.device, on_frames)
+                except BaseException as exc:  # noqa: BLE001 -- reported through the task status
+                    self._log(f"分片 {sh.index} 失败: {exc}")
+                    results[k] = -1
+
+            threads = [threading.Thread(target=work, args=(k, sh), daemon=True) for k, sh in enumerate(sharded.shards)]
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+            rc = next((r for r in results if r not in (0, None)), 0)
+            if self._cancelled:
+                rc = None
+            elif rc == 0:
+                sharded.concat_list_path.write_text(sharded.concat_list_text, encoding="utf-8")
+                self._log(f"拼接: {shlex.join(sharded.concat_cmd)}")
+                proc = self._spawn(sharded.concat_cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                rc = proc.wait()
+            for path in [sh.part_path for sh in sharded.shards] + [sharded.concat_list_path]:
+                try:
+                    if rc == 0 and path.exists():
+                        path.unlink()
+                except Exception:
+                    pass
+        if rc is None or self._cancelled:
+            return None
+        self._last_returncode = rc
+        if rc == 0:
+            if not final:
+                self.signals.progress(self.task.task_id, base + span)
+            return True
+        return False
+
+    def _pump(self, plan, decode_cmd, encode_cmd, device: int, on_frames: Callable[[int], None]) -> Optional[int]:
+        """decoder process -> raw pipe -> GPU colour stage on ``device`` -> raw pipe -> encoder process, three batches in flight.
+        Returns the first non-zero exit code of the two processes (0 = both fine), None when cancelled."""
         from .stage import ColourStage  # deferred: loads liblutr.so, fails loudly when it is missing
-        colour = ColourStage.from_plan(gpu.plan, device=self.device)
-        lut = colour.ctx.lut_from_cube(gpu.plan.lut_path)
+        colour = ColourStage.from_plan(plan, device=device)
+        lut = colour.ctx.lut_from_cube(plan.lut_path)
         nb = self.frames_per_batch
         # three batches in flight: a reader thread fills pinned input buffers from the decoder's pipe, this thread runs the GPU
         # stage (H2D -> kernel -> D2H), a writer thread drains pinned output buffers into the encoder's pipe
         nbuf = 3
         pin_in = [colour.ctx.pinned_buffer(nb * colour.in_frame_bytes) for _ in range(nbuf)]
         pin_out = [colour.ctx.pinned_buffer(nb * colour.out_frame_bytes) for _ in range(nbuf)]
-        total = int(round(info.duration * info.fps)) if info and info.duration and info.fps else 0
-        dec = self._spawn(gpu.decode_cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, bufsize=0)
-        enc = self._spawn(gpu.encode_cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, bufsize=0)
+        dec = self._spawn(decode_cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, bufsize=0)
+        enc = self._spawn(encode_cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, bufsize=0)
         _grow_pipe(dec.stdout)
         _grow_pipe(enc.stdin)
         free_q: "queue.Queue[int]" = queue.Queue()
@@ -201,7 +266,6 @@ class TaskRunner:
         rt, wt = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
         rt.start()
         wt.start()
-        done, last = 0, -1
         try:
             while not self._cancelled and not errors:
                 i, got = filled_q.get()
@@ -210,13 +274,7 @@ class TaskRunner:
                     break
                 colour.run_host(lut, pin_in[i], pin_out[i], n)
                 write_q.put((i, n * colour.out_frame_bytes))
-                done += n
-                if total:
-                    pct = min(int(done / total * span), span - (0 if final else 1))
-                    prog = min(base + pct, 100 if final else 99)
-                    if prog != last:
-                        last = prog
-                        self.signals.progress(self.task.task_id, prog)
+                on_frames(n)
                 if got < len(pin_in[i].array):
                     break
         finally:
@@ -240,12 +298,7 @@ class TaskRunner:
             raise RuntimeError(f"raw pipe failed: {errors[0]}")
         if self._cancelled:
             return None
-        self._last_returncode = rc_enc or rc_dec
-        if rc_dec == 0 and rc_enc == 0:
-            if not final:
-                self.signals.progress(self.task.task_id, base + span)
-            return True
-        return False
+        return rc_enc or rc_dec
 
     def _run_plain(self, stage: CommandStage, info: Optional[VideoInfo], base: int, span: int, final: bool) -> Optional[bool]:
         """A stage without LUT: the reference's own single ffmpeg process, progress parsed from its log."""
@@ -295,9 +348,12 @@ class TaskManager:
     the visible GPUs round-robin so concurrent runners do not share a device unless there are more runners than GPUs."""
 
     def __init__(self, ffmpeg_bin: str = "ffmpeg", max_concurrency: int = 2, devices: Optional[List[int]] = None,
-                 callbacks: Optional[TaskCallbacks] = None):
+                 callbacks: Optional[TaskCallbacks] = None, shard_clips: bool = False):
         self.ffmpeg_bin, self.max_concurrency = ffmpeg_bin, max(1, min(16, max_concurrency))
         self.devices = devices or [0]
+        # shard_clips: every task is cut into frame ranges over ALL devices (long clips, few tasks) instead of dealing whole
+        # tasks to devices (many clips: BASELINE cfg 5)
+        self.shard_clips = shard_clips
         self.callbacks = callbacks or TaskCallbacks()
         self.tasks: List[Task] = []
         self._runners = {}
@@ -312,7 +368,8 @@ class TaskManager:
 
         def work(task: Task, device: int):
             with sem:
-                runner = TaskRunner(task, self.ffmpeg_bin, device, self.callbacks)
+                runner = TaskRunner(task, self.ffmpeg_bin, device, self.callbacks,
+                                    devices=self.devices if self.shard_clips else None)
                 self._runners[task.task_id] = runner
                 runner.run()
 

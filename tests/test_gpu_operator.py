@@ -136,3 +136,64 @@ def test_task_runner_over_real_pipes(tmp_path):
     for i in (0, 3, 4, 19, 20):
         exp = oracle_stage("yuv420p10le", w, h, frames[i], L, out_pix_fmt="yuv420p")
         assert_bit_exact("yuv420p", w, h, out[i * fb:(i + 1) * fb], exp, f"piped frame {i}")
+
+
+def test_task_runner_shards_one_clip_over_devices(tmp_path):
+    """One clip cut into GOP-aligned frame ranges, one decoder -> GPU -> encoder chain per range running concurrently (here both
+    ranges on cuda:0: the test box has one GPU), parts stitched afterwards.  Stand-in processes honour the same argv a real ffmpeg
+    would get: the decoder starts at -ss and stops after -frames:v, the encoder writes its part file, the concat step joins the
+    files of the list.  The stitched output must be the oracle's, frame for frame, in order."""
+    import subprocess
+    import sys
+    from lut_renderer_b200 import Task
+    from lut_renderer_b200.task_manager import TaskCallbacks, TaskRunner
+    from oracle import oracle as O
+    w, h, fps, nframes = 264, 40, 10.0, 47               # GOP = round(fps) = 10 -> ranges [0, 30) and [30, 47)
+    info = VideoInfo(width=w, height=h, pix_fmt="yuv422p10le", bit_depth=10, colorspace="bt709", color_range="tv", fps=fps,
+                     duration=nframes / fps)
+    cube = tmp_path / "look.cube"
+    synth.write_cube(cube, synth.look_lut(17).astype(np.float32))
+    frames = [synth.natural_frame("yuv422p10le", w, h, t=t) for t in range(nframes)]
+    fb = frames[0].nbytes
+    raw_in = tmp_path / "in.raw"
+    raw_in.write_bytes(np.concatenate(frames).tobytes())
+    out_path = tmp_path / "out.mov"
+    task = Task("t1", tmp_path / "in.mov", out_path, cube, None, ProcessingParams(video_codec="prores_ks"), source_info=info)
+    cmds = []
+
+    def popen(cmd, **kw):
+        cmds.append(list(cmd))
+        if "pipe:1" in cmd:      # decoder: frames [ss * fps, + frames:v)
+            start = int(round(float(cmd[cmd.index("-ss") + 1]) * fps)) if "-ss" in cmd else 0
+            count = int(cmd[cmd.index("-frames:v") + 1]) if "-frames:v" in cmd else nframes
+            code = (f"import sys; f=open({str(raw_in)!r},'rb'); f.seek({start * fb}); sys.stdout.buffer.write(f.read({count * fb}))")
+        elif "pipe:0" in cmd:    # encoder: its stdin into the part file named last
+            code = f"import sys, shutil; shutil.copyfileobj(sys.stdin.buffer, open({cmd[-1]!r}, 'wb'))"
+        else:                    # concat: join the files of the list into the output
+            lst = cmd[cmd.index("-i") + 1]
+            code = ("parts = [l.strip()[6:-1] for l in open(%r) if l.strip()]\n"
+                    "open(%r, 'wb').write(b''.join(open(p, 'rb').read() for p in parts))") % (lst, cmd[-1])
+        return subprocess.Popen([sys.executable, "-c", code], **kw)
+
+    class Rec(TaskCallbacks):
+        events = []
+
+        def progress(self, tid, pct):
+            self.events.append(("progress", pct))
+
+        def finished(self, tid, st):
+            self.events.append(("finished", st))
+
+    rec = Rec()
+    TaskRunner(task, callbacks=rec, frames_per_batch=4, popen=popen, devices=[0, 0]).run()
+    assert rec.events[-1] == ("finished", "completed"), rec.events[-5:]
+    decs = sorted((c for c in cmds if "pipe:1" in c), key=lambda c: float(c[c.index("-ss") + 1]))
+    assert [(c[c.index("-ss") + 1], c[c.index("-frames:v") + 1]) for c in decs] == [("0.000000", "30"), ("3.000000", "17")]
+    assert sum(1 for c in cmds if "concat" in c) == 1
+    assert not list(tmp_path.glob("out.part*")) and not (tmp_path / "out.parts.txt").exists()       # parts cleaned up
+    out = np.frombuffer(out_path.read_bytes(), np.uint8)
+    assert out.size == nframes * fb
+    L = O.OracleLut.from_path(cube)
+    for i in (0, 1, 29, 30, 31, 46):
+        exp = oracle_stage("yuv422p10le", w, h, frames[i], L)
+        assert_bit_exact("yuv422p10le", w, h, out[i * fb:(i + 1) * fb], exp, f"sharded frame {i}")
