@@ -197,3 +197,49 @@ def test_task_runner_shards_one_clip_over_devices(tmp_path):
     for i in (0, 1, 29, 30, 31, 46):
         exp = oracle_stage("yuv422p10le", w, h, frames[i], L)
         assert_bit_exact("yuv422p10le", w, h, out[i * fb:(i + 1) * fb], exp, f"sharded frame {i}")
+
+
+@pytest.mark.timeout(120)
+def test_task_runner_cancel_and_encoder_failure(tmp_path):
+    """The pipelined pump must not hang when things go wrong: cancel() while an endless decoder is streaming ends the task as
+    'canceled' (reference task_manager.py:38-44, 180-183); an encoder that dies mid-stream ends it as 'failed: ...'."""
+    import subprocess
+    import sys
+    import threading
+    import time
+    from lut_renderer_b200 import Task
+    from lut_renderer_b200.task_manager import TaskCallbacks, TaskRunner
+    w, h = 264, 40
+    info = VideoInfo(width=w, height=h, pix_fmt="yuv420p", bit_depth=8, colorspace="bt709", color_range="tv", fps=25.0, duration=1000.0)
+    cube = tmp_path / "look.cube"
+    synth.write_cube(cube, synth.look_lut(17).astype(np.float32))
+    fb = w * h * 3 // 2
+    endless = f"import sys\nb = bytes({fb})\nwhile True: sys.stdout.buffer.write(b)"
+    sink = "import sys\nwhile sys.stdin.buffer.read(1 << 20): pass"
+    dies = "import sys\nsys.stdin.buffer.read(1 << 20)\nsys.exit(3)"
+
+    class Rec(TaskCallbacks):
+        def __init__(self):
+            self.events = []
+
+        def status(self, tid, text):
+            self.events.append(("status", text))
+
+        def finished(self, tid, st):
+            self.events.append(("finished", st))
+
+    def run(encoder_code, cancel_after=None):
+        rec = Rec()
+        task = Task("t", tmp_path / "in.mov", tmp_path / "out.mp4", cube, None, ProcessingParams(), source_info=info)
+        popen = lambda cmd, **kw: subprocess.Popen([sys.executable, "-c", endless if "pipe:1" in cmd else encoder_code], **kw)  # noqa: E731
+        r = TaskRunner(task, callbacks=rec, frames_per_batch=4, popen=popen)
+        if cancel_after is not None:
+            threading.Timer(cancel_after, r.cancel).start()
+        t0 = time.perf_counter()
+        r.run()
+        return rec.events, time.perf_counter() - t0
+
+    events, dt = run(sink, cancel_after=1.5)
+    assert events[-1] == ("finished", "canceled") and dt < 60, (events[-3:], dt)
+    events, dt = run(dies)
+    assert events[-1] == ("finished", "failed") and any(e[0] == "status" and e[1].startswith("failed") for e in events) and dt < 60, events[-3:]

@@ -78,3 +78,104 @@ def test_cancel_before_start(tmp_path):
     r.cancel()
     r.run()
     assert rec.events[-1] == ("finished", "completed") or rec.events[-1] == ("finished", "canceled")
+
+
+# ---- the pipelined GPU pump (reader thread | stage | writer thread) with the stage itself replaced by a byte-flipping stand-in: the
+# ---- threading, pipe, cancel, failure and sharding logic is host code and must hold without a GPU ---------------------------------
+class _FakeBuf:
+    def __init__(self, n):
+        import numpy as np
+        self.array = np.zeros(n, np.uint8)
+
+    def close(self):
+        pass
+
+
+class _FakeCtx:
+    def pinned_buffer(self, n):
+        return _FakeBuf(n)
+
+    def lut_from_cube(self, path):
+        return object()
+
+
+class _FakeStage:
+    def __init__(self, plan):
+        self.ctx = _FakeCtx()
+        self.in_frame_bytes = self.out_frame_bytes = plan.width * plan.height * 3 // 2
+
+    @classmethod
+    def from_plan(cls, plan, device=0, float_mode="c"):
+        return cls(plan)
+
+    def run_host(self, lut, src, dst, n):
+        k = n * self.in_frame_bytes
+        dst.array[:k] = 255 - src.array[:k]
+
+    def close(self):
+        pass
+
+
+def _patched_runner(monkeypatch, tmp_path, popen, duration=4.0, devices=None, batch=4):
+    import lut_renderer_b200.stage as stage_mod
+    monkeypatch.setattr(stage_mod, "ColourStage", _FakeStage)
+    info = VideoInfo(width=64, height=32, pix_fmt="yuv420p", bit_depth=8, colorspace="bt709", color_range="tv", fps=10.0, duration=duration)
+    task = Task("t", tmp_path / "in.mov", tmp_path / "out.mp4", tmp_path / "l.cube", None, ProcessingParams(), source_info=info)
+    rec = Rec()
+    return TaskRunner(task, callbacks=rec, frames_per_batch=batch, popen=popen, devices=devices), rec
+
+
+def test_pump_streams_frames_in_order_and_shards(monkeypatch, tmp_path):
+    import subprocess
+    import sys
+    import numpy as np
+    fb, n, fps = 64 * 32 * 3 // 2, 43, 10.0
+    data = np.random.default_rng(0).integers(0, 256, n * fb, dtype=np.uint8)
+    (tmp_path / "in.raw").write_bytes(data.tobytes())
+
+    def popen(cmd, **kw):
+        if "pipe:1" in cmd:
+            start = int(round(float(cmd[cmd.index("-ss") + 1]) * fps)) if "-ss" in cmd else 0
+            count = int(cmd[cmd.index("-frames:v") + 1]) if "-frames:v" in cmd else n
+            code = f"import sys; f=open({str(tmp_path / 'in.raw')!r},'rb'); f.seek({start * fb}); sys.stdout.buffer.write(f.read({count * fb}))"
+        elif "pipe:0" in cmd:
+            code = f"import sys, shutil; shutil.copyfileobj(sys.stdin.buffer, open({cmd[-1]!r}, 'wb'))"
+        else:
+            lst = cmd[cmd.index("-i") + 1]
+            code = ("parts = [l.strip()[6:-1] for l in open(%r) if l.strip()]\n"
+                    "open(%r, 'wb').write(b''.join(open(p, 'rb').read() for p in parts))") % (lst, cmd[-1])
+        return subprocess.Popen([sys.executable, "-c", code], **kw)
+
+    for devices in (None, [0, 1, 2]):
+        r, rec = _patched_runner(monkeypatch, tmp_path, popen, duration=n / fps, devices=devices)
+        r.run()
+        assert rec.events[-1] == ("finished", "completed"), rec.events[-4:]
+        out = np.frombuffer((tmp_path / "out.mp4").read_bytes(), np.uint8)
+        assert out.size == n * fb and np.array_equal(out, 255 - data), devices
+        assert ("progress", 100) in rec.events
+        (tmp_path / "out.mp4").unlink()
+
+
+def test_pump_cancel_and_encoder_failure_do_not_hang(monkeypatch, tmp_path):
+    import subprocess
+    import sys
+    import threading
+    import time
+    fb = 64 * 32 * 3 // 2
+    endless = f"import sys\nb = bytes({fb})\nwhile True: sys.stdout.buffer.write(b)"
+    sink = "import sys\nwhile sys.stdin.buffer.read(1 << 20): pass"
+    dies = "import sys\nsys.stdin.buffer.read(1 << 16)\nsys.exit(3)"
+
+    def mk(encoder):
+        return lambda cmd, **kw: subprocess.Popen([sys.executable, "-c", endless if "pipe:1" in cmd else encoder], **kw)
+
+    r, rec = _patched_runner(monkeypatch, tmp_path, mk(sink), duration=1e6)
+    threading.Timer(1.0, r.cancel).start()
+    t0 = time.perf_counter()
+    r.run()
+    assert rec.events[-1] == ("finished", "canceled") and time.perf_counter() - t0 < 30, rec.events[-3:]
+    r, rec = _patched_runner(monkeypatch, tmp_path, mk(dies), duration=1e6)
+    t0 = time.perf_counter()
+    r.run()
+    assert rec.events[-1] == ("finished", "failed") and time.perf_counter() - t0 < 30, rec.events[-3:]
+    assert any(e[0] == "status" and e[1].startswith("failed") for e in rec.events)
