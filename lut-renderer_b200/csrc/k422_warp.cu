@@ -23,7 +23,9 @@ namespace lutr {
 
 namespace {
 
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR>
+// IN444: the source is yuv444p10le (ProRes 4444 and the like): one chroma sample per pixel, no upsampling filter; everything behind
+// pass A is unchanged (u17 = (C - 512) * 128 == 4 * (C << 5) - 65536, the same expression pass B applies to the 15-bit value).
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR, bool IN444>
 __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
     __shared__ __align__(16) unsigned s_all[kWarps][kWin + kWin / 2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lane_odd = lane ^ 4;
@@ -70,8 +72,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
         const int y0 = (int)rb * R + wib, y1 = min(h, (int)rb * R + R);
         const int x0 = a + 8 * lane, xc = min(max(x0, 0), w - 8);  // this lane's 8 columns in pass A (clamped into the row)
         const uint8_t *pY = K.p.in[0] + (long)frame * K.p.in_step + (long)y0 * K.p.in_stride[0] + 2 * xc;
-        const uint8_t *pU = K.p.in[1] + (long)frame * K.p.in_step + (long)y0 * K.p.in_stride[1] + xc;
-        const uint8_t *pV = K.p.in[2] + (long)frame * K.p.in_step + (long)y0 * K.p.in_stride[2] + xc;
+        const uint8_t *pU = K.p.in[1] + (long)frame * K.p.in_step + (long)y0 * K.p.in_stride[1] + (IN444 ? 2 * xc : xc);
+        const uint8_t *pV = K.p.in[2] + (long)frame * K.p.in_step + (long)y0 * K.p.in_stride[2] + (IN444 ? 2 * xc : xc);
         uint8_t *oY = K.p.out[0] + (long)frame * K.p.out_step + (long)y0 * K.p.out_stride[0] + 2 * (long)(a + 8 + 8 * lane);
         uint8_t *oU = K.p.out[1] + (long)frame * K.p.out_step + (long)y0 * K.p.out_stride[1] + (long)(a + 8 + 8 * lane);
         uint8_t *oV = K.p.out[2] + (long)frame * K.p.out_step + (long)y0 * K.p.out_stride[2] + (long)(a + 8 + 8 * lane);
@@ -79,18 +81,37 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
         const bool do_c = 8 * lane < nout;
 
         uint4 ny = make_uint4(0u, 0u, 0u, 0u);
-        uint2 nu = make_uint2(0u, 0u), nv = make_uint2(0u, 0u);
-        if (y0 < y1) ny = ldg_s16(pY), nu = ldg_s8(pU), nv = ldg_s8(pV);
+        uint4 nu = make_uint4(0u, 0u, 0u, 0u), nv = make_uint4(0u, 0u, 0u, 0u);  // 4:2:2: 4 samples in .x .y; 4:4:4: 8 samples
+        auto load_c = [](const uint8_t *p) {
+            if (IN444) return ldg_s16(p);
+            const uint2 t = ldg_s8(p);
+            return make_uint4(t.x, t.y, 0u, 0u);
+        };
+        if (y0 < y1) ny = ldg_s16(pY), nu = load_c(pU), nv = load_c(pV);
         for (int y = y0; y < y1; y += kWarps) {
             const uint4 cy = ny;
-            const uint2 cu2 = nu, cv2 = nv;
+            const uint4 cu4 = nu, cv4 = nv;
+            const uint2 cu2 = make_uint2(cu4.x, cu4.y), cv2 = make_uint2(cv4.x, cv4.y);
             if (y + kWarps < y1) {  // prefetch this warp's next row of the window
                 pY += kWarps * (long)K.p.in_stride[0], pU += kWarps * (long)K.p.in_stride[1], pV += kWarps * (long)K.p.in_stride[2];
-                ny = ldg_s16(pY), nu = ldg_s8(pU), nv = ldg_s8(pV);
+                ny = ldg_s16(pY), nu = load_c(pU), nv = load_c(pV);
             }
 
             // ---------------- pass A: chroma upsample for columns a + 8*lane .. + 7 ------------------------------------
-            {
+            if (IN444) {  // one chroma sample per column: c15 = C << 5 (never clips), biased and packed like the filtered form
+                const unsigned uw[4] = {cu4.x, cu4.y, cu4.z, cu4.w}, vw[4] = {cv4.x, cv4.y, cv4.z, cv4.w};
+                unsigned wv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const unsigned U = (uw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu, V = (vw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                    wv[k] = (((V << 5) + (unsigned)kCBias) << 16) | ((U << 5) + (unsigned)kCBias);
+                }
+                __syncwarp();  // pass C of the previous row has finished reading sC
+                *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane + 1)) = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+                *reinterpret_cast<uint4 *>(sYw + 4 * lane) = cy;
+                __syncwarp();
+            } else {
                 // chroma words of the neighbouring lanes: (C[i0-2], C[i0-1]) and (C[i0+4], C[i0+5])
                 unsigned ul = __shfl_up_sync(0xFFFFFFFFu, cu2.y, 1), vl = __shfl_up_sync(0xFFFFFFFFu, cv2.y, 1);
                 unsigned ur = __shfl_down_sync(0xFFFFFFFFu, cu2.x, 1), vr = __shfl_down_sync(0xFFFFFFFFu, cv2.x, 1);
@@ -227,23 +248,27 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
 using KernelFn = void (*)(const StageK);
 
 template <int INTERP, bool FMA, bool CLAMP, int NSZ, bool PK, int MINB, int UNR>
-static KernelFn pick_idx(bool fold_nomin) {
-    if (fold_nomin) return k422_warp<INTERP, FMA, CLAMP, 1, true, NSZ, PK, MINB, UNR>;
-    return k422_warp<INTERP, FMA, CLAMP, 2, false, NSZ, PK, MINB, UNR>;
+static KernelFn pick_idx(bool fold_nomin, bool in444) {
+    if (in444) {
+        if (fold_nomin) return k422_warp<INTERP, FMA, CLAMP, 1, true, NSZ, PK, MINB, UNR, true>;
+        return k422_warp<INTERP, FMA, CLAMP, 2, false, NSZ, PK, MINB, UNR, true>;
+    }
+    if (fold_nomin) return k422_warp<INTERP, FMA, CLAMP, 1, true, NSZ, PK, MINB, UNR, false>;
+    return k422_warp<INTERP, FMA, CLAMP, 2, false, NSZ, PK, MINB, UNR, false>;
 }
 
 template <int INTERP, bool PK, int MINB, int UNR>
-static KernelFn pick_sem(bool fma, bool clamp, bool fold_nomin, int n) {
+static KernelFn pick_sem(bool fma, bool clamp, bool fold_nomin, int n, bool in444) {
     if (!fma && !clamp) {
-        if (n == 65) return pick_idx<INTERP, false, false, 65, PK, MINB, UNR>(fold_nomin);
-        if (n == 33) return pick_idx<INTERP, false, false, 33, PK, MINB, UNR>(fold_nomin);
-        return pick_idx<INTERP, false, false, 0, PK, MINB, UNR>(fold_nomin);
+        if (n == 65) return pick_idx<INTERP, false, false, 65, PK, MINB, UNR>(fold_nomin, in444);
+        if (n == 33) return pick_idx<INTERP, false, false, 33, PK, MINB, UNR>(fold_nomin, in444);
+        return pick_idx<INTERP, false, false, 0, PK, MINB, UNR>(fold_nomin, in444);
     }
-    if (!fma) return pick_idx<INTERP, false, true, 0, PK, MINB, UNR>(fold_nomin);
-    return clamp ? pick_idx<INTERP, true, true, 0, PK, MINB, UNR>(fold_nomin) : pick_idx<INTERP, true, false, 0, PK, MINB, UNR>(fold_nomin);
+    if (!fma) return pick_idx<INTERP, false, true, 0, PK, MINB, UNR>(fold_nomin, in444);
+    return clamp ? pick_idx<INTERP, true, true, 0, PK, MINB, UNR>(fold_nomin, in444) : pick_idx<INTERP, true, false, 0, PK, MINB, UNR>(fold_nomin, in444);
 }
 
-int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream) {
+int launch_k422_warp(const StageK &k, bool in444, int interp, int float_mode, void *stream) {
     const bool fma = float_mode == LUTR_FLOAT_FMA, clamp = k.clamp_out != 0;
     const bool fold_nomin = k.fk.idx_fold && k.wk_nomin;
     KernelFn fn = nullptr;
@@ -251,7 +276,7 @@ int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream) 
     // occupancy / unroll / packed-vs-scalar float variants of the headline configuration, selected by stage options
     if (interp == LUTR_INTERP_TETRAHEDRAL && !fma && !clamp && fold_nomin && k.lut.n == 65) {
 #define WK_CASE(P, M, U) \
-    if (k.wk_pk == P && k.min_blocks == M && k.wk_unroll == U) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, P != 0, M, U>;
+    if (k.wk_pk == P && k.min_blocks == M && k.wk_unroll == U) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, P != 0, M, U, false>;
         WK_CASE(1, 2, 4) WK_CASE(1, 4, 4) WK_CASE(0, 3, 4) WK_CASE(1, 2, 2) WK_CASE(1, 3, 2) WK_CASE(1, 4, 2) WK_CASE(0, 3, 2)
         WK_CASE(0, 4, 2) WK_CASE(1, 2, 1) WK_CASE(1, 3, 1) WK_CASE(1, 4, 1) WK_CASE(0, 3, 1) WK_CASE(0, 4, 1)
 #undef WK_CASE
@@ -259,8 +284,8 @@ int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream) 
 #endif
     if (!fn) {
         // tetrahedral: two columns per step, all four steps unrolled (8 gathers in flight); trilinear has 16 gathers per step
-        fn = interp == LUTR_INTERP_TRILINEAR ? pick_sem<LUTR_INTERP_TRILINEAR, true, 2, 1>(fma, clamp, fold_nomin, k.lut.n)
-                                             : pick_sem<LUTR_INTERP_TETRAHEDRAL, true, 3, 4>(fma, clamp, fold_nomin, k.lut.n);
+        fn = interp == LUTR_INTERP_TRILINEAR ? pick_sem<LUTR_INTERP_TRILINEAR, true, 2, 1>(fma, clamp, fold_nomin, k.lut.n, in444)
+                                             : pick_sem<LUTR_INTERP_TETRAHEDRAL, true, 3, 4>(fma, clamp, fold_nomin, k.lut.n, in444);
     }
     const int minb = k.min_blocks >= 2 && k.min_blocks <= 4 ? k.min_blocks : 3;
     const long total = (long)((k.h + k.rows_per_cta - 1) / k.rows_per_cta) * k.nframes * k.tiles_per_row;

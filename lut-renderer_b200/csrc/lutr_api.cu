@@ -359,7 +359,10 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             rc = launch_k10_warp(k, in420, out420, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
             s->last_kernel = !out420 ? "k10_warp<420,422>" : (in420 ? "k10_warp<420,420>" : "k10_warp<422,420>");
         }
-    } else if (s->d.in_fmt == LUTR_PIX_YUV422P10LE) {
+    } else if (s->d.in_fmt == LUTR_PIX_YUV444P10LE && !warp_kernel) {
+        rc = run_any();
+    } else if (s->d.in_fmt == LUTR_PIX_YUV422P10LE || s->d.in_fmt == LUTR_PIX_YUV444P10LE) {
+        const bool in444 = s->d.in_fmt == LUTR_PIX_YUV444P10LE;
         k.rows_per_cta = s->rows_per_cta > 0 ? s->rows_per_cta : 1;
         if (warp_kernel) {
             // rows per CTA unit (8 warps, interleaved rows): as many as still leave every CTA of the persistent grid >= 32 units
@@ -371,8 +374,8 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             k.rows_per_cta = (int)((r + 7) / 8 * 8);
         }
         k.bands = 1;
-        rc = warp_kernel ? launch_k422_warp(k, s->d.interp, s->d.float_mode, st) : launch_yuv422p10(k, s->d.interp, s->d.float_mode, st);
-        s->last_kernel = warp_kernel ? "k422_warp" : (k.idx_mode == 2 ? "k_yuv422p10_tma" : (k.idx_mode >= 0 ? "k_yuv422p10_fast" : "k_yuv422p10"));
+        rc = warp_kernel ? launch_k422_warp(k, in444, s->d.interp, s->d.float_mode, st) : launch_yuv422p10(k, s->d.interp, s->d.float_mode, st);
+        s->last_kernel = warp_kernel ? (in444 ? "k422_warp<444>" : "k422_warp") : (k.idx_mode == 2 ? "k_yuv422p10_tma" : (k.idx_mode >= 0 ? "k_yuv422p10_fast" : "k_yuv422p10"));
     } else if (warp_kernel) {
         // 4:2:0 / 4:2:2 8-bit source warp-window kernel (window width and grid are chosen in the launcher)
         const bool in422 = s->d.in_fmt == LUTR_PIX_YUV422P;
@@ -671,8 +674,9 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
                             d.out_fmt == LUTR_PIX_YUV420P);  // (10-bit source -> 8-bit 4:2:0 delivery: k10_warp8.cu)
     // (the warp-window kernels work on 8-column groups with 16-byte accesses: widths that are not a multiple of 8, e.g. 854x480,
     // take the generic kernel)
+    const bool master444 = d.in_fmt == LUTR_PIX_YUV444P10LE && d.out_fmt == LUTR_PIX_YUV422P10LE && tri_tet;  // ProRes 4444 -> master
     const bool specialised = !pre10 && d.out_range == LUTR_RANGE_TV && d.interp <= LUTR_INTERP_TETRAHEDRAL && (d.width % 8) == 0 &&
-                             (same_fmt || to_master || ordered10);
+                             (same_fmt || to_master || ordered10 || master444);
     CUDA_TRY(cudaSetDevice(ctx->device));
     lutr_stage *s = new (std::nothrow) lutr_stage;
     if (!s) return LUTR_ERR_NOMEM;

@@ -129,7 +129,7 @@ void build_index_table(int depth, int entries, float scale_times_lutmax, float l
 // launchers (stage_kernels.cu); `stream` is a cudaStream_t
 int launch_yuv422p10(const StageK &k, int interp, int float_mode, void *stream);
 int launch_yuv420p8(const StageK &k, int interp, int float_mode, void *stream);
-int launch_k422_warp(const StageK &k, int interp, int float_mode, void *stream);
+int launch_k422_warp(const StageK &k, bool in444, int interp, int float_mode, void *stream);  // yuv422p10le | yuv444p10le -> yuv422p10le
 int launch_k420_warp(const StageK &k, bool in422, int interp, int float_mode, bool grid_forced, void *stream);
 // 10-bit chains with a 4:2:0 side (k10_warp.cu): yuv420p10le in and / or yuv420p10le out
 int launch_k10_warp(const StageK &k, bool in420, bool out420, int interp, int float_mode, bool grid_forced, void *stream);

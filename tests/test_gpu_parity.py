@@ -676,3 +676,20 @@ def test_largest_lut_sizes(n):
         frames = [synth.noise_frame(in_fmt, w, h, seed=n)]
         got = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt, options=opts)
         assert_bit_exact(out_fmt, w, h, got[0], oracle_stage(in_fmt, w, h, frames[0], L, out_pix_fmt=out_fmt), f"n={n} {in_fmt}->{out_fmt} {opts}")
+
+
+@pytest.mark.parametrize("w,h,options", [(16, 2, dict()), (240, 9, dict()), (248, 16, dict()), (496, 33, dict(grid_ctas=2)),
+                                         (728, 24, dict(rows_per_cta=8)), (1928, 12, dict()), (3840, 4, dict())])
+@pytest.mark.parametrize("interp,lut_name,kw", [("tetrahedral", "look65", dict()), ("tetrahedral", "rand64", dict(out_matrix="bt601")),
+                                                ("trilinear", "look33", dict(in_matrix="bt2020", out_matrix="bt2020")),
+                                                ("tetrahedral", "wide9", dict(in_range="pc", norm_range="pc"))])
+def test_yuv444p10_source_to_master(w, h, options, interp, lut_name, kw):
+    """10-bit 4:4:4 sources (ProRes 4444 and the like) to the pro-mode master yuv422p10le on the headline kernel's IN444 side: per-pixel
+    chroma, no upsampling filter; window edges, odd heights, several frames."""
+    table = (LUTS[lut_name]() if lut_name in LUTS else synth.random_lut(9, 4) * 1.6 - 0.3).astype(np.float32)
+    frames = _frames("yuv444p10le", w, h, ["natural", "noise", "extremes", "ramp"])
+    got = gpu_stage("yuv444p10le", w, h, frames, table, interp=interp, out_pix_fmt="yuv422p10le", options=options, **kw)
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        exp = oracle_stage("yuv444p10le", w, h, f, L, interp=interp, out_pix_fmt="yuv422p10le", **kw)
+        assert_bit_exact("yuv422p10le", w, h, got[i], exp, f"444p10->422p10 {w}x{h} {options} {interp} {lut_name} frame {i}")
