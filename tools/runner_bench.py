@@ -24,6 +24,7 @@ ap.add_argument("--frames", type=int, default=240)
 ap.add_argument("--size", default="3840x2160")
 ap.add_argument("--fmt", default="yuv422p10le")
 ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--shards", type=int, default=1, help="cut the clip into this many frame ranges, each with its own decoder / encoder chain (all on GPU 0)")
 args = ap.parse_args()
 w, h = (int(v) for v in args.size.split("x"))
 tmp = Path(tempfile.mkdtemp(prefix="lutr_runner_"))
@@ -34,12 +35,18 @@ depth = 10 if "10" in args.fmt else 8
 info = VideoInfo(width=w, height=h, pix_fmt=args.fmt, bit_depth=depth, colorspace="bt709", color_range="tv", fps=25.0, duration=args.frames / 25.0)
 params = ProcessingParams(video_codec="prores_ks" if depth == 10 else "libx264")
 task = Task("bench", tmp / "in.mov", tmp / "out.mov", cube, None, params, source_info=info)
-gen = f"import sys; b=open({str(tmp / 'frame.raw')!r},'rb').read(); o=sys.stdout.buffer\nfor _ in range({args.frames}): o.write(b)"
 sink = "import sys; i=sys.stdin.buffer\nwhile i.read(1<<22): pass"
 
 
 def popen(cmd, **kw):
-    return subprocess.Popen([sys.executable, "-c", gen if "pipe:1" in cmd else sink], **kw)
+    if "pipe:1" in cmd:      # generator: as many frames as this decoder was asked for
+        count = int(cmd[cmd.index("-frames:v") + 1]) if "-frames:v" in cmd else args.frames
+        code = f"import sys; b=open({str(tmp / 'frame.raw')!r},'rb').read(); o=sys.stdout.buffer\nfor _ in range({count}): o.write(b)"
+    elif "pipe:0" in cmd:    # sink (a part file must exist for the concat step of a sharded run)
+        code = sink + f"\nopen({cmd[-1]!r}, 'wb').close()"
+    else:                    # concat step of a sharded run
+        code = f"open({cmd[-1]!r}, 'wb').close()"
+    return subprocess.Popen([sys.executable, "-c", code], **kw)
 
 
 class Rec(TaskCallbacks):
@@ -51,7 +58,7 @@ class Rec(TaskCallbacks):
 
 rec = Rec()
 t0 = time.perf_counter()
-TaskRunner(task, callbacks=rec, frames_per_batch=args.batch, popen=popen).run()
+TaskRunner(task, callbacks=rec, frames_per_batch=args.batch, popen=popen, devices=[0] * args.shards if args.shards > 1 else None).run()
 dt = time.perf_counter() - t0
-print(json.dumps({"frames": args.frames, "size": args.size, "fmt": args.fmt, "batch": args.batch, "status": rec.status_text,
+print(json.dumps({"frames": args.frames, "size": args.size, "fmt": args.fmt, "batch": args.batch, "shards": args.shards, "status": rec.status_text,
                   "fps_including_startup": round(args.frames / dt, 1), "GBs_in": round(args.frames * frame.nbytes / dt / 1e9, 2)}))
