@@ -449,8 +449,13 @@ def plan_colour_stage(params: ProcessingParams, lut_path: Optional[Path], source
             reference_filters.append("zscale=dither=error_diffusion")
         reference_filters.append(f"format={out_pix_fmt}")
     else:
-        # nothing forced: the reference leaves the choice to the encoder; the GPU stage hands back the working format
-        out_pix_fmt = in_pix_fmt
+        # nothing forced: the reference leaves the choice to the encoder, which sees lut3d's RGB output
+        out_pix_fmt = _NEGOTIATED_PIX_FMT.get((params.video_codec, work_depth))
+        if out_pix_fmt:
+            plan_notes.append(f"pix_fmt 未指定: 按编码器协商结果输出 {out_pix_fmt}（lut3d 输出 RGB，{params.video_codec} 选择无色度损失的格式）")
+        else:
+            out_pix_fmt = in_pix_fmt
+            plan_notes.append(f"pix_fmt 未指定: GPU 阶段按源格式输出 {out_pix_fmt}（与参考实现的编码器协商结果可能不同）")
 
     tags = _policy(params, "lut_output_tags", "bt709")
     if tags == "inherit" and params.inherit_color_metadata:
@@ -478,29 +483,68 @@ class GpuCommandStage:
     encode_cmd: List[str]
 
 
+class RawPipeUnsupported(ValueError):
+    """The clip cannot go through the raw-video pipe without changing its timing; the caller runs the reference's
+    single-process command for this stage instead (and says so in the task log)."""
+
+
+# what FFmpeg's format negotiation picks when nothing is forced and lut3d hands RGB to the encoder (SURVEY.md App. A: the
+# reference emits neither format= nor -pix_fmt for 8-bit sources): the encoder's best match for rgb24 / gbrp10le.  Only the
+# encoders whose choice is a planar YUV layout of the stage are listed; others keep the source layout (logged as a deviation).
+_NEGOTIATED_PIX_FMT = {("libx264", 8): "yuv444p", ("libx264", 10): "yuv444p10le"}
+
+
+def _pipe_rate_text(fps: float) -> str:
+    """A frame rate as ffmpeg's -r takes it, exact for the NTSC family (VideoInfo keeps only the float)."""
+    n = round(fps * 1001)
+    if n % 1000 == 0 and abs(n / 1001 - fps) < 2e-3 and abs(fps - round(fps)) > 1e-3:
+        return f"{n}/1001"
+    if abs(fps - round(fps)) < 1e-3:
+        return str(int(round(fps)))
+    return f"{fps:.6f}".rstrip("0").rstrip(".")
+
+
+def _pipe_timing(params: ProcessingParams, info: Optional[VideoInfo]) -> Tuple[List[str], str]:
+    """(timing options of the decoder, frame rate declared on the encoder's rawvideo input).
+
+    rawvideo carries no timestamps, so the pipe must run at a constant rate that reproduces the SOURCE timing; the conversion to a
+    requested output rate stays where the reference has it, on the output side (`-fps_mode cfr -r X`, reference ffmpeg.py:262-286).
+    Variable-frame-rate sources are made constant in the decoder when the reference would force CFR anyway; a VFR source in
+    passthrough mode, or a source of unknown rate, cannot cross the pipe."""
+    vfr = bool(info and info.is_vfr)
+    src_fps = _pipe_rate_text(info.fps) if info and info.fps else None
+    if vfr:
+        if params.fps:       # resample to the requested constant rate in the decoder (same frame selection as cfr on the output)
+            return ["-fps_mode", "cfr", "-r", params.fps], params.fps
+        if params.force_cfr and src_fps:
+            return ["-fps_mode", "cfr", "-r", src_fps], src_fps
+        raise RawPipeUnsupported("源为 VFR 且保持时间戳（passthrough）：原始视频管道无法携带时间戳")
+    if not src_fps:
+        raise RawPipeUnsupported("未知源帧率：原始视频管道需要恒定帧率")
+    return ["-fps_mode", "passthrough"], src_fps
+
+
 def build_gpu_stage(stage: CommandStage, source_info: Optional[VideoInfo], ffmpeg_bin: str = "ffmpeg") -> Optional[GpuCommandStage]:
     """Split a LUT-carrying stage into a raw-video decoder and a raw-video encoder around the GPU stage.
 
     The encoder command carries every option ``build_command`` would have put on the single process
     (codec, rate control, timing, tags); only the `-vf` colour chain is gone and its input is the raw pipe.
-    Audio and metadata are taken from the original source as a second input.
+    Audio and metadata are taken from the original source as a second input.  Raises ``RawPipeUnsupported`` when the
+    source timing cannot be reproduced over a raw pipe (see ``_pipe_timing``).
     """
     plan = plan_colour_stage(stage.params, stage.lut_path, source_info, stage.notes)
     if plan is None:
         return None
     params = stage.params
-    _, fps_text = _resolve_fps(params, source_info)
+    decode_timing, pipe_fps = _pipe_timing(params, source_info)
     decode = [ffmpeg_bin, "-hide_banner", "-v", "error", "-i", str(stage.source_path), "-map", "0:v:0", "-f", "rawvideo",
               # untouched samples: 8-bit full-range sources are named yuvj4xxp; deeper ones keep their own name (no yuvj form exists)
               "-pix_fmt", ("yuvj" + plan.in_pix_fmt[3:]) if plan.in_range == "pc" and plan.in_pix_fmt in ("yuv420p", "yuv422p", "yuv444p")
-              else plan.in_pix_fmt,
-              "-fps_mode", "passthrough", "pipe:1"]
+              else plan.in_pix_fmt] + decode_timing + ["pipe:1"]
     encode = [ffmpeg_bin, "-hide_banner"]
     if params.overwrite:
         encode.append("-y")
-    encode += ["-f", "rawvideo", "-pix_fmt", plan.out_pix_fmt, "-s", f"{plan.width}x{plan.height}"]
-    if fps_text:
-        encode += ["-r", fps_text]
+    encode += ["-f", "rawvideo", "-pix_fmt", plan.out_pix_fmt, "-s", f"{plan.width}x{plan.height}", "-r", pipe_fps]
     encode += ["-i", "pipe:0", "-i", str(stage.source_path), "-map", "0:v:0", "-map", "1:a?", "-map_metadata", "1"]
     if params.video_codec:
         encode += ["-c:v", params.video_codec]
@@ -527,6 +571,7 @@ class ShardCommand:
     decode_cmd: List[str]
     encode_cmd: List[str]
     part_path: Path
+    open_ended: bool = False   # the last range: no -frames:v, it may deliver more frames than planned (never fewer)
 
 
 @dataclass
@@ -565,15 +610,20 @@ def build_sharded_gpu_stage(stage: CommandStage, source_info: Optional[VideoInfo
     out = Path(stage.output_path)
     shards: List[ShardCommand] = []
     lines = []
-    for k, (a, b) in enumerate(gop_aligned_ranges(total, len(devices), gop)):
-        if b <= a:
-            continue
+    ranges = [(a, b) for a, b in gop_aligned_ranges(total, len(devices), gop) if b > a]
+    for k, (a, b) in enumerate(ranges):
+        last = k == len(ranges) - 1
         part = out.with_name(f"{out.stem}.part{k:02d}{out.suffix}")
         dec = list(base.decode_cmd)
         i_at = dec.index("-i")
-        dec[i_at:i_at] = ["-ss", f"{a / fps:.6f}"]           # input seek: frame-accurate for constant-frame-rate sources
-        o_at = dec.index("-f")
-        dec[o_at:o_at] = ["-frames:v", str(b - a)]
+        if a > 0:
+            # input seek half a frame early: ffmpeg's accurate seek drops frames whose pts lie before the target, so a target that
+            # rounding (of this text or of container timestamps) puts a hair past frame a's pts would lose frame a
+            dec[i_at:i_at] = ["-ss", f"{(a - 0.5) / fps:.6f}"]
+        if not last:
+            # the final range runs to the end of the stream: an under-estimated duration must not drop the tail
+            o_at = dec.index("-f")
+            dec[o_at:o_at] = ["-frames:v", str(b - a)]
         enc = []
         skip = 0
         src_inputs = 0
@@ -592,7 +642,7 @@ def build_sharded_gpu_stage(stage: CommandStage, source_info: Optional[VideoInfo
             enc.append(tok)
         enc += ["-map", "0:v:0", "-an", str(part)]
         shards.append(ShardCommand(index=k, device=devices[k % len(devices)], start_frame=a, frames=b - a, decode_cmd=dec,
-                                   encode_cmd=enc, part_path=part))
+                                   encode_cmd=enc, part_path=part, open_ended=last))
         lines.append("file '" + str(part).replace("'", "'\\''") + "'")
     list_path = out.with_name(f"{out.stem}.parts.txt")
     concat = [ffmpeg_bin, "-hide_banner"] + (["-y"] if params.overwrite else []) + \

@@ -20,7 +20,7 @@ import threading
 import time
 from typing import Callable, List, Optional
 
-from .ffmpeg import CommandStage, build_command, build_gpu_stage, build_pipeline, build_sharded_gpu_stage
+from .ffmpeg import CommandStage, RawPipeUnsupported, build_command, build_gpu_stage, build_pipeline, build_sharded_gpu_stage
 from .media_info import VideoInfo, probe_video
 from .models import Task, TaskStatus
 
@@ -162,14 +162,20 @@ class TaskRunner:
                 state["last"] = prog
             self.signals.progress(self.task.task_id, prog)
 
-        sharded = build_sharded_gpu_stage(stage, info, self.devices, self.ffmpeg_bin) if len(self.devices) > 1 else None
+        try:
+            sharded = build_sharded_gpu_stage(stage, info, self.devices, self.ffmpeg_bin) if len(self.devices) > 1 else None
+            gpu = build_gpu_stage(stage, info, self.ffmpeg_bin) if sharded is None else None
+        except RawPipeUnsupported as exc:
+            # rawvideo carries no timestamps: this clip keeps the reference's own single-process command (CPU lut3d inside
+            # ffmpeg), said out loud in the task log -- never a silent switch
+            self._log(f"提示: GPU 色彩阶段不适用于此片段（{exc}），本阶段改用参考实现的单进程 ffmpeg 命令")
+            return self._run_plain(stage, info, base, span, final)
         for note in stage.notes:
             self._log(note)
         if sharded is None:
-            gpu = build_gpu_stage(stage, info, self.ffmpeg_bin)
             self._log(f"解码: {shlex.join(gpu.decode_cmd)}")
             self._log(f"编码: {shlex.join(gpu.encode_cmd)}")
-            rc = self._pump(gpu.plan, gpu.decode_cmd, gpu.encode_cmd, self.device, on_frames)
+            rc, _ = self._pump(gpu.plan, gpu.decode_cmd, gpu.encode_cmd, self.device, on_frames)
         else:
             # one clip over several GPUs: contiguous GOP-aligned frame ranges, one decoder / GPU stage / encoder chain per range,
             # no exchange between them; the parts are stitched by stream copy afterwards
@@ -178,7 +184,12 @@ class TaskRunner:
             def work(k: int, sh) -> None:
                 self._log(f"分片 {sh.index} (GPU {sh.device}, 帧 {sh.start_frame}..{sh.start_frame + sh.frames - 1}): {shlex.join(sh.decode_cmd)}")
                 try:
-                    results[k] = self._pump(sharded.base.plan, sh.decode_cmd, sh.encode_cmd, sh.device, on_frames)
+                    rc_k, frames_k = self._pump(sharded.base.plan, sh.decode_cmd, sh.encode_cmd, sh.device, on_frames)
+                    # a part that is short (or, for a closed range, long) would lose / duplicate frames at the cut: refuse to stitch
+                    if rc_k == 0 and (frames_k < sh.frames or (frames_k > sh.frames and not sh.open_ended)):
+                        self._log(f"分片 {sh.index} 帧数不符: 计划 {sh.frames}，实际 {frames_k}")
+                        rc_k = -2
+                    results[k] = rc_k
                 except BaseException as exc:  # noqa: BLE001 -- reported through the task status
                     self._log(f"分片 {sh.index} 失败: {exc}")
                     results[k] = -1
@@ -211,9 +222,9 @@ class TaskRunner:
             return True
         return False
 
-    def _pump(self, plan, decode_cmd, encode_cmd, device: int, on_frames: Callable[[int], None]) -> Optional[int]:
+    def _pump(self, plan, decode_cmd, encode_cmd, device: int, on_frames: Callable[[int], None]):
         """decoder process -> raw pipe -> GPU colour stage on ``device`` -> raw pipe -> encoder process, three batches in flight.
-        Returns the first non-zero exit code of the two processes (0 = both fine), None when cancelled."""
+        Returns (first non-zero exit code of the two processes -- 0 = both fine, None when cancelled --, frames processed)."""
         from .stage import ColourStage  # deferred: loads liblutr.so, fails loudly when it is missing
         colour = ColourStage.from_plan(plan, device=device)
         lut = colour.ctx.lut_from_cube(plan.lut_path)
@@ -266,6 +277,7 @@ class TaskRunner:
         rt, wt = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
         rt.start()
         wt.start()
+        frames_done = 0
         try:
             while not self._cancelled and not errors:
                 i, got = filled_q.get()
@@ -274,9 +286,12 @@ class TaskRunner:
                     break
                 colour.run_host(lut, pin_in[i], pin_out[i], n)
                 write_q.put((i, n * colour.out_frame_bytes))
+                frames_done += n
                 on_frames(n)
                 if got < len(pin_in[i].array):
                     break
+        except BaseException as exc:  # noqa: BLE001 -- a failing GPU call must take the children down, not leave them blocked on full pipes
+            errors.append(exc)
         finally:
             write_q.put(None)
             wt.join()
@@ -295,15 +310,16 @@ class TaskRunner:
                 b.close()
             colour.close()
         if errors and not self._cancelled:
-            raise RuntimeError(f"raw pipe failed: {errors[0]}")
+            raise RuntimeError(f"colour stage / raw pipe failed: {errors[0]}")
         if self._cancelled:
-            return None
-        return rc_enc or rc_dec
+            return None, frames_done
+        return (rc_enc or rc_dec), frames_done
 
     def _run_plain(self, stage: CommandStage, info: Optional[VideoInfo], base: int, span: int, final: bool) -> Optional[bool]:
-        """A stage without LUT: the reference's own single ffmpeg process, progress parsed from its log."""
+        """The reference's own single ffmpeg process, progress parsed from its log: stages without a LUT, and LUT stages whose
+        timing cannot cross a raw pipe (``RawPipeUnsupported``)."""
         import re
-        cmd = build_command(stage.source_path, stage.output_path, stage.params, None, self.ffmpeg_bin, info, stage.notes)
+        cmd = build_command(stage.source_path, stage.output_path, stage.params, stage.lut_path, self.ffmpeg_bin, info, stage.notes)
         for note in stage.notes:
             self._log(note)
         self._log(f"命令: {shlex.join(cmd)}")

@@ -21,8 +21,11 @@ def _info(pix_fmt, depth, colorspace="bt709", color_range="tv"):
 
 
 CASES = {
-    # fast delivery, defaults: 8-bit source, libx264, nothing forced -> the stage hands back the working layout
-    "default_8bit": (_info("yuv420p", 8), ProcessingParams(), ("yuv420p", "yuv420p", "tv", "tv", "tv", "tetrahedral")),
+    # fast delivery, defaults: 8-bit source, libx264, nothing forced -> the encoder negotiates yuv444p behind lut3d's RGB
+    # (SURVEY App. A cfg 1); an encoder outside the negotiation table gets the working layout back
+    "default_8bit": (_info("yuv420p", 8), ProcessingParams(), ("yuv420p", "yuv444p", "tv", "tv", "tv", "tetrahedral")),
+    "default_8bit_hw": (_info("yuv420p", 8), ProcessingParams(video_codec="h264_videotoolbox"),
+                        ("yuv420p", "yuv420p", "tv", "tv", "tv", "tetrahedral")),
     # BASELINE cfg 2: full-range source, forced bt709, trilinear, force_8bit
     "cfg2_pc_to_tv": (_info("yuvj420p", 8, "bt470bg", "pc"),
                       ProcessingParams(bit_depth_policy="force_8bit", lut_interp="trilinear", lut_input_matrix="bt709"),

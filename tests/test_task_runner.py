@@ -126,6 +126,7 @@ def _patched_runner(monkeypatch, tmp_path, popen, duration=4.0, devices=None, ba
 
 
 def test_pump_streams_frames_in_order_and_shards(monkeypatch, tmp_path):
+    import math
     import subprocess
     import sys
     import numpy as np
@@ -135,8 +136,9 @@ def test_pump_streams_frames_in_order_and_shards(monkeypatch, tmp_path):
 
     def popen(cmd, **kw):
         if "pipe:1" in cmd:
-            start = int(round(float(cmd[cmd.index("-ss") + 1]) * fps)) if "-ss" in cmd else 0
-            count = int(cmd[cmd.index("-frames:v") + 1]) if "-frames:v" in cmd else n
+            # accurate seek: the first frame whose pts is not before the target (the runner seeks half a frame early)
+            start = math.ceil(float(cmd[cmd.index("-ss") + 1]) * fps - 1e-6) if "-ss" in cmd else 0
+            count = int(cmd[cmd.index("-frames:v") + 1]) if "-frames:v" in cmd else n - start
             code = f"import sys; f=open({str(tmp_path / 'in.raw')!r},'rb'); f.seek({start * fb}); sys.stdout.buffer.write(f.read({count * fb}))"
         elif "pipe:0" in cmd:
             code = f"import sys, shutil; shutil.copyfileobj(sys.stdin.buffer, open({cmd[-1]!r}, 'wb'))"
@@ -179,3 +181,76 @@ def test_pump_cancel_and_encoder_failure_do_not_hang(monkeypatch, tmp_path):
     r.run()
     assert rec.events[-1] == ("finished", "failed") and time.perf_counter() - t0 < 30, rec.events[-3:]
     assert any(e[0] == "status" and e[1].startswith("failed") for e in rec.events)
+
+
+def test_short_shard_is_refused_instead_of_stitched(monkeypatch, tmp_path):
+    """A part that delivers fewer frames than its planned range (a seek that dropped a frame, a truncated source) would lose frames
+    at the cut: the runner fails the task instead of concatenating (frame counts are checked before the concat)."""
+    import math
+    import subprocess
+    import sys
+    fb, n, fps = 64 * 32 * 3 // 2, 40, 10.0
+    (tmp_path / "in.raw").write_bytes(bytes(n * fb))
+
+    def popen(cmd, **kw):
+        if "pipe:1" in cmd:
+            start = math.ceil(float(cmd[cmd.index("-ss") + 1]) * fps - 1e-6) if "-ss" in cmd else 0
+            count = int(cmd[cmd.index("-frames:v") + 1]) - 1 if "-frames:v" in cmd else n - start      # every closed range is one short
+            code = f"import sys; f=open({str(tmp_path / 'in.raw')!r},'rb'); f.seek({start * fb}); sys.stdout.buffer.write(f.read({count * fb}))"
+        else:
+            code = "import sys\nwhile sys.stdin.buffer.read(1 << 20): pass"
+        return subprocess.Popen([sys.executable, "-c", code], **kw)
+
+    r, rec = _patched_runner(monkeypatch, tmp_path, popen, duration=n / fps, devices=[0, 1])
+    r.run()
+    assert rec.events[-1] == ("finished", "failed"), rec.events[-4:]
+    assert any(e[0] == "log" and "帧数不符" in e[1] for e in rec.events)
+
+
+def test_stage_failure_kills_the_children_and_fails_the_task(monkeypatch, tmp_path):
+    """run_host raising (a CUDA error, an unsupported stride) must not leave the decoder blocked on a full pipe and the task
+    'running' forever: the children are killed and the task reports failed: <text>."""
+    import subprocess
+    import sys
+    import time
+    import lut_renderer_b200.stage as stage_mod
+    fb = 64 * 32 * 3 // 2
+    endless = f"import sys\nb = bytes({fb})\nwhile True: sys.stdout.buffer.write(b)"
+    sink = "import sys\nwhile sys.stdin.buffer.read(1 << 20): pass"
+
+    class Boom(_FakeStage):
+        calls = 0
+
+        def run_host(self, lut, src, dst, n):
+            Boom.calls += 1
+            if Boom.calls == 2:
+                raise RuntimeError("CUDA error: injected")
+            super().run_host(lut, src, dst, n)
+
+    procs = []
+
+    def popen(cmd, **kw):
+        p = subprocess.Popen([sys.executable, "-c", endless if "pipe:1" in cmd else sink], **kw)
+        procs.append(p)
+        return p
+
+    r, rec = _patched_runner(monkeypatch, tmp_path, popen, duration=1e6)
+    monkeypatch.setattr(stage_mod, "ColourStage", Boom)
+    t0 = time.perf_counter()
+    r.run()
+    assert time.perf_counter() - t0 < 30
+    assert rec.events[-1] == ("finished", "failed") and any(e[0] == "status" and "injected" in e[1] for e in rec.events), rec.events[-3:]
+    assert all(p.poll() is not None for p in procs)
+
+
+def test_vfr_passthrough_source_keeps_the_reference_command(monkeypatch, tmp_path):
+    """rawvideo has no timestamps: a VFR source in passthrough mode cannot cross the pipe, the stage runs as the reference's own
+    single ffmpeg command (with the lut3d filter) and the log says so."""
+    cmds = []
+    info = VideoInfo(width=64, height=32, pix_fmt="yuv420p", bit_depth=8, colorspace="bt709", color_range="tv", fps=25.0, duration=1.0, is_vfr=True)
+    task = Task("t", tmp_path / "in.mov", tmp_path / "out.mp4", tmp_path / "l.cube", None, ProcessingParams(force_cfr=False), source_info=info)
+    rec = Rec()
+    TaskRunner(task, callbacks=rec, popen=lambda cmd, **k: (cmds.append(cmd), FakeProc(["time=00:00:01.00\n"], 0))[1]).run()
+    assert rec.events[-1] == ("finished", "completed")
+    assert len(cmds) == 1 and any("lut3d" in tok for tok in cmds[0]) and "pipe:1" not in cmds[0]
+    assert any(e[0] == "log" and "GPU 色彩阶段不适用" in e[1] for e in rec.events)
