@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblutr.so")
+# LUTR_LIB: another build of the same library (A/B measurements of kernel variants in one GPU session)
+LIB_PATH = os.environ.get("LUTR_LIB") or os.path.join(_HERE, "liblutr.so")
 
 OK, ERR_INVALID_ARG, ERR_INVALID_DATA, ERR_LUT_SIZE, ERR_IO, ERR_NOMEM, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
 

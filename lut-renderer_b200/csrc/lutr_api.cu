@@ -73,6 +73,7 @@ struct lutr_stage {
     int fast_threads = 0;  // threads per CTA of the TMA kernel (0 = auto)
     int wk_pk = 1;         // warp-window kernel: packed f32x2 instructions
     int wk_unroll = 4;     // warp-window kernel: pass B steps unrolled together (experiment builds)
+    int wk_var = -1;       // experiment builds: variant of the headline kernel
     int wk_nk_forced = 0;  // 4:2:0 warp-window kernel: wk_unroll was set explicitly (2 or 4 steps of 64 columns per window)
     int wk_minb = 3;       // warp-window kernel: CTAs per SM the register budget is set for
     bool wk_minb_set = false;  // ... set explicitly (the ordered-row-walk kernels default to 2 CTAs per SM: 128 registers, no spills)
@@ -288,6 +289,9 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             fk.kY = (uint32_t)((16 << 17) + (1 << 10) + (8 << 11)) - magic * (uint32_t)(s->b.ry + s->b.gy + s->b.by);
             fk.kU = (uint32_t)((128 << 17) + (1 << 10)) - magic * (uint32_t)(s->b.ru + s->b.gu + s->b.bu);
             fk.kV = (uint32_t)((128 << 17) + (1 << 10)) - magic * (uint32_t)(s->b.rv + s->b.gv + s->b.bv);
+            fk.cu5[0] = 32u * (uint32_t)s->b.ru, fk.cu5[1] = 32u * (uint32_t)s->b.gu, fk.cu5[2] = 32u * (uint32_t)s->b.bu;
+            fk.cv5[0] = 32u * (uint32_t)s->b.rv, fk.cv5[1] = 32u * (uint32_t)s->b.gv, fk.cv5[2] = 32u * (uint32_t)s->b.bv;
+            fk.kU5 = 32u * fk.kU, fk.kV5 = 32u * fk.kV;
         } else {
             fk.kY = (uint32_t)((32 << 14) + (1 << 8) + (32 << 9)) - magic * (uint32_t)(s->b.ry + s->b.gy + s->b.by);
             fk.kU = (uint32_t)((256 << 15) + (1 << 9)) - 2u * magic * (uint32_t)(s->b.ru + s->b.gu + s->b.bu);
@@ -307,6 +311,7 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             k.wk_pk = s->wk_pk;
             k.wk_one = 1.0f;
             k.wk_unroll = s->wk_unroll;
+            k.wk_var = s->wk_var;
             k.min_blocks = s->d.interp == LUTR_INTERP_TRILINEAR ? 2 : s->wk_minb;
             // the clip of the LUT coordinate to lut_max is dead code unless some code value overshoots it: try them all
             k.wk_nomin = 1;
@@ -840,6 +845,7 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
         if (s->chunk) free_host_pipeline(s);
         s->chunk_mb = value;
     } else if (!std::strcmp(name, "wk_pk")) s->wk_pk = value;
+    else if (!std::strcmp(name, "wk_var")) s->wk_var = value;
     else if (!std::strcmp(name, "wk_unroll")) s->wk_unroll = value, s->wk_nk_forced = 1;
     else if (!std::strcmp(name, "wk_minb")) s->wk_minb = value >= 2 && value <= 4 ? value : 3, s->wk_minb_set = true;
     else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value >= 2 && value <= 4 ? value : 3;

@@ -68,6 +68,9 @@ struct FastK {
     uint32_t vr4, vg4, ug4, ub4;  // 4 * chroma gains (u17 = 4*c15 - 65536 folded in)
     uint32_t kR, kG, kB;          // luma offset, rounding and the -65536*gain terms
     uint32_t kY, kU, kV;          // rounding/offset constants of RGB->YUV with the 0x4B000000 bias folded in
+    // 10-bit 4:2:2 output side: chroma rows of the RGB->YUV matrix and kU / kV times 32 (mod 2^32), so that the 15-bit term
+    // S >> 11 is the high half of the 32-bit sum and one PRMT packs the (u, v) pair (k422_warp.cu, pass B)
+    uint32_t cu5[3], cv5[3], kU5, kV5;
     int32_t n2b, nb, totalb;      // byte steps of the LUT axes: n*n*16, n*16, sum + 16
     // arithmetic index path: s = min(fl(fl(x*in_scale) * sr), lut_max) computed as fma(2^23+x, idx_mul, idx_add) [* idx_sr]
     float idx_mul, idx_add, idx_sr;
@@ -108,6 +111,7 @@ struct StageK {
     float wk_one;                // 1.0f the compiler cannot constant-fold (see addp2 in k422_warp.cu)
     int32_t wk_unroll;           // pass B double-iterations unrolled together (1, 2, 4)
     int32_t wk_nomin;            // 1: the clip of the LUT coordinate to lut_max can never bind (host-checked), drop it
+    int32_t wk_var;              // experiment builds: variant id of the headline kernel (k422_warp.cu), -1 = default
     AnyK any;                    // generic tile kernel only
 };
 

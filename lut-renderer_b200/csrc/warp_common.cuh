@@ -132,6 +132,12 @@ __device__ __forceinline__ f2 addrz2s(f2 a, float b) {  // a + b (b broadcast), 
     }
     return r;
 }
+__device__ __forceinline__ f2 addrm2s(f2 a, float b) {  // a + b (b broadcast), round toward -inf (packed only)
+    f2 r;
+    asm("{.reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%4}; add.rm.f32x2 d,a,b; mov.b64 {%0,%1},d;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b));
+    return r;
+}
 template <bool PK>
 __device__ __forceinline__ f2 fma2s(f2 a, float b, float c) {  // fma(a, b, c), b and c broadcast
     f2 r;
@@ -209,13 +215,15 @@ __device__ __forceinline__ LutC make_lutc(const StageK &K) {
     return C;
 }
 
-// lut3d for NP (1 or 2) pixels of one lane.  m*: 0x4B000000 | code (i.e. the float 2^23 + code); outputs biased ints.
-// PKB: packed instructions also for the blend and the truncating store.  There only three of the four lanes of a float4 node
-// carry data and every per-pixel weight has to be duplicated into a register pair first, so the scalar form can win.
-#ifndef LUTR_PACKED_BLEND
-#define LUTR_PACKED_BLEND 1
+// lut3d for the two pixels of one lane.  m*: 0x4B000000 | code (i.e. the float 2^23 + code); outputs biased ints.
+// A float4 node carries three channels, so a packed instruction on its (z, w) half does one useful operation.  BM picks what to do
+// about it: 0 = packed (x, y) and packed (z, w) per pixel (w wasted); 1 = packed (x, y), scalar z (a scalar FP32 instruction can also
+// issue to the FMA-lite pipe, a packed one occupies both FMA pipes); 2 = packed (x, y) per pixel and the z channels of the lane's two
+// pixels packed together, the per-pixel weights being pairs already.  Same operations, same order, same roundings in all three.
+#ifndef LUTR_BMODE
+#define LUTR_BMODE 1
 #endif
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, bool PKB = PK && (LUTR_PACKED_BLEND != 0)>
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int BM = (PK ? LUTR_BMODE : 0)>
 __device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, const unsigned mr[2],
                                            const unsigned mg[2], const unsigned mb[2], unsigned ro[2], unsigned go[2], unsigned bo[2]) {
     const int N = NSZ ? NSZ : C.n, N2 = NSZ ? NSZ * NSZ : C.n2;
@@ -235,8 +243,23 @@ __device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, con
         pv[c][0] = __float_as_uint(t.x), pv[c][1] = __float_as_uint(t.y);
         dd[c][0] = __float_as_uint(d.x), dd[c][1] = __float_as_uint(d.y);
     }
-    f2 cxy[2], czw[2];
+    // scalar forms of the z channel (BM 1): intrinsics are never contracted
+    auto zmul = [](float a, float b) { return __fmul_rn(a, b); };
+    auto zacc = [&](float c, float w, float acc) { return FMA ? __fmaf_rn(c, w, acc) : __fadd_rn(__fmul_rn(c, w), acc); };
+    f2 cxy[2];
+    f2 czw[2];       // BM 0: (z, w) per pixel;  BM 1: .x = z per pixel;  BM 2: czw[0] = (z of pixel 0, z of pixel 1)
     if (INTERP == LUTR_INTERP_TRILINEAR) {
+        // lerp(v0, v1, f) = v0 + (v1 - v0) * f along r, then g, then b
+        auto lerp = [&](f2 a, f2 b, float f) {
+            const f2 df = sub2<PK>(b, a);
+            return FMA ? fma2ss<PK>(df, f, a) : addp2<PK>(mul2s<PK>(df, f), a, C.one);
+        };
+        auto lerp1 = [&](float a, float b, float f) { return zacc(__fsub_rn(b, a), f, a); };
+        auto lerpp = [&](f2 a, f2 b, f2 f) {
+            const f2 df = sub2<PK>(b, a);
+            return FMA ? fma2<PK>(df, f, a) : addp2<PK>(mul2<PK>(df, f), a, C.one);
+        };
+        float zq[2][8];
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             const unsigned base = pv[0][p] * (unsigned)N2 + (pv[1][p] * (unsigned)N + C.kbase) + pv[2][p];
@@ -245,20 +268,32 @@ __device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, con
 #pragma unroll
             for (int q = 0; q < 8; ++q)
                 v[q] = __ldg(tab + (base + (q & 4 ? N2 : 0) + (q & 2 ? N : 0) + (q & 1)));
-            // lerp(v0, v1, f) = v0 + (v1 - v0) * f along r, then g, then b
-            auto lerp = [&](f2 a, f2 b, float f) {
-                const f2 df = sub2<PK>(b, a);
-                return FMA ? fma2ss<PK>(df, f, a) : addp2<PK>(mul2s<PK>(df, f), a, C.one);
-            };
-            f2 xy[4], zw[4];
+            f2 xy[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                xy[q] = lerp(f2{v[q].x, v[q].y}, f2{v[q + 4].x, v[q + 4].y}, dr);
-                zw[q] = lerp(f2{v[q].z, v[q].w}, f2{v[q + 4].z, v[q + 4].w}, dr);
+            for (int q = 0; q < 4; ++q) xy[q] = lerp(f2{v[q].x, v[q].y}, f2{v[q + 4].x, v[q + 4].y}, dr);
+            cxy[p] = lerp(lerp(xy[0], xy[2], dg), lerp(xy[1], xy[3], dg), db);
+            if (BM == 0) {
+                f2 zw[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) zw[q] = lerp(f2{v[q].z, v[q].w}, f2{v[q + 4].z, v[q + 4].w}, dr);
+                czw[p] = lerp(lerp(zw[0], zw[2], dg), lerp(zw[1], zw[3], dg), db);
+            } else if (BM == 1) {
+                float z[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) z[q] = lerp1(v[q].z, v[q + 4].z, dr);
+                czw[p].x = lerp1(lerp1(z[0], z[2], dg), lerp1(z[1], z[3], dg), db), czw[p].y = 0.f;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) zq[p][q] = v[q].z;
             }
-            const f2 xy0 = lerp(xy[0], xy[2], dg), xy1 = lerp(xy[1], xy[3], dg);
-            const f2 zw0 = lerp(zw[0], zw[2], dg), zw1 = lerp(zw[1], zw[3], dg);
-            cxy[p] = lerp(xy0, xy1, db), czw[p] = lerp(zw0, zw1, db);
+        }
+        if (BM == 2) {
+            const f2 drp = f2{__uint_as_float(dd[0][0]), __uint_as_float(dd[0][1])}, dgp = f2{__uint_as_float(dd[1][0]), __uint_as_float(dd[1][1])};
+            const f2 dbp = f2{__uint_as_float(dd[2][0]), __uint_as_float(dd[2][1])};
+            f2 z[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) z[q] = lerpp(f2{zq[0][q], zq[1][q]}, f2{zq[0][q + 4], zq[1][q + 4]}, drp);
+            czw[0] = lerpp(lerpp(z[0], z[2], dgp), lerpp(z[1], z[3], dgp), dbp);
         }
     } else {
         int mx[2], md[2], mn[2];
@@ -283,23 +318,51 @@ __device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, con
         const float w0s[2] = {w0.x, w0.y}, w1s[2] = {w1.x, w1.y}, w2s[2] = {w2.x, w2.y}, w3s[2] = {d3.x, d3.y};
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            f2 axy = mul2s<PKB>(f2{v0[p].x, v0[p].y}, w0s[p]), azw = mul2s<PKB>(f2{v0[p].z, v0[p].w}, w0s[p]);
-            axy = wacc<PKB, FMA>(f2{vA[p].x, vA[p].y}, w1s[p], axy, C.one), azw = wacc<PKB, FMA>(f2{vA[p].z, vA[p].w}, w1s[p], azw, C.one);
-            axy = wacc<PKB, FMA>(f2{vB[p].x, vB[p].y}, w2s[p], axy, C.one), azw = wacc<PKB, FMA>(f2{vB[p].z, vB[p].w}, w2s[p], azw, C.one);
-            axy = wacc<PKB, FMA>(f2{v1[p].x, v1[p].y}, w3s[p], axy, C.one), azw = wacc<PKB, FMA>(f2{v1[p].z, v1[p].w}, w3s[p], azw, C.one);
-            cxy[p] = axy, czw[p] = azw;
+            f2 axy = mul2s<PK>(f2{v0[p].x, v0[p].y}, w0s[p]);
+            axy = wacc<PK, FMA>(f2{vA[p].x, vA[p].y}, w1s[p], axy, C.one);
+            axy = wacc<PK, FMA>(f2{vB[p].x, vB[p].y}, w2s[p], axy, C.one);
+            cxy[p] = wacc<PK, FMA>(f2{v1[p].x, v1[p].y}, w3s[p], axy, C.one);
+            if (BM == 0) {
+                f2 azw = mul2s<PK>(f2{v0[p].z, v0[p].w}, w0s[p]);
+                azw = wacc<PK, FMA>(f2{vA[p].z, vA[p].w}, w1s[p], azw, C.one);
+                azw = wacc<PK, FMA>(f2{vB[p].z, vB[p].w}, w2s[p], azw, C.one);
+                czw[p] = wacc<PK, FMA>(f2{v1[p].z, v1[p].w}, w3s[p], azw, C.one);
+            } else if (BM == 1) {
+                float az = zmul(v0[p].z, w0s[p]);
+                az = zacc(vA[p].z, w1s[p], az), az = zacc(vB[p].z, w2s[p], az);
+                czw[p].x = zacc(v1[p].z, w3s[p], az), czw[p].y = 0.f;
+            }
+        }
+        if (BM == 2) {
+            f2 az = mul2<PK>(f2{v0[0].z, v0[1].z}, w0);
+            az = FMA ? fma2<PK>(f2{vA[0].z, vA[1].z}, w1, az) : addp2<PK>(mul2<PK>(f2{vA[0].z, vA[1].z}, w1), az, C.one);
+            az = FMA ? fma2<PK>(f2{vB[0].z, vB[1].z}, w2, az) : addp2<PK>(mul2<PK>(f2{vB[0].z, vB[1].z}, w2), az, C.one);
+            czw[0] = FMA ? fma2<PK>(f2{v1[0].z, v1[1].z}, d3, az) : addp2<PK>(mul2<PK>(f2{v1[0].z, v1[1].z}, d3), az, C.one);
         }
     }
+    // out = (int)(v * max), clipped only when the table leaves [0, 1]; truncating store: + 2^23 toward zero leaves 0x4B000000 | (int)v
+    auto clampf = [&](float v) { return fminf(fmaxf(v, 0.f), C.out_scale); };
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        f2 fxy = mul2s<PKB>(cxy[p], C.out_scale), fzw = mul2s<PKB>(czw[p], C.out_scale);
-        if (CLAMP) {
-            fxy.x = fminf(fmaxf(fxy.x, 0.f), C.out_scale), fxy.y = fminf(fmaxf(fxy.y, 0.f), C.out_scale);
-            fzw.x = fminf(fmaxf(fzw.x, 0.f), C.out_scale);
+        f2 fxy = mul2s<PK>(cxy[p], C.out_scale);
+        if (CLAMP) fxy.x = clampf(fxy.x), fxy.y = clampf(fxy.y);
+        const f2 txy = addprz2s<PK>(fxy, 8388608.f, C.one);
+        ro[p] = __float_as_uint(txy.x), go[p] = __float_as_uint(txy.y);
+        if (BM == 0) {
+            f2 fzw = mul2s<PK>(czw[p], C.out_scale);
+            if (CLAMP) fzw.x = clampf(fzw.x);
+            bo[p] = __float_as_uint(addprz2s<PK>(fzw, 8388608.f, C.one).x);
+        } else if (BM == 1) {
+            float fz = __fmul_rn(czw[p].x, C.out_scale);
+            if (CLAMP) fz = clampf(fz);
+            bo[p] = __float_as_uint(__fadd_rz(fz, 8388608.f));
         }
-        // truncating store: + 2^23 toward zero leaves 0x4B000000 | (int)v in the bits
-        const f2 txy = addprz2s<PKB>(fxy, 8388608.f, C.one), tzw = addprz2s<PKB>(fzw, 8388608.f, C.one);
-        ro[p] = __float_as_uint(txy.x), go[p] = __float_as_uint(txy.y), bo[p] = __float_as_uint(tzw.x);
+    }
+    if (BM == 2) {
+        f2 fz = mul2s<PK>(czw[0], C.out_scale);
+        if (CLAMP) fz.x = clampf(fz.x), fz.y = clampf(fz.y);
+        const f2 tz = addprz2s<PK>(fz, 8388608.f, C.one);
+        bo[0] = __float_as_uint(tz.x), bo[1] = __float_as_uint(tz.y);
     }
 }
 
