@@ -92,26 +92,6 @@ bool make_rgb2yuv(int matrix, Rgb2YuvK &k) {
     return true;
 }
 
-void build_index_table(int depth, int entries, float scale_times_lutmax, float lut_max, IdxEntry *out) {
-    // entry i is a two's-complement code of log2(entries) bits; codes outside [0, 2^depth-1] are what the unsigned clip
-    // of the YUV->RGB leg would have produced (negative -> 0, too large -> max)
-    const int maxv = (1 << depth) - 1;
-    const float in_scale = 1.0f / maxv;
-    for (int i = 0; i < entries; ++i) {
-        int v = i >= entries / 2 ? i - entries : i;
-        v = v < 0 ? 0 : (v > maxv ? maxv : v);
-        // lut3d: s = clip(src * scale_f * (scale.c * lut_max), 0, lut_max); prev = (int)s; d = s - prev
-        volatile float a = (float)v * in_scale;   // volatile: one rounding per operation, no contraction
-        volatile float b = a * scale_times_lutmax;
-        float s = b < 0.f ? 0.f : b;
-        s = s > lut_max ? lut_max : s;
-        const int prev = (int)s;
-        volatile float d = s - (float)prev;
-        out[i].prev = prev;
-        out[i].d = d;
-    }
-}
-
 // libswscale >= 7.1 range conversion on the 15-bit intermediates (lumRangeTo/FromJpeg_c, chrRangeTo/FromJpeg_c with the
 // constants of solve_range_convert), pinned against libswscale 9.1.100 through oracle/lutr_oracle.c orc_range_coeffs:
 //   coeff = ceil(((dst_max - dst_min) << 14) / (src_max - src_min)),

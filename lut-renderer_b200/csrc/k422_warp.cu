@@ -347,6 +347,7 @@ int launch_k422_warp(const StageK &k, bool in444, int interp, int float_mode, vo
     const long total = (long)((k.h + k.rows_per_cta - 1) / k.rows_per_cta) * k.nframes * k.tiles_per_row;
     long grid = k.grid_ctas > 0 ? k.grid_ctas : 148 * minb;
     if (grid > total) grid = total;
+    if (k.wk_carveout > 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, k.wk_carveout);  // experiments: % of the unified L1 / shared array
     fn<<<(unsigned)grid, kWarps * 32, 0, (cudaStream_t)stream>>>(k);
     return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
 }

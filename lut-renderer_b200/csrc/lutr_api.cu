@@ -1,4 +1,5 @@
 // C-ABI implementation (include/lutr.h): contexts, LUT upload, stage set-up, launches, host<->device pipelining.
+#include <algorithm>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -18,7 +19,7 @@ struct lutr_ctx {
     int device = 0;
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
-    size_t l2_bytes = 0, persist_max = 0;
+    size_t l2_bytes = 0;
     // freed LUT buffers, kept for the next upload of the same size (a batch queue with per-clip LUTs would otherwise pay a
     // cudaMalloc + cudaFree per clip: 3-4 ms, as long as the GPU needs for five 4K frames)
     std::mutex pool_mu;
@@ -35,11 +36,6 @@ struct lutr_lut {
 };
 
 // device copy of one index table; depends on (bit depth, LUT size, domain scale) only, never overwritten once built
-struct IdxTable {
-    int depth = 0, n = 0;
-    float scale = 0.f;
-    IdxEntry *dev = nullptr;
-};
 
 struct lutr_stage {
     lutr_ctx *ctx = nullptr;
@@ -59,9 +55,6 @@ struct lutr_stage {
     // tunables
     int rows_per_cta = 0;  // 0 = auto
     int band_rows = 0;     // 0 = auto
-    int l2_persist = 1;
-    const lutr_lut *persist_lut = nullptr;
-    std::vector<IdxTable> idx_tables;
     int use_fast = 1;      // 0 forces the generic kernels (testing)
     bool any_only = false; // the combination exists in the generic tile kernel (k_any.cu) only
     int pre10 = 0;         // full-range 10-bit source through the 8-bit intermediate: 1 = with pc -> tv, 2 = range kept
@@ -70,10 +63,11 @@ struct lutr_stage {
     int idx_mode = 3;      // 0 = shared-memory index table, 1 = arithmetic index, 2 = arithmetic index + TMA-staged rows,
                            // 3 = warp-window kernel (k422_warp.cu)
     int min_blocks = 2;    // occupancy variant of the fast kernels (CTAs per SM)
-    int fast_threads = 0;  // threads per CTA of the TMA kernel (0 = auto)
     int wk_pk = 1;         // warp-window kernel: packed f32x2 instructions
     int wk_unroll = 4;     // warp-window kernel: pass B steps unrolled together (experiment builds)
     int wk_var = -1;       // experiment builds: variant of the headline kernel
+    int wk_carveout = 0;   // experiments: preferred shared-memory carveout (percent)
+    int wk_tma = 0;        // 4:2:2 10-bit stage: 1 = the row-staging kernel (k422_tma.cu: TMA / cp.async ring) when the geometry allows; measured slower
     int wk_nk_forced = 0;  // 4:2:0 warp-window kernel: wk_unroll was set explicitly (2 or 4 steps of 64 columns per window)
     int wk_minb = 3;       // warp-window kernel: CTAs per SM the register budget is set for
     bool wk_minb_set = false;  // ... set explicitly (the ordered-row-walk kernels default to 2 CTAs per SM: 128 registers, no spills)
@@ -178,19 +172,6 @@ int check_planes(const lutr_stage *s, const lutr_planes *pl, int fmt, int nframe
     return LUTR_OK;
 }
 
-int set_l2_window(lutr_stage *s, const lutr_lut *lut, cudaStream_t st) {
-    // keep the LUT nodes resident in L2 while frames stream through (frames use no_allocate / streaming accesses)
-    if (!s->l2_persist || s->ctx->persist_max == 0) return LUTR_OK;
-    cudaStreamAttrValue v{};
-    v.accessPolicyWindow.base_ptr = (void *)lut->dev;
-    v.accessPolicyWindow.num_bytes = lut->dev_bytes < s->ctx->persist_max ? lut->dev_bytes : s->ctx->persist_max;
-    v.accessPolicyWindow.hitRatio = 1.0f;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-    return LUTR_OK;
-}
-
 // The fast kernels need one domain scale for all channels and luma rows whose 15-bit sum cannot saturate.
 bool fast_path_ok(const lutr_stage *s, const lutr_lut *lut) {
     if (!s->use_fast || s->d.interp == LUTR_INTERP_NEAREST) return false;
@@ -201,26 +182,6 @@ bool fast_path_ok(const lutr_stage *s, const lutr_lut *lut) {
     // 10 bit: y14 = (sum + (16<<17) + (1<<10)) >> 11 must keep 2*y14 <= 32767;  8 bit: (sum + (32<<14) + (1<<8)) >> 9 likewise
     const long y14 = s->depth == 10 ? (ysum + (16 << 17) + (1 << 10)) >> 11 : (ysum + (32 << 14) + (1 << 8)) >> 9;
     return 2 * y14 <= 32767;
-}
-
-int get_index_table(lutr_stage *s, const lutr_lut *lut, cudaStream_t st, const IdxEntry **out) {
-    for (const IdxTable &t : s->idx_tables)
-        if (t.depth == s->depth && t.n == lut->size && t.scale == lut->scale[0]) {
-            *out = t.dev;
-            return LUTR_OK;
-        }
-    const int entries = s->depth == 10 ? kIdxEntries10 : kIdxEntries8;
-    std::vector<IdxEntry> host(entries);
-    const float lut_max = (float)(lut->size - 1);
-    build_index_table(s->depth, entries, lut->scale[0] * lut_max, lut_max, host.data());
-    IdxTable t;
-    t.depth = s->depth, t.n = lut->size, t.scale = lut->scale[0];
-    CUDA_TRY(cudaMalloc((void **)&t.dev, entries * sizeof(IdxEntry)));
-    // pageable source: the runtime stages it before returning, so `host` may go out of scope
-    CUDA_TRY(cudaMemcpyAsync(t.dev, host.data(), entries * sizeof(IdxEntry), cudaMemcpyHostToDevice, st));
-    s->idx_tables.push_back(t);
-    *out = t.dev;
-    return LUTR_OK;
 }
 
 int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lutr_planes *out, int nframes, cudaStream_t st) {
@@ -241,42 +202,20 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         k.p.in_stride[p] = in->stride[p], k.p.out_stride[p] = out->stride[p];
     }
     k.p.in_step = nframes > 1 ? in->frame_step : 0, k.p.out_step = nframes > 1 ? out->frame_step : 0;
-    if (s->persist_lut != lut) {
-        set_l2_window(s, lut, st);
-        s->persist_lut = lut;
-    }
     int rc;
-    k.idx_tab = nullptr;
     k.idx_mode = -1;
     k.min_blocks = s->min_blocks;
-    k.fast_threads = s->fast_threads;
     k.clamp_out = lut->needs_clamp ? 1 : 0;
     bool warp_kernel = false;
-    if (fast_path_ok(s, lut)) {
-        k.idx_mode = s->idx_mode;
-        if (k.idx_mode == 3) {
-            // warp-window kernel: 8-column lanes (w % 8, 16-byte luma / 8-byte chroma vector accesses: check_planes), 32-bit unit counter
-            const long tiles = (long)((k.w + 239) / 240) * k.h * nframes;
-            warp_kernel = (k.w % 8) == 0 && k.w >= 16 && tiles < (1l << 31);
-            // the 4:2:0 windows are 128 or 256 columns and never wider than the row (the last one is shifted, not clipped)
-            if (s->d.in_fmt == LUTR_PIX_YUV420P && k.w < 256 && s->d.out_fmt == s->d.in_fmt) warp_kernel = false;
-            if (!warp_kernel) k.idx_mode = 2;
-        }
-        if (k.idx_mode == 2) {
-            // TMA-staged rows need 16-byte aligned bulk copies (row starts and row lengths) and the ring must fit in shared memory
-            bool ok = s->d.in_fmt == LUTR_PIX_YUV422P10LE && (k.w % 16) == 0 && (in->frame_step % 16) == 0;  // (never 4:2:0 10-bit)
-            for (int p = 0; p < 3; ++p) ok = ok && ((uintptr_t)in->data[p] % 16) == 0 && (in->stride[p] % 16) == 0;
-            const size_t smem = (size_t)8 * k.w + (size_t)2 * (k.w + 8) * 4 + 16;
-            if (smem * (size_t)s->min_blocks > 200 * 1024) ok = false;
-            if (!ok) {
-                k.idx_mode = 1;
-                if (k.min_blocks < 3) k.min_blocks = 3;
-            }
-        }
-        if (k.idx_mode == 0) {
-            rc = get_index_table(s, lut, st, &k.idx_tab);
-            if (rc != LUTR_OK) return rc;
-        }
+    if (fast_path_ok(s, lut) && s->idx_mode == 3) {
+        // warp-window kernels: 8-column lanes (w % 8, 16-byte luma / 8-byte chroma vector accesses: check_planes), 32-bit unit counter
+        const long tiles = (long)((k.w + 239) / 240) * k.h * nframes;
+        warp_kernel = (k.w % 8) == 0 && k.w >= 16 && tiles < (1l << 31);
+        // the 4:2:0 windows are 128 or 256 columns and never wider than the row (the last one is shifted, not clipped)
+        if (s->d.in_fmt == LUTR_PIX_YUV420P && k.w < 256 && s->d.out_fmt == s->d.in_fmt) warp_kernel = false;
+    }
+    if (warp_kernel) {
+        k.idx_mode = 3;
         const uint32_t magic = 0x4B000000u;  // bits of 8388608.0f: bias of the truncated LUT outputs
         FastK &fk = k.fk;
         const uint32_t yK = (uint32_t)(-s->f.yOff10 * s->f.yC) + (1u << 19);
@@ -306,12 +245,13 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         fk.idx_sr = fk.idx_fold ? 1.f : sr;
         fk.idx_add = -(fk.idx_mul * 8388608.f);
         fk.maxv = maxv;
-        if (warp_kernel) {
+        {
             k.tiles_per_row = (k.w + 239) / 240;  // 4:2:2; the 4:2:0 windows are sized below
             k.wk_pk = s->wk_pk;
             k.wk_one = 1.0f;
             k.wk_unroll = s->wk_unroll;
             k.wk_var = s->wk_var;
+            k.wk_carveout = s->wk_carveout;
             k.min_blocks = s->d.interp == LUTR_INTERP_TRILINEAR ? 2 : s->wk_minb;
             // the clip of the LUT coordinate to lut_max is dead code unless some code value overshoots it: try them all
             k.wk_nomin = 1;
@@ -364,24 +304,35 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             rc = launch_k10_warp(k, in420, out420, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
             s->last_kernel = !out420 ? "k10_warp<420,422>" : (in420 ? "k10_warp<420,420>" : "k10_warp<422,420>");
         }
-    } else if (s->d.in_fmt == LUTR_PIX_YUV444P10LE && !warp_kernel) {
+    } else if (!warp_kernel) {
         rc = run_any();
     } else if (s->d.in_fmt == LUTR_PIX_YUV422P10LE || s->d.in_fmt == LUTR_PIX_YUV444P10LE) {
         const bool in444 = s->d.in_fmt == LUTR_PIX_YUV444P10LE;
-        k.rows_per_cta = s->rows_per_cta > 0 ? s->rows_per_cta : 1;
-        if (warp_kernel) {
-            // rows per CTA unit (8 warps, interleaved rows): as many as still leave every CTA of the persistent grid >= 32 units
+        {
+            // Work unit of a CTA = (frame, block of R rows, window); its 8 warps take interleaved rows.  Measured on the B200
+            // (profiles/r02_grid_rows_sweep.jsonl): a persistent grid with a fixed share of units per CTA leaves a sixth of the
+            // warp slots idle (the warp scheduler is not fair, CTAs drift apart and the fast ones run out of work), one unit per
+            // CTA with the hardware dealing CTAs to SMs as they retire is 9 % faster; long units (R = 128: 16 rows per warp)
+            // amortise the row prefetch.  So: R as large as still leaves ~6 units per resident CTA slot, grid = all units.
             long r = s->rows_per_cta;
             if (r <= 0) {
-                r = (long)k.tiles_per_row * k.h * nframes / (32l * k.grid_ctas);
-                r = r < 8 ? 8 : (r > 64 ? 64 : r);
+                const long slots = 3l * s->ctx->sm_count;
+                r = (long)k.tiles_per_row * k.h * nframes / (6l * slots);
+                r = r < 16 ? 16 : (r > 128 ? 128 : r);
             }
-            k.rows_per_cta = (int)((r + 7) / 8 * 8);
+            k.rows_per_cta = (int)(r / 8 * 8 < 8 ? 8 : r / 8 * 8);
+            if (s->grid_ctas <= 0) k.grid_ctas = (int)std::min<long>((long)k.tiles_per_row * ((k.h + k.rows_per_cta - 1) / k.rows_per_cta) * nframes, 1l << 30);
         }
         k.bands = 1;
-        rc = warp_kernel ? launch_k422_warp(k, in444, s->d.interp, s->d.float_mode, st) : launch_yuv422p10(k, s->d.interp, s->d.float_mode, st);
-        s->last_kernel = warp_kernel ? (in444 ? "k422_warp<444>" : "k422_warp") : (k.idx_mode == 2 ? "k_yuv422p10_tma" : (k.idx_mode >= 0 ? "k_yuv422p10_fast" : "k_yuv422p10"));
-    } else if (warp_kernel) {
+        if (!in444 && s->wk_tma && k422_tma_ok(k)) {
+            k.wk_bulk = s->wk_tma == 2;
+            rc = launch_k422_tma(k, s->d.interp, s->d.float_mode, st);
+            s->last_kernel = s->wk_tma == 2 ? "k422_tma" : "k422_ring";
+        } else {
+            rc = launch_k422_warp(k, in444, s->d.interp, s->d.float_mode, st);
+            s->last_kernel = in444 ? "k422_warp<444>" : "k422_warp";
+        }
+    } else if (s->d.in_fmt == LUTR_PIX_YUV420P || s->d.in_fmt == LUTR_PIX_YUV422P) {
         // 4:2:0 / 4:2:2 8-bit source warp-window kernel (window width and grid are chosen in the launcher)
         const bool in422 = s->d.in_fmt == LUTR_PIX_YUV422P;
         k.wk_unroll = s->wk_nk_forced ? s->wk_unroll : 0;
@@ -400,24 +351,8 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             s->last_kernel = in422 ? "k420_warp<422>" : "k420_warp";
         }
         if (rc == LUTR_ERR_UNSUPPORTED) rc = run_any();  // this LUT / option combination needs a row of at least 256 columns
-    } else if (mixed || s->d.in_fmt != LUTR_PIX_YUV420P) {
-        rc = run_any();
     } else {
-        // bands per frame: enough CTAs to fill the device a few times over, but bands of >= 16 rows (7 halo rows each)
-        int rows = s->band_rows;
-        if (rows <= 0) {
-            const int target_ctas = s->ctx->sm_count * 8;
-            int bands = (target_ctas + nframes - 1) / nframes;
-            if (bands < 1) bands = 1;
-            rows = (k.h + bands - 1) / bands;
-            if (rows < 32) rows = 32;
-        }
-        rows = (rows + 1) & ~1;
-        if (rows > k.h) rows = k.h;
-        k.rows_per_cta = rows;
-        k.bands = (k.h + rows - 1) / rows;
-        rc = launch_yuv420p8(k, s->d.interp, s->d.float_mode, st);
-        s->last_kernel = k.idx_mode >= 0 && s->d.interp != LUTR_INTERP_NEAREST ? "k_yuv420p8_fast" : "k_yuv420p8";
+        rc = run_any();
     }
     if (rc != LUTR_OK) {
         set_error("kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -425,12 +360,6 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     }
     s->launches.fetch_add(1, std::memory_order_relaxed);
     return LUTR_OK;
-}
-
-void free_index_tables(lutr_stage *s) {
-    for (IdxTable &t : s->idx_tables)
-        if (t.dev) cudaFree(t.dev);
-    s->idx_tables.clear();
 }
 
 void free_host_pipeline(lutr_stage *s) {
@@ -539,13 +468,9 @@ int lutr_ctx_create(int32_t device, lutr_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     c->cc_major = prop.major, c->cc_minor = prop.minor;
     c->l2_bytes = (size_t)prop.l2CacheSize;
-    c->persist_max = (size_t)prop.accessPolicyMaxWindowSize;
-    // allow up to 1/4 of L2 to be set aside for persisting lines (the LUT is <= 256^3*16 B, usually 0.6-4.4 MB)
-    size_t want = (size_t)prop.persistingL2CacheMaxSize;
-    if (want > c->l2_bytes / 4) want = c->l2_bytes / 4;
-    if (want) {
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
-    }
+    // No persisting-L2 window for the LUT: a 0.6-4.4 MB table that every warp gathers from stays in the 126 MB L2 by itself while
+    // the frames stream past with L1::no_allocate accesses (measured in round 1: the window changed nothing), and a per-stream
+    // access-policy attribute is state that outlives the call on the caller's stream.
     *out = c;
     return LUTR_OK;
 }
@@ -718,7 +643,6 @@ void lutr_stage_destroy(lutr_stage *s) {
     cudaSetDevice(s->ctx->device);
     if (s->compute) cudaStreamSynchronize(s->compute);
     free_host_pipeline(s);
-    free_index_tables(s);
     if (s->ev_ok)
         for (int i = 0; i < lutr_stage::NBUF; ++i) {
             cudaEventDestroy(s->ev_in[i]);
@@ -846,13 +770,13 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
         s->chunk_mb = value;
     } else if (!std::strcmp(name, "wk_pk")) s->wk_pk = value;
     else if (!std::strcmp(name, "wk_var")) s->wk_var = value;
+    else if (!std::strcmp(name, "wk_tma")) s->wk_tma = value;
+    else if (!std::strcmp(name, "wk_carveout")) s->wk_carveout = value;
     else if (!std::strcmp(name, "wk_unroll")) s->wk_unroll = value, s->wk_nk_forced = 1;
     else if (!std::strcmp(name, "wk_minb")) s->wk_minb = value >= 2 && value <= 4 ? value : 3, s->wk_minb_set = true;
     else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value >= 2 && value <= 4 ? value : 3;
-    else if (!std::strcmp(name, "fast_threads")) s->fast_threads = value;
-    else if (!std::strcmp(name, "l2_persist")) {
-        s->l2_persist = value;
-        s->persist_lut = nullptr;
+    else if (!std::strcmp(name, "fast_threads") || !std::strcmp(name, "l2_persist")) {
+        // accepted for older callers; the kernel families they tuned are gone (the LUT stays L2-resident by itself)
     } else {
         set_error("unknown option '%s'", name);
         return LUTR_ERR_INVALID_ARG;

@@ -1,5 +1,5 @@
 // Internal declarations shared by the host side (cube_parser.cpp, colour_tables.cpp, lutr_api.cu)
-// and the kernels (stage_kernels.cu).  Not part of the C-ABI (include/lutr.h).
+// and the kernels.  Not part of the C-ABI (include/lutr.h).
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -46,15 +46,6 @@ struct LutK {
     float out_scale;    // (float)(2^depth - 1)
 };
 
-// Per-channel index table of the fast kernels: entry i (a 12-bit / 11-bit two's-complement code value, so that the
-// clamp of the YUV->RGB result is part of the lookup) -> {prev node index, fraction d} exactly as lut3d computes them.
-struct IdxEntry {
-    int32_t prev;
-    float d;
-};
-constexpr int kIdxEntries10 = 4096;  // (R >> 20) & 0xFFF for the 10-bit path
-constexpr int kIdxEntries8 = 2048;   // (yy + c) & 0x7FF for the 8-bit path
-
 struct PlaneSet {
     const uint8_t *in[3];
     uint8_t *out[3];
@@ -99,18 +90,18 @@ struct StageK {
     LutK lut;
     PlaneSet p;
     FastK fk;
-    const IdxEntry *idx_tab;  // device copy of the index table (fast kernels), nullptr -> generic kernels
     int32_t clamp_out;        // 1: LUT entries leave [0,1], the store needs its clip
     int32_t grid_ctas;        // persistent grid size of the fast kernels
-    int32_t idx_mode;         // 0: shared-memory index table, 1: arithmetic index (no table)
+    int32_t idx_mode;         // 3: warp-window kernels, -1: generic tile kernel
     int32_t min_blocks;       // occupancy variant of the fast kernel (2, 3 or 4 CTAs per SM)
-    int32_t fast_threads;     // threads per CTA of the TMA kernel (0 = 256)
     // warp-window kernel (k422_warp.cu)
     int32_t tiles_per_row;       // ceil(w / 240)
     int32_t wk_pk;               // 1: packed f32x2 instructions
     float wk_one;                // 1.0f the compiler cannot constant-fold (see addp2 in k422_warp.cu)
     int32_t wk_unroll;           // pass B double-iterations unrolled together (1, 2, 4)
     int32_t wk_nomin;            // 1: the clip of the LUT coordinate to lut_max can never bind (host-checked), drop it
+    int32_t wk_bulk;             // row-staging kernel: 1 = bulk async copies (TMA), 0 = per-lane cp.async
+    int32_t wk_carveout;         // experiments: preferred shared-memory carveout in percent (0 = driver's choice)
     int32_t wk_var;              // experiment builds: variant id of the headline kernel (k422_warp.cu), -1 = default
     AnyK any;                    // generic tile kernel only
 };
@@ -127,13 +118,11 @@ inline int pix_sub(int fmt) {  // log2 chroma subsampling: sx | sy << 1
 // swscale's 15-bit range conversion constants (colour_tables.cpp): out15 = min((in15 * coeff + offset) >> 14, 32767)
 void range_coeffs(int depth, bool to_jpeg, bool chroma, int32_t *coeff, int32_t *offset);
 
-// host-side construction of the index table (colour_tables.cpp): same float operations as lut3d's per-pixel prologue
-void build_index_table(int depth, int entries, float scale_times_lutmax, float lut_max, IdxEntry *out);
-
-// launchers (stage_kernels.cu); `stream` is a cudaStream_t
-int launch_yuv422p10(const StageK &k, int interp, int float_mode, void *stream);
-int launch_yuv420p8(const StageK &k, int interp, int float_mode, void *stream);
+// launchers; `stream` is a cudaStream_t
 int launch_k422_warp(const StageK &k, bool in444, int interp, int float_mode, void *stream);  // yuv422p10le | yuv444p10le -> yuv422p10le
+// TMA-staged form of the same stage (k422_tma.cu); k422_tma_ok: the geometry allows 16-byte bulk copies
+bool k422_tma_ok(const StageK &k);
+int launch_k422_tma(const StageK &k, int interp, int float_mode, void *stream);
 int launch_k420_warp(const StageK &k, bool in422, int interp, int float_mode, bool grid_forced, void *stream);
 // 10-bit chains with a 4:2:0 side (k10_warp.cu): yuv420p10le in and / or yuv420p10le out
 int launch_k10_warp(const StageK &k, bool in420, bool out420, int interp, int float_mode, bool grid_forced, void *stream);

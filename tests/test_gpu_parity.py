@@ -91,16 +91,17 @@ def test_yuv422p10_rows_per_cta_and_domain_scale():
             assert_bit_exact("yuv422p10le", w, h, got[i], exp[i], f"422p10 rows_per_cta={rows} frame {i}")
 
 
-@pytest.mark.parametrize("options", [dict(fast_path=0), dict(idx_mode=0, min_blocks=3), dict(idx_mode=0, min_blocks=4),
-                                     dict(idx_mode=1, min_blocks=3), dict(idx_mode=1, min_blocks=4), dict(grid_ctas=1), dict(grid_ctas=7),
-                                     dict(idx_mode=2, min_blocks=3), dict(idx_mode=2, min_blocks=4), dict(idx_mode=2, grid_ctas=1),
-                                     dict(idx_mode=2, grid_ctas=2), dict(idx_mode=2, grid_ctas=5),
-                                     dict(idx_mode=3), dict(idx_mode=3, grid_ctas=1), dict(idx_mode=3, grid_ctas=3, rows_per_cta=8),
-                                     dict(idx_mode=3, rows_per_cta=64), dict(idx_mode=3, float_mode="fma")])
+@pytest.mark.parametrize("options", [dict(fast_path=0), dict(), dict(grid_ctas=1), dict(grid_ctas=7), dict(grid_ctas=3, rows_per_cta=8),
+                                     dict(rows_per_cta=64), dict(rows_per_cta=128, grid_ctas=2), dict(float_mode="fma"),
+                                     # the row-staging kernel (k422_tma.cu): 1 = per-lane cp.async ring, 2 = bulk async copies (TMA + mbarrier)
+                                     dict(wk_tma=1), dict(wk_tma=2), dict(wk_tma=1, grid_ctas=1), dict(wk_tma=2, grid_ctas=1),
+                                     dict(wk_tma=1, rows_per_cta=8, grid_ctas=5), dict(wk_tma=2, rows_per_cta=8, grid_ctas=5),
+                                     dict(wk_tma=2, rows_per_cta=128), dict(wk_tma=1, float_mode="fma"), dict(wk_tma=2, float_mode="fma")])
 @pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
 def test_yuv422p10_kernel_variants(options, interp):
-    """Every code path of the 4:2:2 stage (generic kernel, index table / arithmetic index, occupancy variants, tiny persistent
-    grids) gives the same bits; LUTs: values inside [0,1] (no store clip), outside (clip), size-1 not a power of two."""
+    """Every code path of the 4:2:2 stage (generic tile kernel, warp-window kernel with register prefetch, row-staging kernel with
+    either copy engine, tiny grids whose CTAs walk many units, short and long units) gives the same bits; LUTs: values inside [0,1]
+    (no store clip), outside (clip), size-1 not a power of two."""
     w, h = 656, 21
     options = dict(options)
     float_mode = options.pop("float_mode", "c")
@@ -110,7 +111,7 @@ def test_yuv422p10_kernel_variants(options, interp):
         table = table.astype(np.float32)
         got = gpu_stage("yuv422p10le", w, h, frames, table, interp=interp, options=options, float_mode=float_mode)
         if float_mode == "fma":  # opt-in contraction: same bits from every kernel that implements it
-            ref = gpu_stage("yuv422p10le", w, h, frames, table, interp=interp, options=dict(idx_mode=2), float_mode=float_mode)
+            ref = gpu_stage("yuv422p10le", w, h, frames, table, interp=interp, options=dict(fast_path=0), float_mode=float_mode)
             for i in range(len(frames)):
                 assert np.array_equal(got[i], ref[i]), f"422p10 fma {lut_name} {interp} frame {i}"
             continue
@@ -122,21 +123,22 @@ def test_yuv422p10_kernel_variants(options, interp):
 
 @pytest.mark.parametrize("w", [16, 232, 240, 248, 256, 472, 480, 488, 496, 728, 1928])
 @pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
-def test_yuv422p10_window_edges(w, interp):
-    """Row widths around the 240-column windows of the warp-window kernel (exactly one window, one column group more or
-    less, ragged last windows), several frames, more rows than one CTA unit and a row count that is not a multiple of 8."""
+@pytest.mark.parametrize("extra", [dict(), dict(wk_tma=1), dict(wk_tma=2)])
+def test_yuv422p10_window_edges(w, interp, extra):
+    """Row widths around the 240-column windows of the warp-window kernel and the 248-column windows of the row-staging kernel
+    (exactly one window, one column group more or less, ragged last windows; widths that are not a multiple of 16 take the
+    warp-window kernel whatever wk_tma says), several frames, more rows than one CTA unit and a row count that is not a multiple of 8."""
     h = 19
     table = LUTS["look65"]().astype(np.float32)
     frames = _frames("yuv422p10le", w, h, ["natural", "noise", "extremes"])
-    got = gpu_stage("yuv422p10le", w, h, frames, table, interp=interp, options=dict(idx_mode=3, rows_per_cta=8))
+    got = gpu_stage("yuv422p10le", w, h, frames, table, interp=interp, options=dict(rows_per_cta=8, **extra))
     L = oracle_lut(table)
     for i, f in enumerate(frames):
         assert_bit_exact("yuv422p10le", w, h, got[i], oracle_stage("yuv422p10le", w, h, f, L, interp=interp),
                          f"422p10 window edges w={w} {interp} frame {i}")
 
 
-@pytest.mark.parametrize("options", [dict(fast_path=0), dict(idx_mode=1), dict(idx_mode=1, band_rows=12), dict(idx_mode=1, band_rows=26),
-                                     dict(idx_mode=3), dict(idx_mode=3, grid_ctas=2)])
+@pytest.mark.parametrize("options", [dict(fast_path=0), dict(), dict(grid_ctas=2), dict(grid_ctas=444)])
 @pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
 def test_yuv420p_kernel_variants(options, interp):
     w, h = 328, 54
@@ -161,7 +163,7 @@ def test_yuv420p_warp_windows(w, h, options, interp, kw):
     that span several windows and frames (tiny grids), frame heights down to the 12-row minimum, with and without the pc->tv pass."""
     table = LUTS["look33"]().astype(np.float32)
     frames = _frames("yuv420p", w, h, ["natural", "noise", "extremes", "noise"])
-    got = gpu_stage("yuv420p", w, h, frames, table, interp=interp, options=dict(idx_mode=3, **options), **kw)
+    got = gpu_stage("yuv420p", w, h, frames, table, interp=interp, options=dict(**options), **kw)
     L = oracle_lut(table)
     for i, f in enumerate(frames):
         assert_bit_exact("yuv420p", w, h, got[i], oracle_stage("yuv420p", w, h, f, L, interp=interp, **kw),
@@ -256,17 +258,6 @@ def test_yuv420p_geometries(w, h):
     L = oracle_lut(table)
     for i, f in enumerate(frames):
         assert_bit_exact("yuv420p", w, h, got[i], oracle_stage("yuv420p", w, h, f, L), f"420p {w}x{h} frame {i}")
-
-
-@pytest.mark.parametrize("band_rows", [12, 16, 18, 34, 62, 4096])
-def test_yuv420p_band_decomposition(band_rows):
-    w, h = 96, 62
-    table = LUTS["rand17"]().astype(np.float32)
-    frames = _frames("yuv420p", w, h, ["noise", "natural", "extremes"])
-    got = gpu_stage("yuv420p", w, h, frames, table, options={"band_rows": band_rows, "idx_mode": 1})
-    L = oracle_lut(table)
-    for i, f in enumerate(frames):
-        assert_bit_exact("yuv420p", w, h, got[i], oracle_stage("yuv420p", w, h, f, L), f"420p band_rows={band_rows} frame {i}")
 
 
 @pytest.mark.parametrize("kw", [dict(in_range="pc", norm_range="tv", interp="trilinear"),           # BASELINE cfg 2
@@ -499,7 +490,8 @@ def test_10bit_to_yuv420p_8bit_delivery(pix_fmt, w, h, options, interp, lut_name
     ("yuv420p10le", "yuv420p10le", 488, 30, dict(grid_ctas=2)), ("yuv422p10le", "yuv420p10le", 488, 30, dict(grid_ctas=3)),
     ("yuv420p10le", "yuv420p", 488, 30, dict(grid_ctas=2)), ("yuv422p10le", "yuv420p", 496, 30, dict(grid_ctas=5)),
     ("yuv444p", "yuv420p10le", 200, 36, dict()), ("yuv420p10le", "yuv444p", 200, 36, dict()),
-    ("yuv422p10le", "yuv422p10le", 256, 6, dict(fast_path=0)), ("yuv422p10le", "yuv422p10le", 256, 6, dict(idx_mode=2)),
+    ("yuv422p10le", "yuv422p10le", 256, 6, dict(fast_path=0)), ("yuv422p10le", "yuv422p10le", 256, 6, dict(wk_tma=1)),
+    ("yuv422p10le", "yuv422p10le", 256, 6, dict(wk_tma=2)), ("yuv422p10le", "yuv422p10le", 512, 9, dict(wk_tma=2, rows_per_cta=8)),
     ("yuv420p", "yuv420p", 64, 14, dict())])
 def test_no_kernel_writes_outside_its_frames(in_fmt, out_fmt, w, h, options):
     """Guard bands around the output batch stay untouched for every kernel family (compute-sanitizer is not available on this
@@ -548,6 +540,8 @@ def test_fuzz_geometries_formats_options():
             options["grid_ctas"] = int(rng.integers(1, 9))
         if rng.random() < 0.2:
             options["any_kernel"] = 1
+        if rng.random() < 0.3:
+            options["wk_tma"] = int(rng.integers(1, 3))      # row-staging kernel where the stage and geometry allow it
         scale = (1.0, 1.0, 1.0) if rng.random() < 0.8 else (0.5, 1.0, 0.75)
         table = luts[int(rng.integers(len(luts)))].astype(np.float32)
         frames = [synth.noise_frame(in_fmt, w, h, seed=int(rng.integers(1 << 30))),
@@ -672,7 +666,7 @@ def test_largest_lut_sizes(n):
     L = oracle_lut(table)
     for in_fmt, out_fmt, w, h, opts in (("yuv422p10le", "yuv422p10le", 496, 6, dict()), ("yuv420p", "yuv420p", 256, 16, dict()),
                                         ("yuv420p10le", "yuv420p", 256, 16, dict()), ("yuv444p", "yuv444p10le", 136, 8, dict()),
-                                        ("yuv422p10le", "yuv422p10le", 256, 4, dict(idx_mode=2))):
+                                        ("yuv422p10le", "yuv422p10le", 256, 4, dict(wk_tma=2))):
         frames = [synth.noise_frame(in_fmt, w, h, seed=n)]
         got = gpu_stage(in_fmt, w, h, frames, table, out_pix_fmt=out_fmt, options=opts)
         assert_bit_exact(out_fmt, w, h, got[0], oracle_stage(in_fmt, w, h, frames[0], L, out_pix_fmt=out_fmt), f"n={n} {in_fmt}->{out_fmt} {opts}")
