@@ -56,6 +56,15 @@ CFG5 = dict(clips=64, frames_per_clip=24,
 BYTES_PER_PIXEL = {"yuv420p": 1.5, "yuv422p": 2.0, "yuv444p": 3.0, "yuv420p10le": 3.0, "yuv422p10le": 4.0, "yuv444p10le": 6.0}  # per side; algorithmic bytes/frame = (in + out) * w * h
 
 
+def config_dict(cfg, args, world):
+    """The `config` object of the JSON line: what is measured, identical for the repo arm and the reference arm."""
+    F = cfg["frames_per_step"]
+    bpp_in, bpp_out = BYTES_PER_PIXEL[cfg["pix_fmt"]], BYTES_PER_PIXEL[cfg.get("out_pix_fmt") or cfg["pix_fmt"]]
+    return {"workload": cfg["desc"], "content": args.content, "frames_per_launch": F, "float_mode": args.float_mode, "options": list(args.opt),
+            "l2": f"inputs larger than L2 ({F * bpp_in * cfg['w'] * cfg['h'] / 1e6:.0f} MB read + {F * bpp_out * cfg['w'] * cfg['h'] / 1e6:.0f} MB written per launch)",
+            "sharding": "contiguous frame range per GPU, no collective"}
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -225,9 +234,10 @@ def run_reference(args, cfg, rank, world):
         "ms_per_step": round(1e3 * total_s / max(1, args.steps), 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u16+f32" if "10" in cfg["pix_fmt"] else "u8+f32", "data": "synthetic",
         "gpix_per_s": round(fps * mpix / 1e3, 4),
-        "config": {"workload": cfg["desc"], "content": args.content, "frames_per_step": round(total_frames / max(1, args.steps), 1)},
+        "config": config_dict(cfg, args, world),
         "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{legs}; {cores} frame-parallel threads x {sample_s:.1f}s per step, {total_frames} frames total"},
+                         "sample": f"{legs}; {cores} frame-parallel threads x {sample_s:.1f}s per step, {total_frames} frames total "
+                                   f"({total_frames / max(1, args.steps):.1f} per step)"},
         "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -383,7 +393,8 @@ def main():
     ap.add_argument("--float-mode", default="c", choices=["c", "fma"])
     ap.add_argument("--frames-per-step", type=int, default=0)
     ap.add_argument("--rows-per-cta", type=int, default=0)
-    ap.add_argument("--band-rows", type=int, default=0)
+    ap.add_argument("--min-seconds", type=float, default=1.05, help="a step repeats the launch so that the K timed steps last at least this long")
+    ap.add_argument("--no-classes", action="store_true", help="skip the second content class (content_classes)")
     ap.add_argument("--opt", action="append", default=[], help="stage tunable name=value (see lutr_stage_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -431,8 +442,6 @@ def main():
                         interp=cfg["interp"], float_mode=args.float_mode, device=local_rank)
     if args.rows_per_cta:
         stage.set_option("rows_per_cta", args.rows_per_cta)
-    if args.band_rows:
-        stage.set_option("band_rows", args.band_rows)
     for kv in args.opt:
         name, _, value = kv.partition("=")
         stage.set_option(name, int(value))
@@ -445,37 +454,51 @@ def main():
     tstream = torch.cuda.Stream(device=device)
     torch.cuda.set_stream(tstream)
 
-    def step():
-        stage.run(lut, src, dst, F, stream=tstream)
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    launches0 = stage.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    launches = stage.launch_count - launches0
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        return float(t.item())
+
+    def timed(buf, steps, launches_per_step):
+        """`steps` steps of `launches_per_step` launches over the frames in `buf`: (ms over all of them, launches, clocks)."""
+        barrier()
+        sampler = ClockSampler(local_rank)
+        n0 = stage.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        e0.record()
+        for _ in range(steps * launches_per_step):
+            stage.run(lut, buf, dst, F, stream=tstream)
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        return reduce_max(e0.elapsed_time(e1)), stage.launch_count - n0, clocks
+
+    # warm-up, then size a step: one launch processes F frames; a step repeats it so that the K timed steps last >= --min-seconds
+    # (a 2.4 ms launch times 100 steps would give NVML three clock samples)
+    for _ in range(args.warmup):
+        stage.run(lut, src, dst, F, stream=tstream)
+    ms_probe, _, _ = timed(src, 1, 3)
+    per_launch_probe = max(ms_probe / 3, 1e-3)
+    L = max(1, int(np.ceil(args.min_seconds * 1e3 / (args.steps * per_launch_probe))))
+    if world > 1:
+        lt = torch.tensor([L], dtype=torch.int64, device=device)
+        dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+        L = int(lt.item())
+    ms, launches, clocks = timed(src, args.steps, L)
+    if world > 1:
         lt = torch.tensor([launches], dtype=torch.int64, device=device)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
+    per_launch_ms = ms / (args.steps * L)
 
     # spot check: the timed outputs are the right pixels (first frame of this rank against the oracle)
     parity, parity_planes = None, {}
@@ -485,9 +508,9 @@ def main():
             from lut_renderer_b200 import synth
             got = dst[:stage.out_frame_bytes].cpu().numpy()
             first = src[:stage.in_frame_bytes].cpu().numpy()
-            L = O.OracleLut.from_table(table)
+            L_or = O.OracleLut.from_table(table)
             Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(first, cfg["pix_fmt"], cfg["w"], cfg["h"])]
-            exp = O.stage_any(L, cfg["pix_fmt"], cfg.get("out_pix_fmt", cfg["pix_fmt"]), Y, U, V, interp=cfg["interp"],
+            exp = O.stage_any(L_or, cfg["pix_fmt"], cfg.get("out_pix_fmt", cfg["pix_fmt"]), Y, U, V, interp=cfg["interp"],
                               range_pass=cfg["in_range"] == "pc" and cfg["norm_range"] == "tv")
             parity = "bit-exact" if np.array_equal(got, synth.pack_planes(exp)) else "MISMATCH"
             # north_star's statement per plane: share of identical samples, max and mean absolute error (in code values)
@@ -498,13 +521,32 @@ def main():
         except Exception as exc:  # the checker is optional for the measurement
             parity = f"unchecked ({exc})"
 
+    bytes_per_frame = (BYTES_PER_PIXEL[cfg["pix_fmt"]] + BYTES_PER_PIXEL[cfg.get("out_pix_fmt") or cfg["pix_fmt"]]) * cfg["w"] * cfg["h"]
+    peak, peak_src = measured_peak_hbm()
+
+    # the other content class (A = natural, B = worst-case gather): same stage, same launch shape, a shorter region
+    classes = {}
+    if not args.no_classes:
+        classes[args.content] = {"value": round(world * F * args.steps * L / (ms / 1e3), 2),
+                                 "frac": round(bytes_per_frame * F / (per_launch_ms / 1e3) / 1e9 / peak, 4)}
+        for other in ("natural", "noise"):
+            if other in classes:
+                continue
+            src_o, _ = device_frames(cfg, other, F, device, rank)
+            for _ in range(3):
+                stage.run(lut, src_o, dst, F, stream=tstream)
+            n_o = max(3, int(np.ceil(0.4e3 / per_launch_probe / 3)))  # >= 0.4 s even if this class ran as fast as the main one
+            ms_o, _, _ = timed(src_o, 1, n_o)
+            classes[other] = {"value": round(world * F * n_o / (ms_o / 1e3), 2),
+                              "frac": round(bytes_per_frame * F / (ms_o / n_o / 1e3) / 1e9 / peak, 4)}
+            del src_o
+
     # end to end: the call a user makes (ColourStage.run_host) on pinned host frames, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        # the same step as the device-resident measurement (F frames per call), bounded to 4 GB of pinned memory per direction and
-        # 16 GB over all ranks of the box
-        budget = min(4e9, 8e9 / world)
-        Fe = max(1, min(F, int(budget // max(stage.in_frame_bytes, stage.out_frame_bytes))))
+        # the same F frames per call at every N (4.2 GB pinned per rank and direction at 4K 10-bit): fill and drain of the 3-slot
+        # device ring stay amortised the same way whatever the number of ranks
+        Fe = F
         pin_in = stage.ctx.pinned_buffer(Fe * stage.in_frame_bytes)
         pin_out = stage.ctx.pinned_buffer(Fe * stage.out_frame_bytes)
         for i in range(Fe):
@@ -517,17 +559,14 @@ def main():
         for _ in range(e2e_steps):
             stage.run_host(lut, pin_in, pin_out, Fe)   # synchronous: output bytes are in host memory on return
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = reduce_max(time.perf_counter() - t0)
         e2e = {"value": round(world * Fe * e2e_steps / dt, 2), "unit": "frames/s", "h2d_bytes_per_step": Fe * stage.in_frame_bytes,
                "d2h_bytes_per_step": Fe * stage.out_frame_bytes, "frames_per_step": Fe, "steps": e2e_steps,
                "api": "ColourStage.run_host -> lutr_stage_run_host (pinned host buffers)",
                "cpu_affinity": "cores local to the GPU (NVML)" if full_affinity else "unchanged"}
-        # what the bus allows: pinned copies in both directions at once (the path moves one frame in and one out per frame)
+        # what the bus allows: pinned copies in both directions at once, ALL ranks copying at the same time (barrier first)
         try:
+            barrier()
             pcie = pcie_simultaneous_gbs(device)
             moved = max(stage.in_frame_bytes, stage.out_frame_bytes) * Fe * e2e_steps / dt / 1e9
             e2e["pcie_each_direction_gbs"] = round(pcie, 1)
@@ -538,15 +577,14 @@ def main():
         pin_out.close()
 
     if rank == 0:
-        fps = world * F * args.steps / (ms / 1e3)
+        fps = world * F * args.steps * L / (ms / 1e3)
         mpix = cfg["w"] * cfg["h"] / 1e6
-        bytes_per_frame = (BYTES_PER_PIXEL[cfg["pix_fmt"]] + BYTES_PER_PIXEL[cfg.get("out_pix_fmt") or cfg["pix_fmt"]]) * cfg["w"] * cfg["h"]
-        per_launch_ms = ms / args.steps
         achieved = bytes_per_frame * F / (per_launch_ms / 1e3) / 1e9
-        peak, peak_src = measured_peak_hbm()
         kernel = stage.kernel_name
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "measured at N=1 only (rank 0 of a one-GPU run)"}
+        if args.no_cpu_baseline:
+            cpu = None
+        elif world == 1:
             from oracle import cpu_baseline as C
             from oracle import oracle as O
             if full_affinity:
@@ -559,13 +597,13 @@ def main():
         line = {
             "metric": "4K 10-bit frames/s" if args.config == "cfg3" else f"{args.config} frames/s",
             "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(per_launch_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u16+f32" if "10" in cfg["pix_fmt"] else "u8+f32", "data": "synthetic",
             "gpix_per_s": round(fps * mpix / 1e3, 3),
-            "config": {"workload": cfg["desc"], "content": args.content, "frames_per_step": F, "float_mode": args.float_mode, "options": args.opt,
-                       "l2": f"inputs larger than L2 ({F * stage.in_frame_bytes / 1e6:.0f} MB read + {F * stage.out_frame_bytes / 1e6:.0f} MB written per step)",
-                       "sharding": "contiguous frame range per GPU, no collective", "parity_spot_check": parity,
-                       "parity_vs_oracle_first_frame": parity_planes},
+            "launches_per_step": L, "frames_per_step": F * L, "ms_per_launch": round(per_launch_ms, 4), "timed_region_s": round(ms / 1e3, 3),
+            "config": config_dict(cfg, args, world),
+            "parity": {"spot_check": parity, "vs_oracle_first_frame": parity_planes},
+            "content_classes": classes,
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1),
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": ncu_traffic(args.config, F), "peak_source": peak_src,

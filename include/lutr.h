@@ -46,7 +46,8 @@ typedef enum lutr_status {
     LUTR_ERR_IO = -4,           /* .cube file cannot be opened / read                                    */
     LUTR_ERR_NOMEM = -5,
     LUTR_ERR_CUDA = -6,         /* no device, wrong architecture, or a CUDA runtime error                */
-    LUTR_ERR_UNSUPPORTED = -7   /* valid request outside what the kernels implement      */
+    LUTR_ERR_UNSUPPORTED = -7,  /* valid request outside what the kernels implement      */
+    LUTR_ERR_CANCELLED = -8     /* lutr_stage_pump: the caller's cancel flag was raised (task_manager.py:38-44: "canceled") */
 } lutr_status;
 
 /* Pixel formats of the stage input / output (`format=` / `-pix_fmt`, ffmpeg.py:233, 287-310). */
@@ -165,12 +166,30 @@ LUTR_API int lutr_stage_sync(lutr_stage *stage);
 LUTR_API int64_t lutr_stage_launch_count(const lutr_stage *stage);
 /* name of the kernel family the most recent enqueue of this stage launched ("" before the first one); diagnostics */
 LUTR_API const char *lutr_stage_kernel_name(const lutr_stage *stage);
-/* run-time tunables, for benchmarking and testing: "grid_ctas" (persistent grid of the warp-window kernels), "host_chunk_mb" (input
- * megabytes per slot of the host pipeline's 3-slot device ring, default 64), "l2_persist" (0/1: LUT in a persisting L2 window),
- * "any_kernel" (1: route every launch through the generic tile kernel), "wk_minb" (CTAs per SM the warp-window kernels are built
- * for: 2..4), "wk_unroll" (4:2:0 8-bit kernel: window width in 64-column steps), "fast_path" (0: generic kernels of the two
- * original stage types), "idx_mode" (4:2:2 10-bit kernel family: 3 = warp-window kernel, 2 = TMA-staged rows, 1 / 0 = earlier fast
- * kernels), "rows_per_cta", "band_rows", "min_blocks", "fast_threads" (geometry of those earlier kernels). */
+/* Raw-pipe pump: the whole data path of one LUT stage of the reference's runner (task_manager.py:134-190 blocks on ONE ffmpeg
+ * whose filter graph holds lut3d; the re-plumbed runner starts a decoding and an encoding ffmpeg and calls this between them).
+ * Reads tightly packed frames of the stage's input layout from `fd_in` until end of file, runs them through the stage, writes the
+ * output frames to `fd_out` in order.  Pinned host ring, H2D / kernel / D2H on the stage's streams, a reader and a writer thread
+ * inside the call; the pipes are grown to the kernel's maximum (F_SETPIPE_SZ).  `frames_per_batch` <= 0 picks ~64 MB batches.
+ * `cancel` (may be NULL) is polled at least every 100 ms: non-zero ends the call with LUTR_ERR_CANCELLED.  `progress` (may be NULL)
+ * is called on the calling thread after each batch with the number of frames handed to the GPU so far.  A trailing partial frame is
+ * dropped.  Returns LUTR_ERR_IO when a pipe fails (e.g. the encoder went away: EPIPE) -- the text is in lutr_last_error(). */
+typedef struct lutr_pump_stats {
+    int64_t frames_in, frames_out; /* frames read and processed / frames written */
+    int64_t bytes_in, bytes_out;
+    double seconds;
+} lutr_pump_stats;
+typedef void (*lutr_progress_fn)(void *user, int64_t frames_done);
+LUTR_API int lutr_stage_pump(lutr_stage *stage, const lutr_lut *lut, int fd_in, int fd_out, int32_t frames_per_batch,
+                             const volatile int32_t *cancel, lutr_progress_fn progress, void *user, lutr_pump_stats *stats);
+
+/* run-time tunables, for benchmarking and testing: "grid_ctas" (CTAs launched by the warp-window kernels, 0 = the library's choice),
+ * "rows_per_cta" (rows of one work unit of the 4:2:2 10-bit kernels), "host_chunk_mb" (input megabytes per slot of the host pipeline's
+ * 3-slot device ring, default 64), "any_kernel" (1: route every launch through the generic tile kernel), "fast_path" (0: the same,
+ * older name), "wk_minb" (CTAs per SM the warp-window kernels are built for: 2..4), "wk_unroll" (4:2:0 8-bit kernel: window width in
+ * 64-column steps), "wk_tma" (4:2:2 10-bit stage: 1 = row-staging kernel with a cp.async ring, 2 = with TMA bulk copies; default 0 =
+ * register prefetch, the fastest of the three).  "idx_mode", "min_blocks", "fast_threads", "l2_persist" are accepted and ignored
+ * (tunables of kernel generations that are no longer in the library). */
 LUTR_API int lutr_stage_set_option(lutr_stage *stage, const char *name, int32_t value);
 
 /* ---- coefficient tables (exposed so the parity tests can pin them against libswscale) --------------- */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # LUTR_LIB: another build of the same library (A/B measurements of kernel variants in one GPU session)
 LIB_PATH = os.environ.get("LUTR_LIB") or os.path.join(_HERE, "liblutr.so")
 
-OK, ERR_INVALID_ARG, ERR_INVALID_DATA, ERR_LUT_SIZE, ERR_IO, ERR_NOMEM, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
+OK, ERR_INVALID_ARG, ERR_INVALID_DATA, ERR_LUT_SIZE, ERR_IO, ERR_NOMEM, ERR_CUDA, ERR_UNSUPPORTED, ERR_CANCELLED = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
 PIX_FMT = {"yuv420p": 0, "yuv422p10le": 1, "yuv420p10le": 2, "yuv422p": 3, "yuv444p": 4, "yuv444p10le": 5}
 RANGE = {"tv": 0, "pc": 1}
@@ -38,6 +38,13 @@ class StageDesc(Structure):
 
 class Planes(Structure):
     _fields_ = [("data", c_void_p * 3), ("stride", c_int32 * 3), ("frame_step", c_int64)]
+
+
+class PumpStats(Structure):
+    _fields_ = [("frames_in", c_int64), ("frames_out", c_int64), ("bytes_in", c_int64), ("bytes_out", c_int64), ("seconds", ctypes.c_double)]
+
+
+PROGRESS_FN = ctypes.CFUNCTYPE(None, c_void_p, c_int64)
 
 
 # every symbol include/lutr.h declares: (restype, argtypes)
@@ -65,6 +72,8 @@ SIGNATURES = {
     "lutr_stage_packed_planes": (ctypes.c_int, [c_void_p, c_int32, c_void_p, POINTER(Planes)]),
     "lutr_stage_run": (ctypes.c_int, [c_void_p, c_void_p, POINTER(Planes), POINTER(Planes), c_int32, c_void_p]),
     "lutr_stage_run_host": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32]),
+    "lutr_stage_pump": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_int32, POINTER(c_int32), PROGRESS_FN, c_void_p,
+                                       POINTER(PumpStats)]),
     "lutr_stage_sync": (ctypes.c_int, [c_void_p]),
     "lutr_stage_launch_count": (c_int64, [c_void_p]),
     "lutr_stage_kernel_name": (c_char_p, [c_void_p]),

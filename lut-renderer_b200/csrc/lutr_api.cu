@@ -1,13 +1,24 @@
 // C-ABI implementation (include/lutr.h): contexts, LUT upload, stage set-up, launches, host<->device pipelining.
-#include <algorithm>
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <poll.h>
+#include <pthread.h>
+#include <signal.h>
+#include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cerrno>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -54,14 +65,11 @@ struct lutr_stage {
     bool ev_ok = false;
     // tunables
     int rows_per_cta = 0;  // 0 = auto
-    int band_rows = 0;     // 0 = auto
     int use_fast = 1;      // 0 forces the generic kernels (testing)
     bool any_only = false; // the combination exists in the generic tile kernel (k_any.cu) only
     int pre10 = 0;         // full-range 10-bit source through the 8-bit intermediate: 1 = with pc -> tv, 2 = range kept
     int force_any = 0;     // option "any_kernel": 1 routes every launch through the generic tile kernel (testing)
     int grid_ctas = 0;     // 0 = min_blocks CTAs per SM
-    int idx_mode = 3;      // 0 = shared-memory index table, 1 = arithmetic index, 2 = arithmetic index + TMA-staged rows,
-                           // 3 = warp-window kernel (k422_warp.cu)
     int min_blocks = 2;    // occupancy variant of the fast kernels (CTAs per SM)
     int wk_pk = 1;         // warp-window kernel: packed f32x2 instructions
     int wk_unroll = 4;     // warp-window kernel: pass B steps unrolled together (experiment builds)
@@ -207,7 +215,7 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     k.min_blocks = s->min_blocks;
     k.clamp_out = lut->needs_clamp ? 1 : 0;
     bool warp_kernel = false;
-    if (fast_path_ok(s, lut) && s->idx_mode == 3) {
+    if (fast_path_ok(s, lut)) {
         // warp-window kernels: 8-column lanes (w % 8, 16-byte luma / 8-byte chroma vector accesses: check_planes), 32-bit unit counter
         const long tiles = (long)((k.w + 239) / 240) * k.h * nframes;
         warp_kernel = (k.w % 8) == 0 && k.w >= 16 && tiles < (1l << 31);
@@ -387,6 +395,7 @@ const char *lutr_status_string(int status) {
         case LUTR_ERR_NOMEM: return "out of memory";
         case LUTR_ERR_CUDA: return "CUDA error / no usable sm_100 device";
         case LUTR_ERR_UNSUPPORTED: return "unsupported configuration";
+        case LUTR_ERR_CANCELLED: return "cancelled";
         default: return "unknown status";
     }
 }
@@ -756,11 +765,11 @@ const char *lutr_stage_kernel_name(const lutr_stage *s) { return s ? s->last_ker
 int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     if (!s || !name) return LUTR_ERR_INVALID_ARG;
     if (!std::strcmp(name, "rows_per_cta")) s->rows_per_cta = value;
-    else if (!std::strcmp(name, "band_rows")) s->band_rows = value;
+    else if (!std::strcmp(name, "band_rows")) { /* accepted, ignored: band kernels are gone */ }
     else if (!std::strcmp(name, "fast_path")) s->use_fast = value;
     else if (!std::strcmp(name, "any_kernel")) s->force_any = value;
     else if (!std::strcmp(name, "grid_ctas")) s->grid_ctas = value;
-    else if (!std::strcmp(name, "idx_mode")) s->idx_mode = value < 0 || value > 3 ? 1 : value;
+    else if (!std::strcmp(name, "idx_mode")) { /* accepted, ignored (see include/lutr.h) */ }
     else if (!std::strcmp(name, "host_chunk_mb")) {
         if (value < 1 || value > 4096) {
             set_error("host_chunk_mb must be in [1, 4096]");
@@ -774,7 +783,7 @@ int lutr_stage_set_option(lutr_stage *s, const char *name, int32_t value) {
     else if (!std::strcmp(name, "wk_carveout")) s->wk_carveout = value;
     else if (!std::strcmp(name, "wk_unroll")) s->wk_unroll = value, s->wk_nk_forced = 1;
     else if (!std::strcmp(name, "wk_minb")) s->wk_minb = value >= 2 && value <= 4 ? value : 3, s->wk_minb_set = true;
-    else if (!std::strcmp(name, "min_blocks")) s->min_blocks = value >= 2 && value <= 4 ? value : 3;
+    else if (!std::strcmp(name, "min_blocks")) { /* accepted, ignored */ }
     else if (!std::strcmp(name, "fast_threads") || !std::strcmp(name, "l2_persist")) {
         // accepted for older callers; the kernel families they tuned are gone (the LUT stays L2-resident by itself)
     } else {
@@ -799,3 +808,225 @@ int lutr_tables_rgb2yuv(int32_t matrix, int32_t out[9]) {
 }
 
 }  // extern "C"
+
+// ---- raw-pipe pump: decoder process -> fd_in -> [pinned ring -> H2D -> kernel -> D2H -> pinned ring] -> fd_out -> encoder process --------
+// Replaces the blocking `Popen(ffmpeg ... -vf lut3d ...)` of the reference's TaskRunner._run_stage (reference
+// src/lut_renderer/task_manager.py:134-190) for a LUT stage.  Three threads: a reader fills pinned input slots straight from the
+// pipe, the calling thread enqueues copy-in / kernel / copy-out on the stage's three streams (fully asynchronous), a writer waits for
+// a slot's copy-out event and drains it into the pipe.  No interpreter lock, no intermediate buffers, 1 MB+ pipe buffers.
+namespace {
+
+struct PumpQueue {  // tiny blocking queue of slot indices (-1 = end of stream)
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<int> q;
+    void push(int v) {
+        { std::lock_guard<std::mutex> g(m); q.push_back(v); }
+        cv.notify_one();
+    }
+    int pop() {
+        std::unique_lock<std::mutex> g(m);
+        cv.wait(g, [&] { return !q.empty(); });
+        const int v = q.front();
+        q.pop_front();
+        return v;
+    }
+};
+
+struct PumpSlot {
+    uint8_t *hin = nullptr, *hout = nullptr, *din = nullptr, *dout = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
+    int frames = 0;
+    bool last = false;
+};
+
+void grow_pipe(int fd) {
+    // F_SETPIPE_SZ: as large as the kernel allows (the default is 64 KB, a 4K 10-bit frame is 33 MB): fewer wake-ups on both sides
+    for (int mb = 64; mb >= 1; mb /= 2)
+        if (fcntl(fd, F_SETPIPE_SZ, mb << 20) >= 0) return;
+}
+
+bool wait_fd(int fd, short events, const volatile int32_t *cancel, const std::atomic<bool> &stop) {
+    for (;;) {
+        if (stop.load(std::memory_order_relaxed) || (cancel && *cancel)) return false;
+        struct pollfd p = {fd, events, 0};
+        const int r = poll(&p, 1, 100);
+        if (r > 0) return true;  // readable / writable, hang-up or error: the read / write call reports which
+        if (r < 0 && errno != EINTR) return true;
+    }
+}
+
+}  // namespace
+
+extern "C" int lutr_stage_pump(lutr_stage *s, const lutr_lut *lut, int fd_in, int fd_out, int32_t frames_per_batch,
+                               const volatile int32_t *cancel, lutr_progress_fn progress, void *user, lutr_pump_stats *stats) {
+    if (!s || !lut || fd_in < 0 || fd_out < 0) {
+        set_error("lutr_stage_pump: NULL stage / LUT or bad file descriptor");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    if (lut->ctx->device != s->ctx->device) {
+        set_error("lutr_stage_pump: LUT and stage are on different devices");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    constexpr int NS = 4;
+    const size_t per = s->in_bytes > s->out_bytes ? s->in_bytes : s->out_bytes;
+    int batch = frames_per_batch > 0 ? frames_per_batch : (int)(((size_t)64 << 20) / per);
+    batch = batch < 1 ? 1 : (batch > 64 ? 64 : batch);
+    PumpSlot slot[NS];
+    std::atomic<bool> stop{false};
+    std::string rerr, werr;  // error text of the reader / writer thread (set_error is thread-local)
+    int rc = LUTR_OK;
+    auto release = [&]() {
+        for (PumpSlot &t : slot) {
+            if (t.hin) cudaFreeHost(t.hin);
+            if (t.hout) cudaFreeHost(t.hout);
+            if (t.din) cudaFree(t.din);
+            if (t.dout) cudaFree(t.dout);
+            if (t.ev_in) cudaEventDestroy(t.ev_in);
+            if (t.ev_k) cudaEventDestroy(t.ev_k);
+            if (t.ev_out) cudaEventDestroy(t.ev_out);
+        }
+    };
+    for (PumpSlot &t : slot) {
+        cudaError_t e = cudaHostAlloc((void **)&t.hin, (size_t)batch * s->in_bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&t.hout, (size_t)batch * s->out_bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&t.din, (size_t)batch * s->in_bytes);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&t.dout, (size_t)batch * s->out_bytes);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t.ev_in, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t.ev_k, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t.ev_out, cudaEventDisableTiming | cudaEventBlockingSync);
+        if (e != cudaSuccess) {
+            set_error("lutr_stage_pump: ring allocation failed: %s", cudaGetErrorString(e));
+            release();
+            return LUTR_ERR_CUDA;
+        }
+    }
+    grow_pipe(fd_in);
+    grow_pipe(fd_out);
+    PumpQueue free_q, filled_q, out_q;
+    for (int i = 0; i < NS; ++i) free_q.push(i);
+    int64_t frames_in = 0, frames_out = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+
+    std::thread reader([&]() {
+        for (;;) {
+            const int i = free_q.pop();
+            if (i < 0) break;
+            PumpSlot &t = slot[i];
+            const size_t want = (size_t)batch * s->in_bytes;
+            size_t got = 0;
+            bool eof = false;
+            while (got < want) {
+                if (!wait_fd(fd_in, POLLIN, cancel, stop)) { eof = true; break; }
+                const ssize_t n = read(fd_in, t.hin + got, want - got);
+                if (n > 0) got += (size_t)n;
+                else if (n == 0) { eof = true; break; }
+                else if (errno != EINTR && errno != EAGAIN) {
+                    rerr = std::string("read from the decoder pipe failed: ") + std::strerror(errno);
+                    eof = true;
+                    break;
+                }
+            }
+            t.frames = (int)(got / s->in_bytes);  // a trailing partial frame is dropped, as ffmpeg's rawvideo demuxer does
+            t.last = eof;
+            filled_q.push(i);
+            if (eof) break;
+        }
+    });
+    std::thread writer([&]() {
+        cudaSetDevice(s->ctx->device);
+        sigset_t pipe_set, old_set;
+        sigemptyset(&pipe_set);
+        sigaddset(&pipe_set, SIGPIPE);
+        pthread_sigmask(SIG_BLOCK, &pipe_set, &old_set);  // a vanished encoder is an EPIPE error here, not a fatal signal
+        bool broken = false;
+        for (;;) {
+            const int i = out_q.pop();
+            if (i < 0) break;
+            PumpSlot &t = slot[i];
+            if (cudaEventSynchronize(t.ev_out) != cudaSuccess && werr.empty()) werr = "copy-out of a batch failed", broken = true;
+            const size_t want = (size_t)t.frames * s->out_bytes;
+            size_t put = 0;
+            while (!broken && put < want) {
+                if (!wait_fd(fd_out, POLLOUT, cancel, stop)) { broken = true; break; }
+                const ssize_t n = write(fd_out, t.hout + put, want - put);
+                if (n > 0) put += (size_t)n;
+                else if (n < 0 && errno != EINTR && errno != EAGAIN) {
+                    werr = std::string("write to the encoder pipe failed: ") + std::strerror(errno);
+                    if (errno == EPIPE) {
+                        struct timespec zero = {0, 0};
+                        sigtimedwait(&pipe_set, nullptr, &zero);  // consume the pending SIGPIPE before the mask is restored
+                    }
+                    broken = true;
+                    stop.store(true);
+                }
+            }
+            if (!broken) frames_out += t.frames;
+            free_q.push(i);
+        }
+        pthread_sigmask(SIG_SETMASK, &old_set, nullptr);
+    });
+
+    // dispatcher (this thread)
+    for (;;) {
+        const int i = filled_q.pop();
+        PumpSlot &t = slot[i];
+        const bool last = t.last;
+        if (t.frames > 0 && rc == LUTR_OK && !stop.load() && !(cancel && *cancel)) {
+            lutr_planes pin{}, pout{};
+            packed_planes(s->d.in_fmt, s->d.width, s->d.height, t.din, &pin);
+            packed_planes(s->d.out_fmt, s->d.width, s->d.height, t.dout, &pout);
+            cudaError_t e = cudaMemcpyAsync(t.din, t.hin, (size_t)t.frames * s->in_bytes, cudaMemcpyHostToDevice, s->h2d);
+            if (e == cudaSuccess) e = cudaEventRecord(t.ev_in, s->h2d);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s->compute, t.ev_in, 0);
+            if (e == cudaSuccess) {
+                rc = enqueue(s, lut, &pin, &pout, t.frames, s->compute);
+                if (rc == LUTR_OK) {
+                    e = cudaEventRecord(t.ev_k, s->compute);
+                    if (e == cudaSuccess) e = cudaStreamWaitEvent(s->d2h, t.ev_k, 0);
+                    if (e == cudaSuccess) e = cudaMemcpyAsync(t.hout, t.dout, (size_t)t.frames * s->out_bytes, cudaMemcpyDeviceToHost, s->d2h);
+                    if (e == cudaSuccess) e = cudaEventRecord(t.ev_out, s->d2h);
+                }
+            }
+            if (e != cudaSuccess) {
+                set_error("lutr_stage_pump: CUDA error %s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+                rc = LUTR_ERR_CUDA;
+            }
+            if (rc == LUTR_OK) {
+                frames_in += t.frames;
+                out_q.push(i);
+                if (progress) progress(user, frames_in);
+            } else {
+                stop.store(true);
+                free_q.push(i);
+            }
+        } else {
+            free_q.push(i);
+        }
+        if (last) break;
+    }
+    out_q.push(-1);
+    writer.join();
+    stop.store(true);
+    free_q.push(-1);  // a reader still waiting for a slot
+    reader.join();
+    cudaStreamSynchronize(s->d2h);
+    cudaStreamSynchronize(s->compute);
+    release();
+    if (stats) {
+        stats->frames_in = frames_in, stats->frames_out = frames_out;
+        stats->bytes_in = frames_in * (int64_t)s->in_bytes, stats->bytes_out = frames_out * (int64_t)s->out_bytes;
+        stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (rc != LUTR_OK) return rc;
+    if (cancel && *cancel) {
+        set_error("lutr_stage_pump: cancelled");
+        return LUTR_ERR_CANCELLED;
+    }
+    if (!werr.empty() || !rerr.empty()) {
+        set_error("lutr_stage_pump: %s", (!werr.empty() ? werr : rerr).c_str());
+        return LUTR_ERR_IO;
+    }
+    return LUTR_OK;
+}

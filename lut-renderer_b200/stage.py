@@ -204,6 +204,19 @@ class ColourStage:
         """H2D -> kernel -> D2H for tightly packed host frames; returns when ``dst`` is complete."""
         N.check(N.lib().lutr_stage_run_host(self._h, lut._h, _address(src), _address(dst), int(nframes)))
 
+    def pump(self, lut: DeviceLut, fd_in: int, fd_out: int, frames_per_batch: int = 0, cancel=None, on_frames=None) -> dict:
+        """Stream raw frames from ``fd_in`` through the stage into ``fd_out`` until end of file (lutr_stage_pump: reader thread,
+        pinned ring, H2D / kernel / D2H, writer thread, all inside the library and outside the interpreter lock).
+
+        ``cancel``: a ``ctypes.c_int32`` the caller may set to 1 from another thread; ``on_frames(total)`` is called after every
+        batch.  Returns the pump statistics; raises ``LutrError`` (status ERR_CANCELLED / ERR_IO / ERR_CUDA) otherwise."""
+        stats = N.PumpStats()
+        cb = N.PROGRESS_FN((lambda user, total: on_frames(int(total))) if on_frames else (lambda user, total: None))
+        flag = cancel if cancel is not None else ctypes.c_int32(0)
+        N.check(N.lib().lutr_stage_pump(self._h, lut._h, int(fd_in), int(fd_out), int(frames_per_batch), byref(flag), cb, None, byref(stats)))
+        return {"frames_in": stats.frames_in, "frames_out": stats.frames_out, "bytes_in": stats.bytes_in, "bytes_out": stats.bytes_out,
+                "seconds": stats.seconds}
+
     def sync(self) -> None:
         N.check(N.lib().lutr_stage_sync(self._h))
 

@@ -13,7 +13,7 @@ Stages without a LUT (pro mode stage 2) still run as the reference's single ffmp
 """
 from __future__ import annotations
 
-import queue
+import ctypes
 import shlex
 import subprocess
 import threading
@@ -34,38 +34,18 @@ class TaskCallbacks:
     def log(self, task_id: str, message: str) -> None: ...
 
 
-def _grow_pipe(stream, size: int = 1 << 20) -> None:
-    """Ask the kernel for a 1 MB pipe buffer (Linux F_SETPIPE_SZ; the default is 64 KB, a 4K 10-bit frame is 33 MB): fewer wake-ups
-    per frame on both sides of the raw pipes.  Silently keeps the default where the call is unavailable or refused."""
-    try:
-        import fcntl
-        fcntl.fcntl(stream.fileno(), getattr(fcntl, "F_SETPIPE_SZ", 1031), size)
-    except Exception:
-        pass
-
-
-def _read_exact(pipe, view) -> int:
-    """Fill ``view`` (a writable memoryview) from ``pipe``; returns bytes read (short only at EOF)."""
-    got = 0
-    while got < len(view):
-        n = pipe.readinto(view[got:])
-        if not n:
-            break
-        got += n
-    return got
-
-
 class TaskRunner:
     def __init__(self, task: Task, ffmpeg_bin: str = "ffmpeg", device: int = 0, callbacks: Optional[TaskCallbacks] = None,
-                 frames_per_batch: int = 8, popen: Callable = subprocess.Popen, probe: Callable = probe_video,
+                 frames_per_batch: int = 0, popen: Callable = subprocess.Popen, probe: Callable = probe_video,
                  devices: Optional[List[int]] = None):
         self.task, self.ffmpeg_bin, self.device = task, ffmpeg_bin, device
         # more than one entry: every LUT stage of the task is cut into GOP-aligned frame ranges, one per listed GPU
         self.devices = list(devices) if devices else [device]
         self.signals = callbacks or TaskCallbacks()
-        self.frames_per_batch = max(1, frames_per_batch)
+        self.frames_per_batch = max(0, frames_per_batch)   # 0 = the library picks ~64 MB batches
         self._popen, self._probe = popen, probe
         self._procs: List = []
+        self._cancel_flags: List = []   # ctypes flags of running lutr_stage_pump calls
         self._cancelled = False
         self._lock = threading.Lock()
 
@@ -74,6 +54,8 @@ class TaskRunner:
         self._cancelled = True
         with self._lock:
             procs = list(self._procs)
+            for flag in self._cancel_flags:
+                flag.value = 1
         for p in procs:
             try:
                 if p.poll() is None:
@@ -223,96 +205,54 @@ class TaskRunner:
         return False
 
     def _pump(self, plan, decode_cmd, encode_cmd, device: int, on_frames: Callable[[int], None]):
-        """decoder process -> raw pipe -> GPU colour stage on ``device`` -> raw pipe -> encoder process, three batches in flight.
+        """decoder process -> raw pipe -> GPU colour stage on ``device`` -> raw pipe -> encoder process.
+
+        The data path is one library call (``ColourStage.pump`` -> ``lutr_stage_pump``): a reader thread fills a pinned ring straight
+        from the decoder's pipe, the GPU stage runs H2D / kernel / D2H on its three streams, a writer thread drains into the encoder's
+        pipe -- no Python on the per-frame path.  This method only owns the two child processes, cancellation and the exit codes.
         Returns (first non-zero exit code of the two processes -- 0 = both fine, None when cancelled --, frames processed)."""
         from .stage import ColourStage  # deferred: loads liblutr.so, fails loudly when it is missing
         colour = ColourStage.from_plan(plan, device=device)
         lut = colour.ctx.lut_from_cube(plan.lut_path)
-        nb = self.frames_per_batch
-        # three batches in flight: a reader thread fills pinned input buffers from the decoder's pipe, this thread runs the GPU
-        # stage (H2D -> kernel -> D2H), a writer thread drains pinned output buffers into the encoder's pipe
-        nbuf = 3
-        pin_in = [colour.ctx.pinned_buffer(nb * colour.in_frame_bytes) for _ in range(nbuf)]
-        pin_out = [colour.ctx.pinned_buffer(nb * colour.out_frame_bytes) for _ in range(nbuf)]
         dec = self._spawn(decode_cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, bufsize=0)
         enc = self._spawn(encode_cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, bufsize=0)
-        _grow_pipe(dec.stdout)
-        _grow_pipe(enc.stdin)
-        free_q: "queue.Queue[int]" = queue.Queue()
-        filled_q: "queue.Queue" = queue.Queue()
-        write_q: "queue.Queue" = queue.Queue()
-        for i in range(nbuf):
-            free_q.put(i)
-        errors: List[BaseException] = []
+        flag = ctypes.c_int32(1 if self._cancelled else 0)
+        with self._lock:
+            self._cancel_flags.append(flag)
+        seen = [0]
 
-        def reader():
-            try:
-                while not self._cancelled:
-                    i = free_q.get()
-                    if i is None:
-                        break
-                    got = _read_exact(dec.stdout, memoryview(pin_in[i].array))
-                    filled_q.put((i, got))
-                    if got < len(pin_in[i].array):
-                        return
-            except BaseException as exc:  # noqa: BLE001 -- reported through the task status
-                errors.append(exc)
-            filled_q.put((None, 0))
+        def progress(total: int) -> None:
+            on_frames(total - seen[0])
+            seen[0] = total
 
-        def writer():
-            broken = False
-            while True:
-                item = write_q.get()
-                if item is None:
-                    return
-                i, nbytes = item
-                if not broken:
-                    try:
-                        enc.stdin.write(memoryview(pin_out[i].array)[:nbytes])
-                    except BaseException as exc:  # noqa: BLE001 -- the encoder went away: stop feeding it
-                        errors.append(exc)
-                        broken = True
-                free_q.put(i)
-
-        rt, wt = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
-        rt.start()
-        wt.start()
+        error: Optional[BaseException] = None
         frames_done = 0
         try:
-            while not self._cancelled and not errors:
-                i, got = filled_q.get()
-                n = got // colour.in_frame_bytes if i is not None else 0
-                if n == 0:
-                    break
-                colour.run_host(lut, pin_in[i], pin_out[i], n)
-                write_q.put((i, n * colour.out_frame_bytes))
-                frames_done += n
-                on_frames(n)
-                if got < len(pin_in[i].array):
-                    break
-        except BaseException as exc:  # noqa: BLE001 -- a failing GPU call must take the children down, not leave them blocked on full pipes
-            errors.append(exc)
+            stats = colour.pump(lut, dec.stdout.fileno(), enc.stdin.fileno(), self.frames_per_batch, flag, progress)
+            frames_done = int(stats["frames_out"])
+        except BaseException as exc:  # noqa: BLE001 -- a failing GPU call / pipe must take the children down, not leave them blocked
+            error = exc
         finally:
-            write_q.put(None)
-            wt.join()
+            with self._lock:
+                self._cancel_flags.remove(flag)
             try:
                 enc.stdin.close()
             except Exception:
                 pass
-            if self._cancelled or errors:
+            if self._cancelled or error is not None:
                 for p in (dec, enc):
                     if p.poll() is None:
                         p.kill()
-            free_q.put(None)          # releases a reader that waits for a buffer; one blocked in read() ends with the decoder
             rc_dec, rc_enc = dec.wait(), enc.wait()
-            rt.join(timeout=5.0)
-            for b in pin_in + pin_out:
-                b.close()
+            try:
+                dec.stdout.close()
+            except Exception:
+                pass
             colour.close()
-        if errors and not self._cancelled:
-            raise RuntimeError(f"colour stage / raw pipe failed: {errors[0]}")
         if self._cancelled:
             return None, frames_done
+        if error is not None:
+            raise RuntimeError(f"colour stage / raw pipe failed: {error}")
         return (rc_enc or rc_dec), frames_done
 
     def _run_plain(self, stage: CommandStage, info: Optional[VideoInfo], base: int, span: int, final: bool) -> Optional[bool]:

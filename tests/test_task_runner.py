@@ -82,24 +82,15 @@ def test_cancel_before_start(tmp_path):
 
 # ---- the pipelined GPU pump (reader thread | stage | writer thread) with the stage itself replaced by a byte-flipping stand-in: the
 # ---- threading, pipe, cancel, failure and sharding logic is host code and must hold without a GPU ---------------------------------
-class _FakeBuf:
-    def __init__(self, n):
-        import numpy as np
-        self.array = np.zeros(n, np.uint8)
-
-    def close(self):
-        pass
-
-
 class _FakeCtx:
-    def pinned_buffer(self, n):
-        return _FakeBuf(n)
-
     def lut_from_cube(self, path):
         return object()
 
 
 class _FakeStage:
+    """Stand-in for ColourStage on a box without a GPU: same `pump` contract (read whole frames from fd_in until EOF, write the
+    processed frames to fd_out, poll the cancel flag, raise on a broken pipe), the 'colour stage' being a byte flip."""
+
     def __init__(self, plan):
         self.ctx = _FakeCtx()
         self.in_frame_bytes = self.out_frame_bytes = plan.width * plan.height * 3 // 2
@@ -108,9 +99,42 @@ class _FakeStage:
     def from_plan(cls, plan, device=0, float_mode="c"):
         return cls(plan)
 
-    def run_host(self, lut, src, dst, n):
-        k = n * self.in_frame_bytes
-        dst.array[:k] = 255 - src.array[:k]
+    def process(self, data):
+        import numpy as np
+        return (255 - np.frombuffer(data, np.uint8)).tobytes()
+
+    def pump(self, lut, fd_in, fd_out, frames_per_batch=0, cancel=None, on_frames=None):
+        import os
+        import select
+        from lut_renderer_b200._native import ERR_CANCELLED, ERR_IO, LutrError
+        fb, nb, total, pending = self.in_frame_bytes, max(1, frames_per_batch), 0, b""
+        while True:
+            if cancel is not None and cancel.value:
+                raise LutrError(ERR_CANCELLED, "cancelled")
+            if not select.select([fd_in], [], [], 0.1)[0]:
+                continue
+            chunk = os.read(fd_in, nb * fb - len(pending))
+            pending += chunk
+            if chunk and len(pending) < nb * fb:
+                continue
+            n = len(pending) // fb
+            if n:
+                out = memoryview(self.process(pending[:n * fb]))
+                while out:
+                    if cancel is not None and cancel.value:
+                        raise LutrError(ERR_CANCELLED, "cancelled")
+                    if not select.select([], [fd_out], [], 0.1)[1]:
+                        continue
+                    try:
+                        out = out[os.write(fd_out, out[:1 << 16]):]
+                    except OSError as exc:
+                        raise LutrError(ERR_IO, f"write to the encoder pipe failed: {exc}")
+                total += n
+                pending = pending[n * fb:]
+                if on_frames:
+                    on_frames(total)
+            if not chunk:
+                return {"frames_in": total, "frames_out": total}
 
     def close(self):
         pass
@@ -221,11 +245,11 @@ def test_stage_failure_kills_the_children_and_fails_the_task(monkeypatch, tmp_pa
     class Boom(_FakeStage):
         calls = 0
 
-        def run_host(self, lut, src, dst, n):
+        def process(self, data):
             Boom.calls += 1
             if Boom.calls == 2:
                 raise RuntimeError("CUDA error: injected")
-            super().run_host(lut, src, dst, n)
+            return super().process(data)
 
     procs = []
 

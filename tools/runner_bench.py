@@ -20,10 +20,10 @@ from lut_renderer_b200 import ProcessingParams, Task, VideoInfo, synth  # noqa: 
 from lut_renderer_b200.task_manager import TaskCallbacks, TaskRunner  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--frames", type=int, default=240)
+ap.add_argument("--frames", type=int, default=480)
 ap.add_argument("--size", default="3840x2160")
 ap.add_argument("--fmt", default="yuv422p10le")
-ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--batch", type=int, default=0, help="frames per batch of the pump (0 = the library picks ~64 MB)")
 ap.add_argument("--shards", type=int, default=1, help="cut the clip into this many frame ranges, each with its own decoder / encoder chain (all on GPU 0)")
 args = ap.parse_args()
 w, h = (int(v) for v in args.size.split("x"))
@@ -35,12 +35,14 @@ depth = 10 if "10" in args.fmt else 8
 info = VideoInfo(width=w, height=h, pix_fmt=args.fmt, bit_depth=depth, colorspace="bt709", color_range="tv", fps=25.0, duration=args.frames / 25.0)
 params = ProcessingParams(video_codec="prores_ks" if depth == 10 else "libx264")
 task = Task("bench", tmp / "in.mov", tmp / "out.mov", cube, None, params, source_info=info)
-sink = "import sys; i=sys.stdin.buffer\nwhile i.read(1<<22): pass"
+sink = "f=open(0,'rb',buffering=0); b=bytearray(1<<22)\nwhile f.readinto(b): pass"
 
 
 def popen(cmd, **kw):
     if "pipe:1" in cmd:      # generator: as many frames as this decoder was asked for
-        count = int(cmd[cmd.index("-frames:v") + 1]) if "-frames:v" in cmd else args.frames
+        import math
+        start = math.ceil(float(cmd[cmd.index("-ss") + 1]) * 25.0 - 1e-6) if "-ss" in cmd else 0
+        count = int(cmd[cmd.index("-frames:v") + 1]) if "-frames:v" in cmd else args.frames - start
         code = f"import sys; b=open({str(tmp / 'frame.raw')!r},'rb').read(); o=sys.stdout.buffer\nfor _ in range({count}): o.write(b)"
     elif "pipe:0" in cmd:    # sink (a part file must exist for the concat step of a sharded run)
         code = sink + f"\nopen({cmd[-1]!r}, 'wb').close()"
