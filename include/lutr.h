@@ -77,7 +77,10 @@ typedef enum lutr_interp {
     LUTR_INTERP_TRILINEAR = 1,
     LUTR_INTERP_TETRAHEDRAL = 2,
     LUTR_INTERP_PYRAMID = 3, /* accepted by the reference's whitelist (ffmpeg.py:243); generic kernel only */
-    LUTR_INTERP_PRISM = 4
+    LUTR_INTERP_PRISM = 4,
+    LUTR_INTERP_NONE = 5     /* no lut3d at all: pro mode stage 2 (ffmpeg.py:459-471), the encoding ffmpeg's own yuv422p10le ->
+                                yuv420p | yuv420p10le | yuv422p conversion (auto-inserted swscale pass).  The `lut` argument of the
+                                run / pump calls is ignored (may be NULL); matrices and ranges must be equal on both sides. */
 } lutr_interp;
 
 /* Float evaluation order of the LUT blend.  C = FFmpeg's C code (separate mul and add; what packed

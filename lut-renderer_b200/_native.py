@@ -19,7 +19,7 @@ PIX_FMT = {"yuv420p": 0, "yuv422p10le": 1, "yuv420p10le": 2, "yuv422p": 3, "yuv4
 RANGE = {"tv": 0, "pc": 1}
 MATRIX = {"bt709": 0, "bt601": 1, "smpte170m": 1, "bt470bg": 1, "bt2020": 2, "bt2020nc": 2, "bt2020c": 2, "fcc": 3,
           "smpte240m": 4}
-INTERP = {"nearest": 0, "trilinear": 1, "tetrahedral": 2, "pyramid": 3, "prism": 4}
+INTERP = {"nearest": 0, "trilinear": 1, "tetrahedral": 2, "pyramid": 3, "prism": 4, "none": 5}
 FLOAT_MODE = {"c": 0, "fma": 1}
 
 

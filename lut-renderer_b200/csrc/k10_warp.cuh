@@ -431,7 +431,7 @@ int launch_k10(const StageK &k, int interp, int float_mode, bool grid_forced, vo
                                                   : pick_sem<IN420, OUT420, OUT8, LUTR_INTERP_TETRAHEDRAL, 3>(fma, clamp, fold_nomin, k.lut.n);
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return LUTR_ERR_CUDA;
     const long total_c = (long)k.nframes * k.tiles_per_row * (k.h / 2);
-    long grid = grid_forced ? k.grid_ctas : 148 * minb;
+    long grid = k.grid_ctas > 0 ? k.grid_ctas : 148 * minb;
     // small jobs: a smaller grid so that a share is at least 16 chroma rows and the ring warm-up / halo rows stay cheap
     if (!grid_forced && total_c / (kW10 * grid) < 16) grid = total_c / (kW10 * 16) > 0 ? total_c / (kW10 * 16) : 1;
     fn<<<(unsigned)grid, kW10 * 32, smem, (cudaStream_t)stream>>>(k);

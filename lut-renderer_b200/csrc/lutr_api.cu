@@ -67,6 +67,7 @@ struct lutr_stage {
     int rows_per_cta = 0;  // 0 = auto
     int use_fast = 1;      // 0 forces the generic kernels (testing)
     bool any_only = false; // the combination exists in the generic tile kernel (k_any.cu) only
+    bool convert_only = false;  // interp = LUTR_INTERP_NONE: LUT-less conversion of the master (k_convert.cu)
     int pre10 = 0;         // full-range 10-bit source through the 8-bit intermediate: 1 = with pc -> tv, 2 = range kept
     int force_any = 0;     // option "any_kernel": 1 routes every launch through the generic tile kernel (testing)
     int grid_ctas = 0;     // 0 = min_blocks CTAs per SM
@@ -195,6 +196,24 @@ bool fast_path_ok(const lutr_stage *s, const lutr_lut *lut) {
 int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lutr_planes *out, int nframes, cudaStream_t st) {
     StageK k{};
     k.w = s->d.width, k.h = s->d.height, k.nframes = nframes;
+    if (s->convert_only) {  // pro mode stage 2 without a LUT: one streaming kernel, at most 65535 frames per launch (grid z)
+        for (int f0 = 0; f0 < nframes; f0 += 65535) {
+            k.nframes = std::min(65535, nframes - f0);
+            for (int p = 0; p < 3; ++p) {
+                k.p.in[p] = (const uint8_t *)in->data[p] + (size_t)f0 * in->frame_step, k.p.out[p] = (uint8_t *)out->data[p] + (size_t)f0 * out->frame_step;
+                k.p.in_stride[p] = in->stride[p], k.p.out_stride[p] = out->stride[p];
+            }
+            k.p.in_step = nframes > 1 ? in->frame_step : 0, k.p.out_step = nframes > 1 ? out->frame_step : 0;
+            const int rc = launch_k_convert(k, s->d.out_fmt, st);
+            if (rc != LUTR_OK) {
+                set_error("kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return rc;
+            }
+            s->launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        s->last_kernel = "k_convert";
+        return LUTR_OK;
+    }
     k.range_pass = (s->d.in_range == LUTR_RANGE_PC && s->d.norm_range == LUTR_RANGE_TV) ? 1 : 0;
     k.f = s->f, k.b = s->b;
     const float lut_max = (float)(lut->size - 1);
@@ -296,8 +315,10 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             rc = run_any();
         } else {
             k.rows_per_cta = 0, k.bands = 1;
-            k.grid_ctas = s->grid_ctas;
             k.min_blocks = s->wk_minb_set ? s->wk_minb : 2;  // measured: +5..10 % over 3 CTAs x 80 registers (spills)
+            // more CTAs than resident slots: the hardware deals them out as others retire (profiles/r02_grid_sweep_other_kernels.jsonl);
+            // every share pays 6 halo rows of the vertical output filter, which bounds the useful multiple
+            k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : 6 * k.min_blocks * s->ctx->sm_count;
             rc = launch_k10_warp8(k, s->d.in_fmt == LUTR_PIX_YUV420P10LE, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
             s->last_kernel = s->d.in_fmt == LUTR_PIX_YUV420P10LE ? "k10_warp8<420>" : "k10_warp8<422>";
         }
@@ -307,8 +328,9 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         } else {
             const bool in420 = s->d.in_fmt == LUTR_PIX_YUV420P10LE, out420 = s->d.out_fmt == LUTR_PIX_YUV420P10LE;
             k.rows_per_cta = 0, k.bands = 1;
-            k.grid_ctas = s->grid_ctas;
             k.min_blocks = s->wk_minb_set ? s->wk_minb : 2;  // measured: +5..10 % over 3 CTAs x 80 registers (spills)
+            // as above; a 4:2:2 output side is row-local (no halo rows per share), so shares can be much shorter
+            k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : (out420 ? 6 : 24) * k.min_blocks * s->ctx->sm_count;
             rc = launch_k10_warp(k, in420, out420, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
             s->last_kernel = !out420 ? "k10_warp<420,422>" : (in420 ? "k10_warp<420,420>" : "k10_warp<422,420>");
         }
@@ -345,6 +367,8 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         const bool in422 = s->d.in_fmt == LUTR_PIX_YUV422P;
         k.wk_unroll = s->wk_nk_forced ? s->wk_unroll : 0;
         k.rows_per_cta = 0, k.bands = 1;
+        if (s->grid_ctas <= 0)  // as above: 4 x the resident CTAs with the 6 halo rows of a 4:2:0 output (2 x for trilinear), 16 x without
+            k.grid_ctas *= s->d.out_fmt != LUTR_PIX_YUV420P ? 16 : (s->d.interp == LUTR_INTERP_TRILINEAR ? 2 : 4);
         if (s->d.out_fmt == LUTR_PIX_YUV422P10LE) {
             rc = launch_k420_warp10(k, in422, s->d.interp, s->d.float_mode, s->grid_ctas > 0, st);
             s->last_kernel = in422 ? "k420_warp10<422>" : "k420_warp10";
@@ -569,7 +593,7 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
         return LUTR_ERR_INVALID_ARG;
     }
     const lutr_stage_desc &d = *desc;
-    if (d.width <= 0 || d.height <= 0 || d.interp < 0 || d.interp > LUTR_INTERP_PRISM || d.float_mode < 0 || d.float_mode > 1 ||
+    if (d.width <= 0 || d.height <= 0 || d.interp < 0 || d.interp > LUTR_INTERP_NONE || d.float_mode < 0 || d.float_mode > 1 ||
         d.in_matrix < 0 || d.in_matrix > 4 || d.out_matrix < 0 || d.out_matrix > 4 || d.in_range < 0 || d.in_range > 1 ||
         d.norm_range < 0 || d.norm_range > 1 || d.out_range < 0 || d.out_range > 1 || d.in_fmt < 0 ||
         d.in_fmt > LUTR_PIX_YUV444P10LE || d.out_fmt < 0 || d.out_fmt > LUTR_PIX_YUV444P10LE) {
@@ -599,6 +623,17 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
         set_error("stage: 4:2:0 input / output needs an even height >= %d", min_h);
         return LUTR_ERR_UNSUPPORTED;
     }
+    const bool convert_only = d.interp == LUTR_INTERP_NONE;
+    if (convert_only) {
+        // pro mode stage 2 (reference ffmpeg.py:459-471): the master is yuv422p10le, tv range, and the conversion changes neither matrix nor range
+        const bool out_ok = d.out_fmt == LUTR_PIX_YUV420P || d.out_fmt == LUTR_PIX_YUV420P10LE || d.out_fmt == LUTR_PIX_YUV422P;
+        if (d.in_fmt != LUTR_PIX_YUV422P10LE || !out_ok || d.in_range != LUTR_RANGE_TV || d.out_range != LUTR_RANGE_TV ||
+            d.in_matrix != d.out_matrix || (d.width % 8) || (d.height % 2) || d.height < 14) {
+            set_error("stage: interp=none converts yuv422p10le (tv) to yuv420p / yuv420p10le / yuv422p with the same matrix and range; "
+                      "width a multiple of 8, even height >= 14");
+            return LUTR_ERR_UNSUPPORTED;
+        }
+    }
     // combinations with a specialised warp-window kernel; everything else runs the generic tile kernel (k_any.cu)
     const bool tri_tet = d.interp == LUTR_INTERP_TRILINEAR || d.interp == LUTR_INTERP_TETRAHEDRAL;
     const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
@@ -623,7 +658,8 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
     s->d = d;
     s->depth = pre10 ? 8 : pix_depth(d.in_fmt);  // depth of the RGB intermediate the LUT works on
     s->pre10 = pre10 ? (range_pass ? 1 : 2) : 0;
-    s->any_only = !specialised;
+    s->any_only = !specialised && !convert_only;
+    s->convert_only = convert_only;
     // YUV->RGB sees the range left by the normalisation pass
     make_yuv2rgb(d.in_matrix, d.norm_range == LUTR_RANGE_PC, s->f);
     make_rgb2yuv(d.out_matrix, s->b);
@@ -679,11 +715,11 @@ int lutr_stage_packed_planes(const lutr_stage *s, int32_t which, void *base, lut
 
 int lutr_stage_run(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lutr_planes *out, int32_t nframes,
                    void *cuda_stream) {
-    if (!s || !lut || !in || !out || nframes <= 0) {
+    if (!s || (!lut && !s->convert_only) || !in || !out || nframes <= 0) {
         set_error("lutr_stage_run: NULL argument or nframes <= 0");
         return LUTR_ERR_INVALID_ARG;
     }
-    if (lut->ctx->device != s->ctx->device) {
+    if (lut && lut->ctx->device != s->ctx->device) {
         set_error("lutr_stage_run: LUT lives on device %d, stage on device %d", lut->ctx->device, s->ctx->device);
         return LUTR_ERR_INVALID_ARG;
     }
@@ -695,11 +731,11 @@ int lutr_stage_run(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, co
 }
 
 int lutr_stage_run_host(lutr_stage *s, const lutr_lut *lut, const void *in_host, void *out_host, int32_t nframes) {
-    if (!s || !lut || !in_host || !out_host || nframes <= 0) {
+    if (!s || (!lut && !s->convert_only) || !in_host || !out_host || nframes <= 0) {
         set_error("lutr_stage_run_host: NULL argument or nframes <= 0");
         return LUTR_ERR_INVALID_ARG;
     }
-    if (lut->ctx->device != s->ctx->device) {
+    if (lut && lut->ctx->device != s->ctx->device) {
         set_error("lutr_stage_run_host: LUT and stage are on different devices");
         return LUTR_ERR_INVALID_ARG;
     }
@@ -865,11 +901,11 @@ bool wait_fd(int fd, short events, const volatile int32_t *cancel, const std::at
 
 extern "C" int lutr_stage_pump(lutr_stage *s, const lutr_lut *lut, int fd_in, int fd_out, int32_t frames_per_batch,
                                const volatile int32_t *cancel, lutr_progress_fn progress, void *user, lutr_pump_stats *stats) {
-    if (!s || !lut || fd_in < 0 || fd_out < 0) {
+    if (!s || (!lut && !s->convert_only) || fd_in < 0 || fd_out < 0) {
         set_error("lutr_stage_pump: NULL stage / LUT or bad file descriptor");
         return LUTR_ERR_INVALID_ARG;
     }
-    if (lut->ctx->device != s->ctx->device) {
+    if (lut && lut->ctx->device != s->ctx->device) {
         set_error("lutr_stage_pump: LUT and stage are on different devices");
         return LUTR_ERR_INVALID_ARG;
     }

@@ -127,7 +127,8 @@ int launch_k420_warp(const StageK &k, bool in422, int interp, int float_mode, bo
 // 10-bit chains with a 4:2:0 side (k10_warp.cu): yuv420p10le in and / or yuv420p10le out
 int launch_k10_warp(const StageK &k, bool in420, bool out420, int interp, int float_mode, bool grid_forced, void *stream);
 int launch_k10_warp8(const StageK &k, bool in420, int interp, int float_mode, bool grid_forced, void *stream);  // ... -> yuv420p (8 bit)
-int launch_k_any(const StageK &k, int interp, int float_mode, void *stream);  // generic tile kernel, the whole format matrix
+int launch_k_any(const StageK &k, int interp, int float_mode, void *stream);
+int launch_k_convert(const StageK &k, int out_fmt, void *stream);  // LUT-less yuv422p10le -> yuv420p | yuv420p10le | yuv422p (k_convert.cu)  // generic tile kernel, the whole format matrix
 int launch_k420_warp10(const StageK &k, bool in422, int interp, int float_mode, bool grid_forced, void *stream);  // yuv422p10le out
 int launch_k420_warp422(const StageK &k, bool in422, int interp, int float_mode, bool grid_forced, void *stream);  // yuv422p (8 bit) out
 int launch_k420_warp444(const StageK &k, bool in422, int interp, int float_mode, bool grid_forced, void *stream);  // yuv444p (8 bit) out

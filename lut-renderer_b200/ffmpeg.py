@@ -474,6 +474,30 @@ def plan_colour_stage(params: ProcessingParams, lut_path: Optional[Path], source
         notes=plan_notes)
 
 
+def plan_conversion_stage(params: ProcessingParams, source_info: Optional[VideoInfo],
+                          notes: Optional[List[str]] = None) -> Optional[ColourStagePlan]:
+    """Pro mode stage 2 (reference ffmpeg.py:459-471): no LUT, but the encoding ffmpeg still converts the yuv422p10le master to the
+    delivery pix_fmt with an auto-inserted swscale pass.  Returns the plan of that conversion for the GPU stage (``interp="none"``)
+    when it is one the stage implements -- yuv422p10le, limited range, to yuv420p / yuv420p10le / yuv422p, width a multiple of 8 --
+    else None (nothing to convert, or a conversion that stays inside ffmpeg)."""
+    info = source_info
+    if not info or not info.width or not info.height or str(info.pix_fmt or "") != "yuv422p10le":
+        return None
+    if str(info.color_range or "tv").lower() == "pc" or params.video_codec in ("", "copy"):
+        return None
+    quiet: List[str] = []
+    out_pix_fmt = _resolve_pix_fmt(params, info, quiet)
+    if out_pix_fmt not in ("yuv420p", "yuv420p10le", "yuv422p") or int(info.width) % 8 or int(info.height) % 2 or int(info.height) < 14:
+        return None
+    if notes is not None:
+        notes.append(f"分发编码: 像素格式转换 yuv422p10le -> {out_pix_fmt} 在 GPU 上完成（无 LUT，swscale 等价算法）")
+    matrix = _effective_matrix(None, info.colorspace)
+    return ColourStagePlan(width=int(info.width), height=int(info.height), in_pix_fmt="yuv422p10le", out_pix_fmt=out_pix_fmt,
+                           in_range="tv", norm_range="tv", in_matrix=matrix, out_matrix=matrix, out_range="tv", interp="none",
+                           lut_path=None, rgb_intermediate="none", reference_filters=[f"format={out_pix_fmt}"],
+                           notes=notes if notes is not None else [])
+
+
 @dataclass
 class GpuCommandStage:
     """decode -> raw pipe -> GPU colour stage -> raw pipe -> encode, for one ``CommandStage`` with a LUT."""
@@ -524,15 +548,20 @@ def _pipe_timing(params: ProcessingParams, info: Optional[VideoInfo]) -> Tuple[L
     return ["-fps_mode", "passthrough"], src_fps
 
 
-def build_gpu_stage(stage: CommandStage, source_info: Optional[VideoInfo], ffmpeg_bin: str = "ffmpeg") -> Optional[GpuCommandStage]:
+def build_gpu_stage(stage: CommandStage, source_info: Optional[VideoInfo], ffmpeg_bin: str = "ffmpeg",
+                    convert_without_lut: bool = False) -> Optional[GpuCommandStage]:
     """Split a LUT-carrying stage into a raw-video decoder and a raw-video encoder around the GPU stage.
 
     The encoder command carries every option ``build_command`` would have put on the single process
     (codec, rate control, timing, tags); only the `-vf` colour chain is gone and its input is the raw pipe.
     Audio and metadata are taken from the original source as a second input.  Raises ``RawPipeUnsupported`` when the
-    source timing cannot be reproduced over a raw pipe (see ``_pipe_timing``).
+    source timing cannot be reproduced over a raw pipe (see ``_pipe_timing``).  ``convert_without_lut``: also split a stage WITHOUT a
+    LUT (pro mode stage 2) when its pixel-format conversion is one the GPU stage implements (``plan_conversion_stage``).
     """
-    plan = plan_colour_stage(stage.params, stage.lut_path, source_info, stage.notes)
+    if stage.lut_path:
+        plan = plan_colour_stage(stage.params, stage.lut_path, source_info, stage.notes)
+    else:
+        plan = plan_conversion_stage(stage.params, source_info, stage.notes) if convert_without_lut else None
     if plan is None:
         return None
     params = stage.params
@@ -554,7 +583,7 @@ def build_gpu_stage(stage: CommandStage, source_info: Optional[VideoInfo], ffmpe
     fps_value = _timing_args(encode, params, source_info, quiet)
     encode += ["-pix_fmt", plan.out_pix_fmt]
     _rate_and_codec_args(encode, params, fps_value, quiet)
-    _output_tag_args(encode, params, source_info, True, quiet)
+    _output_tag_args(encode, params, source_info, bool(stage.lut_path), quiet)
     _audio_and_mux_args(encode, params)
     encode.append(str(stage.output_path))
     return GpuCommandStage(stage=stage, plan=plan, decode_cmd=decode, encode_cmd=encode)

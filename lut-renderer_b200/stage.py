@@ -155,7 +155,7 @@ class ColourStage:
                  in_range: str = "tv", norm_range: Optional[str] = None, in_matrix: str = "bt709", out_matrix: str = "bt709",
                  out_range: str = "tv", interp: str = "tetrahedral", float_mode: str = "c", device: int = 0, via_8bit: bool = False):
         out_pix_fmt = out_pix_fmt or pix_fmt
-        if interp not in GPU_INTERPS:
+        if interp not in GPU_INTERPS and interp != "none":   # "none": LUT-less conversion of the master (pro mode stage 2)
             raise N.LutrError(N.ERR_UNSUPPORTED, f"interp={interp} is not implemented on the GPU stage (have {GPU_INTERPS})")
         for name, table, value in (("pix_fmt", N.PIX_FMT, pix_fmt), ("out_pix_fmt", N.PIX_FMT, out_pix_fmt)):
             if value not in table:
@@ -188,7 +188,7 @@ class ColourStage:
         pin, pout = N.Planes(), N.Planes()
         N.check(N.lib().lutr_stage_packed_planes(self._h, 0, _address(src), byref(pin)))
         N.check(N.lib().lutr_stage_packed_planes(self._h, 1, _address(dst), byref(pout)))
-        N.check(N.lib().lutr_stage_run(self._h, lut._h, byref(pin), byref(pout), int(nframes), _stream_arg(stream)))
+        N.check(N.lib().lutr_stage_run(self._h, (lut._h if lut is not None else None), byref(pin), byref(pout), int(nframes), _stream_arg(stream)))
 
     def run_planes(self, lut: DeviceLut, in_planes, in_strides, out_planes, out_strides, nframes: int = 1,
                    in_frame_step: int = 0, out_frame_step: int = 0, stream=None) -> None:
@@ -197,12 +197,12 @@ class ColourStage:
             pin.data[i], pin.stride[i] = _address(in_planes[i]), int(in_strides[i])
             pout.data[i], pout.stride[i] = _address(out_planes[i]), int(out_strides[i])
         pin.frame_step, pout.frame_step = int(in_frame_step), int(out_frame_step)
-        N.check(N.lib().lutr_stage_run(self._h, lut._h, byref(pin), byref(pout), int(nframes), _stream_arg(stream)))
+        N.check(N.lib().lutr_stage_run(self._h, (lut._h if lut is not None else None), byref(pin), byref(pout), int(nframes), _stream_arg(stream)))
 
     # -- host frames (the raw-pipe path) ---------------------------------------------------------------------
     def run_host(self, lut: DeviceLut, src, dst, nframes: int = 1) -> None:
         """H2D -> kernel -> D2H for tightly packed host frames; returns when ``dst`` is complete."""
-        N.check(N.lib().lutr_stage_run_host(self._h, lut._h, _address(src), _address(dst), int(nframes)))
+        N.check(N.lib().lutr_stage_run_host(self._h, (lut._h if lut is not None else None), _address(src), _address(dst), int(nframes)))
 
     def pump(self, lut: DeviceLut, fd_in: int, fd_out: int, frames_per_batch: int = 0, cancel=None, on_frames=None) -> dict:
         """Stream raw frames from ``fd_in`` through the stage into ``fd_out`` until end of file (lutr_stage_pump: reader thread,
@@ -213,7 +213,7 @@ class ColourStage:
         stats = N.PumpStats()
         cb = N.PROGRESS_FN((lambda user, total: on_frames(int(total))) if on_frames else (lambda user, total: None))
         flag = cancel if cancel is not None else ctypes.c_int32(0)
-        N.check(N.lib().lutr_stage_pump(self._h, lut._h, int(fd_in), int(fd_out), int(frames_per_batch), byref(flag), cb, None, byref(stats)))
+        N.check(N.lib().lutr_stage_pump(self._h, (lut._h if lut is not None else None), int(fd_in), int(fd_out), int(frames_per_batch), byref(flag), cb, None, byref(stats)))
         return {"frames_in": stats.frames_in, "frames_out": stats.frames_out, "bytes_in": stats.bytes_in, "bytes_out": stats.bytes_out,
                 "seconds": stats.seconds}
 

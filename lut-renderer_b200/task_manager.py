@@ -37,10 +37,13 @@ class TaskCallbacks:
 class TaskRunner:
     def __init__(self, task: Task, ffmpeg_bin: str = "ffmpeg", device: int = 0, callbacks: Optional[TaskCallbacks] = None,
                  frames_per_batch: int = 0, popen: Callable = subprocess.Popen, probe: Callable = probe_video,
-                 devices: Optional[List[int]] = None):
+                 devices: Optional[List[int]] = None, gpu_stage2: bool = False):
         self.task, self.ffmpeg_bin, self.device = task, ffmpeg_bin, device
         # more than one entry: every LUT stage of the task is cut into GOP-aligned frame ranges, one per listed GPU
         self.devices = list(devices) if devices else [device]
+        # pro mode stage 2 has no LUT and by default stays the reference's single ffmpeg command; with gpu_stage2 its pixel-format
+        # conversion (yuv422p10le master -> yuv420p / yuv420p10le / yuv422p) runs on the GPU stage between a decoder and an encoder
+        self.gpu_stage2 = gpu_stage2
         self.signals = callbacks or TaskCallbacks()
         self.frames_per_batch = max(0, frames_per_batch)   # 0 = the library picks ~64 MB batches
         self._popen, self._probe = popen, probe
@@ -127,7 +130,14 @@ class TaskRunner:
 
     def _run_stage(self, stage: CommandStage, info: Optional[VideoInfo], base: int, span: int, final: bool) -> Optional[bool]:
         if not stage.lut_path:
-            return self._run_plain(stage, info, base, span, final)
+            gpu = None
+            if self.gpu_stage2:
+                try:
+                    gpu = build_gpu_stage(stage, info, self.ffmpeg_bin, convert_without_lut=True)
+                except RawPipeUnsupported:
+                    gpu = None
+            if gpu is None:
+                return self._run_plain(stage, info, base, span, final)
         total = int(round(info.duration * info.fps)) if info and info.duration and info.fps else 0
         done_lock = threading.Lock()
         state = {"done": 0, "last": -1}
@@ -145,8 +155,11 @@ class TaskRunner:
             self.signals.progress(self.task.task_id, prog)
 
         try:
-            sharded = build_sharded_gpu_stage(stage, info, self.devices, self.ffmpeg_bin) if len(self.devices) > 1 else None
-            gpu = build_gpu_stage(stage, info, self.ffmpeg_bin) if sharded is None else None
+            if not stage.lut_path:
+                sharded = None     # (gpu: the LUT-less conversion stage built above)
+            else:
+                sharded = build_sharded_gpu_stage(stage, info, self.devices, self.ffmpeg_bin) if len(self.devices) > 1 else None
+                gpu = build_gpu_stage(stage, info, self.ffmpeg_bin) if sharded is None else None
         except RawPipeUnsupported as exc:
             # rawvideo carries no timestamps: this clip keeps the reference's own single-process command (CPU lut3d inside
             # ffmpeg), said out loud in the task log -- never a silent switch
@@ -213,7 +226,7 @@ class TaskRunner:
         Returns (first non-zero exit code of the two processes -- 0 = both fine, None when cancelled --, frames processed)."""
         from .stage import ColourStage  # deferred: loads liblutr.so, fails loudly when it is missing
         colour = ColourStage.from_plan(plan, device=device)
-        lut = colour.ctx.lut_from_cube(plan.lut_path)
+        lut = colour.ctx.lut_from_cube(plan.lut_path) if plan.lut_path else None   # None: LUT-less conversion (interp="none")
         dec = self._spawn(decode_cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, bufsize=0)
         enc = self._spawn(encode_cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, bufsize=0)
         flag = ctypes.c_int32(1 if self._cancelled else 0)

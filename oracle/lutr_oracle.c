@@ -1297,3 +1297,81 @@ ORC_API int orc_stage_any(const OrcLut *l, int interp, int in_fmt, int out_fmt, 
     free(pre);
     return ORC_OK;
 }
+
+/* ---- pro mode stage 2 without a LUT (reference ffmpeg.py:459-471 + :287-310): the encoding ffmpeg converts the yuv422p10le master
+ * to the delivery pix_fmt with an auto-inserted scaler, YUV -> YUV, no RGB in between, same matrix and range on both sides.
+ * PINNED against libswscale 9.1.100 (tests/test_oracle_swscale.py test_convert_422p10_*):
+ *   -> yuv420p    generic scaler: 15-bit samples v << 5; luma (y15 + ff_dither_8x8_128[y & 7][x & 7]) >> 7; chroma through the 8-tap
+ *                 vertical decimation of orc_rgb_to_yuv_any's 8-bit output stage (x86 per-tap truncation, C code on the last row,
+ *                 dither column offset 3 for V)
+ *   -> yuv420p10le  luma unchanged ((v << 5) + 16) >> 5; chroma exact 8-tap vertical, (sum + (1 << 16)) >> 17
+ *   -> yuv422p    swscale's planar copy (same subsampling): every plane min((v + d) >> 2, 255), d = {{1,2},{3,0}}[y & 1][x & 1]
+ * Returns ORC_OK or -1 for an output layout that is not modelled. */
+ORC_API int orc_convert_yuv422p10(int out_fmt, const uint16_t *Y, const uint16_t *U, const uint16_t *V, void *Yo, void *Uo, void *Vo,
+                                  int w, int h)
+{
+    static const int d2[2][2] = {{1, 2}, {3, 0}};
+    const int cw = w / 2;
+    if (out_fmt == ORC_PIX_YUV422P) {
+        const uint16_t *src[3] = {Y, U, V};
+        uint8_t *dst[3] = {(uint8_t *)Yo, (uint8_t *)Uo, (uint8_t *)Vo};
+        for (int p = 0; p < 3; p++) {
+            const int pw = p ? cw : w;
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < pw; x++) {
+                    const int r = (src[p][(size_t)y * pw + x] + d2[y & 1][x & 1]) >> 2;
+                    dst[p][(size_t)y * pw + x] = (uint8_t)(r > 255 ? 255 : r);
+                }
+        }
+        return ORC_OK;
+    }
+    if (out_fmt != ORC_PIX_YUV420P && out_fmt != ORC_PIX_YUV420P10)
+        return -1;
+    const int od = out_fmt == ORC_PIX_YUV420P ? 8 : 10, ch = h / 2;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const int y15 = Y[(size_t)y * w + x] << 5;
+            if (od == 8)
+                ((uint8_t *)Yo)[(size_t)y * w + x] = (uint8_t)clip_u((y15 + k_dither_8x8_128[y & 7][x & 7]) >> 7, 255);
+            else
+                ((uint16_t *)Yo)[(size_t)y * w + x] = (uint16_t)clip_u((y15 + 16) >> 5, 1023);
+        }
+    for (int j = 0; j < ch; j++) {
+        int rows[8], coef[8], n = 0;
+        for (int k = 0; k < 8; k++) { /* fold taps whose source row lies outside the frame onto the edge row */
+            const int row = clampi(2 * j - 3 + k, 0, h - 1);
+            if (n && rows[n - 1] == row)
+                coef[n - 1] += k_v420_taps[k];
+            else
+                rows[n] = row, coef[n] = k_v420_taps[k], n++;
+        }
+        for (int p = 1; p < 3; p++) {
+            const uint16_t *C = p == 1 ? U : V;
+            for (int i = 0; i < cw; i++) {
+                int o;
+                if (od == 10) {
+                    int64_t s = 1 << 16;
+                    for (int k = 0; k < n; k++)
+                        s += (int64_t)(C[(size_t)rows[k] * cw + i] << 5) * coef[k];
+                    o = clip_u((int)(s >> 17), 1023);
+                    ((uint16_t *)(p == 1 ? Uo : Vo))[(size_t)j * cw + i] = (uint16_t)o;
+                    continue;
+                }
+                const int d = k_dither_8x8_128[j & 7][(i + (p == 2 ? 3 : 0)) & 7];
+                if (j == ch - 1) {
+                    int s = d << 12;
+                    for (int k = 0; k < n; k++)
+                        s += (C[(size_t)rows[k] * cw + i] << 5) * coef[k];
+                    o = s >> 19;
+                } else {
+                    int s = (d + 56) >> 4;
+                    for (int k = 0; k < n; k++)
+                        s += ((C[(size_t)rows[k] * cw + i] << 5) * coef[k]) >> 16;
+                    o = s >> 3;
+                }
+                ((uint8_t *)(p == 1 ? Uo : Vo))[(size_t)j * cw + i] = (uint8_t)clip_u(o, 255);
+            }
+        }
+    }
+    return ORC_OK;
+}

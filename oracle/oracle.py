@@ -305,3 +305,16 @@ def stage_any(lut, in_fmt, out_fmt, Y, U, V, interp="tetrahedral", range_pass=Fa
     if r:
         raise RuntimeError(f"orc_stage_any: {r}")
     return out
+
+
+def convert_yuv422p10(out_fmt, Y, U, V):
+    """Pro mode stage 2 without a LUT: yuv422p10le -> yuv420p / yuv420p10le / yuv422p as the encoding ffmpeg's auto-inserted scaler
+    converts it (YUV -> YUV, same matrix and range; orc_convert_yuv422p10)."""
+    h, w = Y.shape
+    shapes, dt = pix_geometry(out_fmt, w, h)
+    out = [np.empty(s, dt) for s in shapes]
+    Y, U, V = (np.ascontiguousarray(p, dtype=np.uint16) for p in (Y, U, V))
+    r = lib().orc_convert_yuv422p10(PIX_ID[out_fmt], _p(Y), _p(U), _p(V), _p(out[0]), _p(out[1]), _p(out[2]), w, h)
+    if r:
+        raise RuntimeError(f"orc_convert_yuv422p10: {out_fmt} is not modelled")
+    return out

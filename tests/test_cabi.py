@@ -76,7 +76,7 @@ def test_unsupported_requests_are_named_before_touching_the_device():
     assert e.value.status == N.ERR_UNSUPPORTED
     # every layout / interp of the operator maps to an enum of include/lutr.h
     assert set(N.PIX_FMT) == {"yuv420p", "yuv422p", "yuv444p", "yuv420p10le", "yuv422p10le", "yuv444p10le"}
-    assert set(N.INTERP) == {"nearest", "trilinear", "tetrahedral", "pyramid", "prism"}
+    assert set(N.INTERP) == {"nearest", "trilinear", "tetrahedral", "pyramid", "prism", "none"}   # none: LUT-less pro stage 2 conversion
 
 
 def test_header_is_plain_c_and_links(tmp_path):

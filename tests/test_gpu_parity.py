@@ -687,3 +687,42 @@ def test_yuv444p10_source_to_master(w, h, options, interp, lut_name, kw):
     for i, f in enumerate(frames):
         exp = oracle_stage("yuv444p10le", w, h, f, L, interp=interp, out_pix_fmt="yuv422p10le", **kw)
         assert_bit_exact("yuv422p10le", w, h, got[i], exp, f"444p10->422p10 {w}x{h} {options} {interp} {lut_name} frame {i}")
+
+
+@pytest.mark.parametrize("out_fmt", ["yuv420p", "yuv420p10le", "yuv422p"])
+@pytest.mark.parametrize("w,h", [(16, 14), (72, 16), (264, 40), (1920, 36), (3840, 2160)])
+def test_convert_master_without_lut(out_fmt, w, h):
+    """Pro mode stage 2 (reference ffmpeg.py:459-471): the yuv422p10le master to the delivery pix_fmt without a LUT -- interp="none",
+    lut=None -- bit-exact against the oracle's restatement of the encoding ffmpeg's swscale pass (itself pinned to libswscale):
+    dithered luma, 8-tap vertical chroma decimation with folded edge rows and the exact last row, several frames."""
+    import torch
+    from lut_renderer_b200.stage import ColourStage
+    from oracle import oracle as O
+    frames = _frames("yuv422p10le", w, h, ["noise", "natural", "extremes"] if w < 3000 else ["noise"])
+    st = ColourStage(w, h, "yuv422p10le", out_pix_fmt=out_fmt, interp="none")
+    src = torch.from_numpy(np.concatenate(frames)).cuda()
+    dst = torch.zeros(len(frames) * st.out_frame_bytes, dtype=torch.uint8, device="cuda")
+    st.run(None, src, dst, len(frames), stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert st.kernel_name == "k_convert" and st.launch_count == 1
+    out = dst.cpu().numpy()
+    for i, f in enumerate(frames):
+        Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(f, "yuv422p10le", w, h)]
+        exp = synth.pack_planes(O.convert_yuv422p10(out_fmt, Y, U, V))
+        assert_bit_exact(out_fmt, w, h, out[i * st.out_frame_bytes:(i + 1) * st.out_frame_bytes], exp, f"convert -> {out_fmt} {w}x{h} frame {i}")
+    # host path of the same stage (what the runner's pump calls)
+    pin_in, pin_out = st.ctx.pinned_buffer(len(frames) * st.in_frame_bytes), st.ctx.pinned_buffer(len(frames) * st.out_frame_bytes)
+    pin_in.array[:] = np.concatenate(frames)
+    st.run_host(None, pin_in, pin_out, len(frames))
+    assert np.array_equal(pin_out.array, out)
+    pin_in.close(), pin_out.close(), st.close()
+
+
+def test_convert_stage_rejects_what_it_does_not_model():
+    from lut_renderer_b200 import _native as N
+    from lut_renderer_b200.stage import ColourStage
+    for kw in (dict(pix_fmt="yuv420p10le", out_pix_fmt="yuv420p"), dict(pix_fmt="yuv422p10le", out_pix_fmt="yuv444p"),
+               dict(pix_fmt="yuv422p10le", out_pix_fmt="yuv420p", out_matrix="bt601"), dict(pix_fmt="yuv422p10le", out_pix_fmt="yuv420p", out_range="pc")):
+        with pytest.raises(N.LutrError) as e:
+            ColourStage(256, 16, interp="none", **kw)
+        assert e.value.status == N.ERR_UNSUPPORTED

@@ -265,3 +265,22 @@ def test_any_10bit_full_range_prepass(fmt, w, h):
         ref = S.SwsConverter(8192, 16, fmt, dst_fmt, src_range=1, dst_range=0).convert([ramp, ramp, ramp], S.alloc_planes(dst_fmt, 8192, 16))
         for plane in range(3):
             assert np.array_equal(O.prepass_10_to_8(1, plane, ramp), ref[plane])
+
+
+@pytest.mark.parametrize("out_fmt", ["yuv420p", "yuv420p10le", "yuv422p"])
+@pytest.mark.parametrize("w,h", [(256, 32), (72, 16), (1920, 36), (3840, 18)])
+def test_convert_422p10_without_lut_matches_swscale(out_fmt, w, h):
+    """Pro mode stage 2 (reference ffmpeg.py:459-471): no LUT, the encoding ffmpeg converts the yuv422p10le master to the delivery
+    pix_fmt with an auto-inserted scaler (YUV -> YUV, bicubic flags, same matrix and range).  orc_convert_yuv422p10 is bit-exact
+    against the real libswscale on full-code-range noise, on extreme values and on a flat frame (edge rows, last chroma row)."""
+    rng = np.random.default_rng(7 * w + h)
+    shapes, _ = O.pix_geometry("yuv422p10le", w, h)
+    cases = [[rng.integers(0, 1024, s, dtype=np.uint16) for s in shapes],
+             [rng.choice(np.array([0, 1, 511, 512, 1022, 1023], np.uint16), s) for s in shapes],
+             [np.full(s, v, np.uint16) for s, v in zip(shapes, (940, 64, 960))]]
+    conv = S.SwsConverter(w, h, "yuv422p10le", out_fmt)
+    for k, P in enumerate(cases):
+        ref = conv.convert(P, S.alloc_planes(out_fmt, w, h))
+        got = O.convert_yuv422p10(out_fmt, *P)
+        for plane in range(3):
+            assert np.array_equal(got[plane], ref[plane]), (out_fmt, w, h, k, plane)
