@@ -643,9 +643,17 @@ enum { ORC_INTERP_NEAREST = 0, ORC_INTERP_TRILINEAR = 1, ORC_INTERP_TETRAHEDRAL 
 #define NEXT(x, l) ((int)(x) + 1 < (l)->size - 1 ? (int)(x) + 1 : (l)->size - 1)
 #define NEAR(x) ((int)((x) + .5))
 
+/* Float evaluation order of the blend.  0 = the C code (one rounding per multiply and per add: what packed rgb24 always gets).
+ * 1 = contracted multiply-adds in the same operand order, the first product of a sum plain: the shape of the AVX2 + FMA3 assembly
+ * upstream installs for planar formats on x86-64 (libavfilter/x86/vf_lut3d.asm, fmaddps) -- restated from memory, unverifiable here.
+ * Set once before use (orc_set_float_mode); pyramid / prism / nearest have no assembly and ignore it. */
+static int g_float_mode = 0;
+ORC_API void orc_set_float_mode(int mode) { g_float_mode = mode ? 1 : 0; }
+ORC_API int orc_get_float_mode(void) { return g_float_mode; }
+
 static inline float lerpf(float v0, float v1, float f)
 {
-    return v0 + (v1 - v0) * f;
+    return g_float_mode ? fmaf(v1 - v0, f, v0) : v0 + (v1 - v0) * f;
 }
 
 static inline rgbvec lerp(const rgbvec *v0, const rgbvec *v1, float f)
@@ -679,6 +687,12 @@ static inline rgbvec tetra_blend(float w0, const rgbvec *c000, float w1, const r
                                  float w3, const rgbvec *c111)
 {
     rgbvec c;
+    if (g_float_mode) {
+        c.r = fmaf(w3, c111->r, fmaf(w2, cB->r, fmaf(w1, cA->r, w0 * c000->r)));
+        c.g = fmaf(w3, c111->g, fmaf(w2, cB->g, fmaf(w1, cA->g, w0 * c000->g)));
+        c.b = fmaf(w3, c111->b, fmaf(w2, cB->b, fmaf(w1, cA->b, w0 * c000->b)));
+        return c;
+    }
     c.r = w0 * c000->r + w1 * cA->r + w2 * cB->r + w3 * c111->r;
     c.g = w0 * c000->g + w1 * cA->g + w2 * cB->g + w3 * c111->g;
     c.b = w0 * c000->b + w1 * cA->b + w2 * cB->b + w3 * c111->b;

@@ -318,3 +318,8 @@ def convert_yuv422p10(out_fmt, Y, U, V):
     if r:
         raise RuntimeError(f"orc_convert_yuv422p10: {out_fmt} is not modelled")
     return out
+
+
+def set_float_mode(mode: str) -> None:
+    """"c" (default) or "fma": evaluation order of the trilinear / tetrahedral blend (see orc_set_float_mode).  Process-wide."""
+    lib().orc_set_float_mode(1 if mode == "fma" else 0)
