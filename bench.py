@@ -510,8 +510,12 @@ def main():
             first = src[:stage.in_frame_bytes].cpu().numpy()
             L_or = O.OracleLut.from_table(table)
             Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(first, cfg["pix_fmt"], cfg["w"], cfg["h"])]
-            exp = O.stage_any(L_or, cfg["pix_fmt"], cfg.get("out_pix_fmt", cfg["pix_fmt"]), Y, U, V, interp=cfg["interp"],
-                              range_pass=cfg["in_range"] == "pc" and cfg["norm_range"] == "tv")
+            O.set_float_mode(args.float_mode)   # the oracle evaluates the blend in the same order as the stage was asked to
+            try:
+                exp = O.stage_any(L_or, cfg["pix_fmt"], cfg.get("out_pix_fmt", cfg["pix_fmt"]), Y, U, V, interp=cfg["interp"],
+                                  range_pass=cfg["in_range"] == "pc" and cfg["norm_range"] == "tv")
+            finally:
+                O.set_float_mode("c")
             parity = "bit-exact" if np.array_equal(got, synth.pack_planes(exp)) else "MISMATCH"
             # north_star's statement per plane: share of identical samples, max and mean absolute error (in code values)
             out_fmt = cfg.get("out_pix_fmt") or cfg["pix_fmt"]

@@ -34,7 +34,11 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+LAST_BUILD = {"nvcc_commands": 0}   # what the most recent build() call actually ran
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    LAST_BUILD["nvcc_commands"] = 0
     if not force and not needs_build():
         return OUT
     objdir = os.path.join(HERE, "build")
@@ -58,6 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc_path(), "-c", "-o", obj] + common + [os.path.join(CSRC, src)]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        LAST_BUILD["nvcc_commands"] += 1
     failed = False
     for src, _, p in procs:
         out, _ = p.communicate()
@@ -70,6 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building liblutr.so")
     cmd = [nvcc_path(), "-shared", "-o", OUT, "-gencode", GENCODE, "-cudart", "static"] + [obj for _, obj, _ in procs]
     res = subprocess.run(cmd, capture_output=True, text=True)
+    LAST_BUILD["nvcc_commands"] += 1
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed linking liblutr.so")

@@ -17,18 +17,23 @@ constexpr bool kRowLocal = kOutSide != 0;  // no vertical chroma filter on the o
 using KernelFn = void (*)(const StageK);
 
 template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int NK, int MINB>
-KernelFn pick_range420(bool range, bool in422) {
+KernelFn pick_range420(int rmode, bool in422) {  // rmode: 0 tv throughout, 1 pc -> tv pass in front, 2 full-range output (8-bit outputs)
+    if constexpr (kOutSide != 1) {
+        if (rmode == 2)
+            return in422 ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, 2, kOutSide, true, MINB>
+                         : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, 2, kOutSide, false, MINB>;
+    }
     if (in422)
-        return range ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, true, kOutSide, true, MINB>
-                     : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, false, kOutSide, true, MINB>;
-    return range ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, true, kOutSide, false, MINB>
-                 : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, false, kOutSide, false, MINB>;
+        return rmode == 1 ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, 1, kOutSide, true, MINB>
+                          : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, 0, kOutSide, true, MINB>;
+    return rmode == 1 ? k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, 1, kOutSide, false, MINB>
+                      : k420_warp<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, NK, 0, kOutSide, false, MINB>;
 }
 
 // Window widths of 128 / 192 / 256 columns (NK = 2 / 3 / 4) and the 33-point specialisation exist for the default semantics
 // with the folded index only (C float order, LUT inside [0,1], size-1 a power of two); everything else runs NK = 4, generic size.
 template <int INTERP, int MINB>
-KernelFn pick420(bool fma, bool clamp, bool fold_nomin, bool range, bool in422, int n, int nk) {
+KernelFn pick420(bool fma, bool clamp, bool fold_nomin, int range, bool in422, int n, int nk) {
     if (!fma && !clamp && fold_nomin) {
         if constexpr (kOutSide == 0) {
             if (n == 33) {
@@ -86,8 +91,9 @@ int launch_k420_warp(const StageK &k_in, bool in422, int interp, int float_mode,
     }
     if (!best_nk) return LUTR_ERR_UNSUPPORTED;  // row narrower than the narrowest window: the caller uses the band kernel
     k.tiles_per_row = (k.w + 64 * best_nk - 1) / (64 * best_nk);
-    KernelFn fn = interp == LUTR_INTERP_TRILINEAR ? pick420<LUTR_INTERP_TRILINEAR, 2>(fma, clamp, fold_nomin, k.range_pass != 0, in422, k.lut.n, best_nk)
-                                                  : pick420<LUTR_INTERP_TETRAHEDRAL, 3>(fma, clamp, fold_nomin, k.range_pass != 0, in422, k.lut.n, best_nk);
+    const int rmode = k.range_pass ? 1 : (k.any.out_full ? 2 : 0);
+    KernelFn fn = interp == LUTR_INTERP_TRILINEAR ? pick420<LUTR_INTERP_TRILINEAR, 2>(fma, clamp, fold_nomin, rmode, in422, k.lut.n, best_nk)
+                                                  : pick420<LUTR_INTERP_TETRAHEDRAL, 3>(fma, clamp, fold_nomin, rmode, in422, k.lut.n, best_nk);
     fn<<<(unsigned)best_grid, kWarps420 * 32, 0, (cudaStream_t)stream>>>(k);
     return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
 }

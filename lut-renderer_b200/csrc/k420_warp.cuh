@@ -41,10 +41,12 @@ __device__ __forceinline__ int pc2tv_c(int v) { return __vimin_s32_relu(((((v <<
 
 // OUT: 0 = yuv420p, 1 = yuv422p10le, 2 = yuv422p, 3 = yuv444p (the last three are row-local: no vertical filter, no halo rows)
 // IN422: the source is yuv422p (one chroma row per luma row) instead of yuv420p; same SIMD-path arithmetic (chroma replicated)
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int NK, bool RANGE, int OUT, bool IN422, int MINB>
+// RMODE: 0 = limited range throughout, 1 = 8-bit pc -> tv pass in front (BASELINE cfg 2), 2 = full-range source kept full range and
+// FULL-RANGE OUTPUT (tags = inherit / none on a pc source, reference ffmpeg.py:216-223; 8-bit outputs only)
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, int NK, int RMODE, int OUT, bool IN422, int MINB>
 __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K) {
     constexpr int W = 64 * NK, CW = W / 2;  // luma / chroma columns per window
-    constexpr bool ROWLOCAL = OUT != 0, OUT10 = OUT == 1;
+    constexpr bool ROWLOCAL = OUT != 0, OUT10 = OUT == 1, RANGE = RMODE == 1;
     // per warp: (2*u14 | 2*v14 << 16) of the last 8 luma rows, and one staged input row (W luma + CW + CW chroma bytes)
     __shared__ __align__(16) unsigned s_ring[kWarps420][ROWLOCAL ? 1 : 8][CW];  // unused for the row-local outputs
     __shared__ __align__(16) unsigned char s_in[kWarps420][2 * W];
@@ -66,6 +68,18 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
     // yuv444p: per-pixel chroma, rounding (256 << 14) + (1 << 8), one float bias per channel, output rounding (32 << 9)
     const unsigned kU444 = (unsigned)((256 << 14) + (1 << 8) + (32 << 9)) - kMagic * (unsigned)(b.ru + b.gu + b.bu);
     const unsigned kV444 = (unsigned)((256 << 14) + (1 << 8) + (32 << 9)) - kMagic * (unsigned)(b.rv + b.gv + b.bv);
+    // Full-range OUTPUT: swscale converts the 15-bit luma / chroma values before its output stage, min((v * coeff + offset) >> 14,
+    // 32767) with the 8-bit constants (the result can be NEGATIVE for chroma below the limited range: signed 16-bit fields in the
+    // ring).  The limited-range instantiations keep their folded constants, the full-range ones spell the steps out.
+    constexpr bool out_full = !OUT10 && RMODE == 2;
+    const int lc = K.any.out_lc, lo = K.any.out_lo, cc = K.any.out_cc, co = K.any.out_co;
+    auto range15 = [](int v, int coeff, int offset) { return min((v * coeff + offset) >> 14, 32767); };
+    // 15-bit luma of the full-range path: 2 * y14, y14 = (S + (32 << 14) + (1 << 8)) >> 9 (fk.kY carries a further 32 << 9)
+    auto luma_full = [&](unsigned sy) {
+        const int y15 = 2 * ((int)(sy + fk.kY - (32u << 9)) >> 9);
+        return (unsigned)__vimin_s32_relu((range15(y15, lc, lo) + 64) >> 7, 255);
+    };
+    auto chroma_full8 = [&](int c15) { return (unsigned)__vimin_s32_relu((range15(c15, cc, co) + 64) >> 7, 255); };
     // staging loads: NK == 2: every lane brings 4 luma + 2 + 2 chroma bytes; NK == 3, 4: the first W / 8 lanes bring 8 + 4 + 4
     constexpr int YB = NK == 2 ? 4 : 8, CB = YB / 2;
     using YLoad = typename std::conditional<NK == 2, unsigned, uint2>::type;
@@ -169,11 +183,17 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
                         // 8-bit row-local outputs: luma as for yuv420p; chroma clip8((2*c14 + 64) >> 7) with
                         //   yuv422p: c14 = S_pair >> 10 (rgb24ToUV_half)  ==  (S_pair + kU + (32 << 10)) >> 16
                         //   yuv444p: c14 = S_pixel >> 9 (rgb24ToUV)       ==  (S_pixel + kU444 + (32 << 9)) >> 15
-                        const unsigned yq0 = (unsigned)((int)(sy0 + fk.kY) >> 15), yq1 = (unsigned)((int)(sy1 + fk.kY) >> 15);
+                        const unsigned yq0 = out_full ? luma_full(sy0) : (unsigned)((int)(sy0 + fk.kY) >> 15);
+                        const unsigned yq1 = out_full ? luma_full(sy1) : (unsigned)((int)(sy1 + fk.kY) >> 15);
                         stg_u16(oY + 64 * kk, yq0 | (yq1 << 8));
                         if (OUT == 2) {
-                            stg_u8(oU + 32 * kk, (unsigned)__vimin_s32_relu((int)(su + fk.kU + (32u << 10)) >> 16, 255));
-                            stg_u8(oV + 32 * kk, (unsigned)__vimin_s32_relu((int)(sv + fk.kV + (32u << 10)) >> 16, 255));
+                            if (out_full) {
+                                stg_u8(oU + 32 * kk, chroma_full8(2 * ((int)(su + fk.kU) >> 10)));
+                                stg_u8(oV + 32 * kk, chroma_full8(2 * ((int)(sv + fk.kV) >> 10)));
+                            } else {
+                                stg_u8(oU + 32 * kk, (unsigned)__vimin_s32_relu((int)(su + fk.kU + (32u << 10)) >> 16, 255));
+                                stg_u8(oV + 32 * kk, (unsigned)__vimin_s32_relu((int)(sv + fk.kV + (32u << 10)) >> 16, 255));
+                            }
                         } else {
                             // per-pixel sums carry ONE 0x4B000000 bias per channel: half of the pair constants' bias term
                             const unsigned kU1 = kU444, kV1 = kV444;
@@ -182,18 +202,25 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
                             for (int p = 0; p < 2; ++p) {
                                 const unsigned s1u = (unsigned)b.ru * ro[p] + (unsigned)b.gu * go[p] + (unsigned)b.bu * bo[p];
                                 const unsigned s1v = (unsigned)b.rv * ro[p] + (unsigned)b.gv * go[p] + (unsigned)b.bv * bo[p];
-                                uq[p] = (unsigned)__vimin_s32_relu((int)(s1u + kU1) >> 15, 255);
-                                vq[p] = (unsigned)__vimin_s32_relu((int)(s1v + kV1) >> 15, 255);
+                                if (out_full) {  // c15 = 2 * c14, c14 = (S + (256 << 14) + (1 << 8)) >> 9
+                                    uq[p] = chroma_full8(2 * ((int)(s1u + kU1 - (32u << 9)) >> 9));
+                                    vq[p] = chroma_full8(2 * ((int)(s1v + kV1 - (32u << 9)) >> 9));
+                                } else {
+                                    uq[p] = (unsigned)__vimin_s32_relu((int)(s1u + kU1) >> 15, 255);
+                                    vq[p] = (unsigned)__vimin_s32_relu((int)(s1v + kV1) >> 15, 255);
+                                }
                             }
                             stg_u16(oU + 64 * kk, uq[0] | (uq[1] << 8));
                             stg_u16(oV + 64 * kk, vq[0] | (vq[1] << 8));
                         }
                     } else {
                         // rgb24ToY: clip8((2*y14 + 64) >> 7), y14 = S >> 9  ==  (S + (32 << 9)) >> 15; no clip can bind (host-checked)
-                        const unsigned yq0 = (unsigned)((int)(sy0 + fk.kY) >> 15), yq1 = (unsigned)((int)(sy1 + fk.kY) >> 15);
+                        const unsigned yq0 = out_full ? luma_full(sy0) : (unsigned)((int)(sy0 + fk.kY) >> 15);
+                        const unsigned yq1 = out_full ? luma_full(sy1) : (unsigned)((int)(sy1 + fk.kY) >> 15);
                         if (own_row) stg_u16(oY + 64 * kk, yq0 | (yq1 << 8));
-                        const unsigned u14 = (unsigned)((int)(su + fk.kU) >> 10), v14 = (unsigned)((int)(sv + fk.kV) >> 10);
-                        ring[y & 7][32 * kk + lane] = ((2u * v14) << 16) + 2u * u14;
+                        unsigned u15 = 2u * (unsigned)((int)(su + fk.kU) >> 10), v15 = 2u * (unsigned)((int)(sv + fk.kV) >> 10);
+                        if (out_full) u15 = (unsigned)range15((int)u15, cc, co) & 0xFFFFu, v15 = (unsigned)range15((int)v15, cc, co);
+                        ring[y & 7][32 * kk + lane] = (v15 << 16) + u15;
                     }
                 }
                 if (ROWLOCAL) oU += K.p.out_stride[1], oV += K.p.out_stride[2];
@@ -216,8 +243,8 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
                         const unsigned qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            au[c] += __mulhi((int)(qq[c] & 0xFFFF), taps[k] << 16);
-                            av[c] += __mulhi((int)(qq[c] >> 16), taps[k] << 16);
+                            au[c] += __mulhi(out_full ? (int)(short)(qq[c] & 0xFFFF) : (int)(qq[c] & 0xFFFF), taps[k] << 16);
+                            av[c] += __mulhi(out_full ? (int)qq[c] >> 16 : (int)(qq[c] >> 16), taps[k] << 16);
                         }
                     }
                 } else {
@@ -233,7 +260,8 @@ __global__ void __launch_bounds__(kWarps420 * 32, MINB) k420_warp(const StageK K
                             const unsigned qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                const int cu = (int)(qq[c] & 0xFFFF), cv = (int)(qq[c] >> 16);
+                                const int cu = out_full ? (int)(short)(qq[c] & 0xFFFF) : (int)(qq[c] & 0xFFFF);
+                                const int cv = out_full ? (int)qq[c] >> 16 : (int)(qq[c] >> 16);
                                 if (exact) au[c] += cu * fold, av[c] += cv * fold;
                                 else au[c] += (cu * fold) >> 16, av[c] += (cv * fold) >> 16;
                             }

@@ -27,7 +27,7 @@ namespace {
 // pass A is unchanged (u17 = (C - 512) * 128 == 4 * (C << 5) - 65536, the same expression pass B applies to the 15-bit value).
 // VAR: bit 0 = chroma upsample in exact packed float arithmetic, bit 1 = RGB->YUV chroma terms scaled so that one PRMT packs them,
 // bit 2 = packed 16-bit clip of the decimated chroma (all bit-exact re-formulations; the flags exist to measure each one)
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR, bool IN444, int BM = LUTR_BMODE, int VAR = 7>
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR, bool IN444, int BM = LUTR_BMODE, int VAR = 7, int TEXV = 0>
 __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
     __shared__ __align__(16) unsigned s_all[kWarps][kWin + kWin / 2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lane_odd = lane ^ 4;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                     mb[p] = clip30_to_magic(Bv);
                 }
                 unsigned ro[2], go[2], bo[2];
-                lut3d_pair<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, PK, PK ? BM : 0>(LC, tab, mr, mg, mb, ro, go, bo);
+                lut3d_pair<INTERP, FMA, CLAMP, IDX, NOMIN, NSZ, PK, PK ? BM : 0, TEXV>(LC, tab, mr, mg, mb, ro, go, bo);
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
                     const int j = 32 * (kk + p) + lane;
@@ -336,6 +336,8 @@ int launch_k422_warp(const StageK &k, bool in444, int interp, int float_mode, vo
     if (k.wk_var == 100 * B + V) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, B, V>;
         WK_CASE(0, 0) WK_CASE(0, 7) WK_CASE(1, 0) WK_CASE(1, 7) WK_CASE(2, 7) WK_CASE(1, 1) WK_CASE(1, 3) WK_CASE(1, 5)
 #undef WK_CASE
+        if (k.wk_var == 2001 && k.lut.tex) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, 1, 7, 1>;  // c111 through TEX
+        if (k.wk_var == 2002 && k.lut.tex) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, 1, 7, 2>;  // + second step
     }
 #endif
     if (!fn) {

@@ -44,6 +44,7 @@ struct lutr_lut {
     float4 *dev = nullptr;   // size^3 nodes + tail padding
     size_t dev_bytes = 0;
     bool needs_clamp = false;  // some entry lies outside [0,1]: the truncating store needs its clip
+    mutable cudaTextureObject_t tex = 0;  // experiment builds (wk_var 2001 / 2002): the table as a point-sampled linear texture
 };
 
 // device copy of one index table; depends on (bit depth, LUT size, domain scale) only, never overwritten once built
@@ -224,6 +225,17 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     k.lut.in_scale = 1.0f / maxv;
     k.lut.sr = lut->scale[0] * lut_max, k.lut.sg = lut->scale[1] * lut_max, k.lut.sb = lut->scale[2] * lut_max;
     k.lut.out_scale = (float)maxv;
+#ifdef LUTR_WK_EXPERIMENTS
+    if (s->wk_var >= 2000 && !lut->tex) {  // texture-path experiment: same memory, fetched by element index
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = lut->dev, rd.res.linear.desc = cudaCreateChannelDesc<float4>(), rd.res.linear.sizeInBytes = lut->dev_bytes;
+        cudaTextureDesc td{};
+        td.filterMode = cudaFilterModePoint, td.readMode = cudaReadModeElementType, td.addressMode[0] = cudaAddressModeClamp;
+        if (cudaCreateTextureObject(&lut->tex, &rd, &td, nullptr) != cudaSuccess) lut->tex = 0, cudaGetLastError();
+    }
+    k.lut.tex = (unsigned long long)lut->tex;
+#endif
     for (int p = 0; p < 3; ++p) {
         k.p.in[p] = (const uint8_t *)in->data[p], k.p.out[p] = (uint8_t *)out->data[p];
         k.p.in_stride[p] = in->stride[p], k.p.out_stride[p] = out->stride[p];
@@ -290,6 +302,10 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         }
     }
     k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : k.min_blocks * s->ctx->sm_count;
+    // output range conversion constants (full-range outputs of the 8-bit warp-window kernels and of the generic kernel)
+    k.any.out_full = s->d.out_range == LUTR_RANGE_PC ? 1 : 0;
+    range_coeffs(pix_depth(s->d.out_fmt), true, false, &k.any.out_lc, &k.any.out_lo);
+    range_coeffs(pix_depth(s->d.out_fmt), true, true, &k.any.out_cc, &k.any.out_co);
     // generic tile kernel: combinations without a specialised kernel, and specialised combinations whose fast path does not apply
     // (per-channel LUT domain scales, interp=nearest on the master stages, rows narrower than a window)
     auto run_any = [&]() {
@@ -649,7 +665,9 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
     // (the warp-window kernels work on 8-column groups with 16-byte accesses: widths that are not a multiple of 8, e.g. 854x480,
     // take the generic kernel)
     const bool master444 = d.in_fmt == LUTR_PIX_YUV444P10LE && d.out_fmt == LUTR_PIX_YUV422P10LE && tri_tet;  // ProRes 4444 -> master
-    const bool specialised = !pre10 && d.out_range == LUTR_RANGE_TV && d.interp <= LUTR_INTERP_TETRAHEDRAL && (d.width % 8) == 0 &&
+    // full-range output: the 8-bit warp-window kernels carry it as a run-time switch (8-bit source, 8-bit output); elsewhere generic
+    const bool pc_out_ok = d.out_range == LUTR_RANGE_TV || (in8 && pix_depth(d.out_fmt) == 8 && d.norm_range == LUTR_RANGE_PC);
+    const bool specialised = !pre10 && pc_out_ok && d.interp <= LUTR_INTERP_TETRAHEDRAL && (d.width % 8) == 0 &&
                              (same_fmt || to_master || ordered10 || master444);
     CUDA_TRY(cudaSetDevice(ctx->device));
     lutr_stage *s = new (std::nothrow) lutr_stage;

@@ -44,6 +44,7 @@ struct LutK {
     float in_scale;     // 1.0f / (2^depth - 1)
     float sr, sg, sb;   // scale.c * lut_max
     float out_scale;    // (float)(2^depth - 1)
+    unsigned long long tex;  // experiment builds: cudaTextureObject_t over `tab` (linear, point sampling), 0 otherwise
 };
 
 struct PlaneSet {

@@ -204,6 +204,7 @@ struct LutC {
     float idx_mul, idx_add, idx_sr, lut_max, out_scale, one;
     unsigned kbase;  // -0x4B000000 * (n*n + n + 1): removes the float bias of the three node indices (wrapping arithmetic)
     int n, n2;
+    unsigned long long tex;  // experiments: the same table as a point-sampled linear texture (0 = none)
 };
 
 __device__ __forceinline__ LutC make_lutc(const StageK &K) {
@@ -212,6 +213,7 @@ __device__ __forceinline__ LutC make_lutc(const StageK &K) {
     C.lut_max = K.lut.lut_max, C.out_scale = K.lut.out_scale, C.one = K.wk_one;
     C.n = K.lut.n, C.n2 = K.lut.n2;
     C.kbase = 0u - kMagic * (unsigned)(C.n2 + C.n + 1);
+    C.tex = K.lut.tex;
     return C;
 }
 
@@ -223,7 +225,9 @@ __device__ __forceinline__ LutC make_lutc(const StageK &K) {
 #ifndef LUTR_BMODE
 #define LUTR_BMODE 1
 #endif
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int BM = (PK ? LUTR_BMODE : 0)>
+// TEXV (experiment): that many of the four tetrahedron vertices (c111, then the second step) are fetched through the texture unit
+// (tex1Dfetch on the same table: exact texels, address arithmetic and data return on the TEX path instead of the LSU path).
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int BM = (PK ? LUTR_BMODE : 0), int TEXV = 0>
 __device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, const unsigned mr[2],
                                            const unsigned mg[2], const unsigned mb[2], unsigned ro[2], unsigned go[2], unsigned bo[2]) {
     const int N = NSZ ? NSZ : C.n, N2 = NSZ ? NSZ * NSZ : C.n2;
@@ -309,7 +313,9 @@ __device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, con
             const int o1 = (ar == mx[p]) ? N2 : ((ag == mx[p]) ? N : 1);
             const int oB = (ab == mn[p]) ? N2 + N : ((ag == mn[p]) ? N2 + 1 : N + 1);
             const float4 *p0 = tab + base;
-            v0[p] = __ldg(p0), vA[p] = __ldg(p0 + o1), vB[p] = __ldg(p0 + oB), v1[p] = __ldg(p0 + (N2 + N + 1));
+            v0[p] = __ldg(p0), vA[p] = __ldg(p0 + o1);
+            vB[p] = TEXV >= 2 ? tex1Dfetch<float4>((cudaTextureObject_t)C.tex, (int)base + oB) : __ldg(p0 + oB);
+            v1[p] = TEXV >= 1 ? tex1Dfetch<float4>((cudaTextureObject_t)C.tex, (int)base + (N2 + N + 1)) : __ldg(p0 + (N2 + N + 1));
         }
         // weights of both pixels as pairs: (1 - d1), (d1 - d2), (d2 - d3), d3
         const f2 d1 = f2{__int_as_float(mx[0]), __int_as_float(mx[1])}, d2 = f2{__int_as_float(md[0]), __int_as_float(md[1])};

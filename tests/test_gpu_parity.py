@@ -739,3 +739,33 @@ def test_convert_stage_rejects_what_it_does_not_model():
         with pytest.raises(N.LutrError) as e:
             ColourStage(256, 16, interp="none", **kw)
         assert e.value.status == N.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("in_fmt,out_fmt,kernel", [("yuv420p", "yuv420p", "k420_warp"), ("yuv420p", "yuv422p", "k420_warp422"),
+                                                   ("yuv420p", "yuv444p", "k420_warp444"), ("yuv422p", "yuv420p", "k420_warp<422>"),
+                                                   ("yuv422p", "yuv422p", "k420_warp422<422>")])
+@pytest.mark.parametrize("interp,norm_range", [("tetrahedral", "pc"), ("trilinear", "pc"), ("tetrahedral", "tv")])
+def test_full_range_output_on_the_8bit_warp_kernels(in_fmt, out_fmt, kernel, interp, norm_range):
+    """tags = inherit / none on a full-range source (reference ffmpeg.py:216-223): the stage output is full range.  The 8-bit
+    warp-window kernels carry swscale's 15-bit range conversion as a run-time switch instead of handing the stage to the generic
+    kernel; several rows per share, window edges, the last chroma row."""
+    import torch
+    from lut_renderer_b200.stage import ColourStage
+    w, h = 328, 38
+    table = LUTS["look33"]().astype(np.float32)
+    frames = _frames(in_fmt, w, h, ["natural", "noise", "extremes"])
+    kw = dict(in_range="pc", norm_range=norm_range, out_range="pc", out_matrix="bt601")
+    st = ColourStage(w, h, in_fmt, out_pix_fmt=out_fmt, interp=interp, **kw)
+    lut = st.ctx.lut_from_table(table)
+    src = torch.from_numpy(np.concatenate(frames)).cuda()
+    dst = torch.zeros(len(frames) * st.out_frame_bytes, dtype=torch.uint8, device="cuda")
+    st.run(lut, src, dst, len(frames), stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    # (a pc -> tv pass in front AND a full-range output is outside what the reference's options produce: generic kernel)
+    assert st.kernel_name == (kernel if norm_range == "pc" else "k_any"), st.kernel_name
+    out = dst.cpu().numpy()
+    L = oracle_lut(table)
+    for i, f in enumerate(frames):
+        exp = oracle_stage(in_fmt, w, h, f, L, interp=interp, out_pix_fmt=out_fmt, **kw)
+        assert_bit_exact(out_fmt, w, h, out[i * st.out_frame_bytes:(i + 1) * st.out_frame_bytes], exp, f"pc out {in_fmt}->{out_fmt} {interp} frame {i}")
+    st.close(), lut.close()
