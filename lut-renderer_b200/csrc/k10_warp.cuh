@@ -112,31 +112,9 @@ __global__ void __launch_bounds__(kW10 * 32, MINB) k10_warp(const StageK K) {
                 if (xc == 0) ul = (cu2.x & 0xFFFFu) * 0x10001u, vl = (cv2.x & 0xFFFFu) * 0x10001u;
                 if (xc == w - 8) ur = (cu2.y >> 16) * 0x10001u, vr = (cv2.y >> 16) * 0x10001u;
             }
-            const int eu[8] = {(int)(ul & 0xFFFF),    (int)(ul >> 16),    (int)(cu2.x & 0xFFFF), (int)(cu2.x >> 16),
-                               (int)(cu2.y & 0xFFFF), (int)(cu2.y >> 16), (int)(ur & 0xFFFF),    (int)(ur >> 16)};
-            const int ev[8] = {(int)(vl & 0xFFFF),    (int)(vl >> 16),    (int)(cv2.x & 0xFFFF), (int)(cv2.x >> 16),
-                               (int)(cv2.y & 0xFFFF), (int)(cv2.y >> 16), (int)(vr & 0xFFFF),    (int)(vr >> 16)};
-            constexpr int kB9 = kCBias << 9, kTop = 32767 + kCBias;
+            const unsigned wu[4] = {ul, cu2.x, cu2.y, ur}, wvv[4] = {vl, cv2.x, cv2.y, vr};
             unsigned wv[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int j = k >> 1;
-                int tu, tv;
-                if (!(k & 1)) {
-                    tu = -461 * eu[j] + 3943 * eu[j + 1] + 14284 * eu[j + 2] - 1382 * eu[j + 3] + kB9;
-                    tv = -461 * ev[j] + 3943 * ev[j + 1] + 14284 * ev[j + 2] - 1382 * ev[j + 3] + kB9;
-                } else {
-                    tu = -1382 * eu[j + 1] + 14284 * eu[j + 2] + 3943 * eu[j + 3] - 461 * eu[j + 4] + kB9;
-                    tv = -1382 * ev[j + 1] + 14284 * ev[j + 2] + 3943 * ev[j + 3] - 461 * ev[j + 4] + kB9;
-                }
-                if (k == 0 || k == 2) {
-                    if (edge_tile && xc == 0) {
-                        if (k == 0) tu = 17729 * eu[2] - 1345 * eu[3] + kB9, tv = 17729 * ev[2] - 1345 * ev[3] + kB9;
-                        if (k == 2) tu = 3835 * eu[2] + 13894 * eu[3] - 1345 * eu[4] + kB9, tv = 3835 * ev[2] + 13894 * ev[3] - 1345 * ev[4] + kB9;
-                    }
-                }
-                wv[k] = __vminu2((unsigned)(tv >> 9) * 65536u + (unsigned)(tu >> 9), (unsigned)kTop * 0x10001u);
-            }
+            chroma_up8<0>(wu, wvv, edge_tile && xc == 0, wv);  // exact float filter (warp_common.cuh)
             unsigned *dst = ring + (crow & (NR - 1)) * kWin;
             *reinterpret_cast<uint4 *>(dst + 4 * swz_chunk(2 * lane)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             *reinterpret_cast<uint4 *>(dst + 4 * swz_chunk(2 * lane + 1)) = make_uint4(wv[4], wv[5], wv[6], wv[7]);
@@ -238,9 +216,10 @@ __global__ void __launch_bounds__(kW10 * 32, MINB) k10_warp(const StageK K) {
                     // 10 bit: clip10((min(2*y14, 32767) + 16) >> 5) with y14 = (S - (8 << 11)) >> 11  ==  S >> 15 (no clip binds, host-checked)
                     // 8 bit:  clip8((2*y14 + d) >> 7), d = ordered dither
                     const unsigned yq = OUT8 ? (unsigned)__vimin_s32_relu((2 * ((sy >> 11) - 8) + dY) >> 7, 255) : (unsigned)(sy >> 15);
-                    const unsigned u14 = (unsigned)((int)((unsigned)b.ru * ro[p] + (unsigned)b.gu * go[p] + (unsigned)b.bu * bo[p] + fk.kU) >> 11);
-                    const unsigned v14 = (unsigned)((int)((unsigned)b.rv * ro[p] + (unsigned)b.gv * go[p] + (unsigned)b.bv * bo[p] + fk.kV) >> 11);
-                    sC[32 * (kk + p) + (p ? lane_odd : lane)] = (v14 << 16) + u14;
+                    // u14 = S >> 11 == (32 * S) >> 16: matrix rows pre-scaled by 32 on the host, one PRMT packs (u14 | v14 << 16)
+                    const unsigned su5 = fk.cu5[0] * ro[p] + fk.cu5[1] * go[p] + fk.cu5[2] * bo[p] + fk.kU5;
+                    const unsigned sv5 = fk.cv5[0] * ro[p] + fk.cv5[1] * go[p] + fk.cv5[2] * bo[p] + fk.kV5;
+                    sC[32 * (kk + p) + (p ? lane_odd : lane)] = __byte_perm(su5, sv5, 0x7632u);
                     sY[jc] = (unsigned short)yq;
                 }
             }

@@ -203,38 +203,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_tma(const StageK K) {
                         wv[k] = __byte_perm(wu[1 + (k >> 2)], wvv[1 + (k >> 2)], sel);
                     }
                 } else {
-                    // The 4-tap filter in float: on centred samples (C - 512) every partial sum is an integer below 2^24 in magnitude
-                    // (sum |tap| * 512 = 10.3 M), and so are the sums of the taps pre-scaled by 2^-9 in units of 2^-9 -- exact in fp32.
-                    // One packed instruction per tap filters U and V together.  T >> 9 = floor(Tc / 512) + 16384: adding
-                    // 1.5 * 2^23 + 16384 + kCBias rounding toward -inf leaves the biased 15-bit value in the low 16 mantissa bits.
-                    f2 f[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const unsigned sel = (k & 1) ? 0x7632u : 0x7610u;  // bytes (sample, 0x00, 0x4B): the float 2^23 + C
-                        f[k] = add2s<true>(f2{__uint_as_float(__byte_perm(wu[k >> 1], kMagic, sel)),
-                                              __uint_as_float(__byte_perm(wvv[k >> 1], kMagic, sel))}, -(8388608.f + 512.f));
-                    }
-                    constexpr float q = 1.f / 512.f, kMagicRm = 12582912.f + 16384.f + (float)kCBias;
-                    constexpr int kTop = 32767 + kCBias;
-                    const bool left = ws < 0 && lane == 0;  // this lane holds row columns 0 and 2 (window columns 4 and 6)
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int j = k >> 1;
-                        f2 acc;
-                        if (!(k & 1)) {  // even column 2i: taps on C[i-2 .. i+1]
-                            acc = mul2s<true>(f[j], -461.f * q), acc = fma2ss<true>(f[j + 1], 3943.f * q, acc);
-                            acc = fma2ss<true>(f[j + 2], 14284.f * q, acc), acc = fma2ss<true>(f[j + 3], -1382.f * q, acc);
-                        } else {         // odd column 2i+1: taps on C[i-1 .. i+2]
-                            acc = mul2s<true>(f[j + 1], -1382.f * q), acc = fma2ss<true>(f[j + 2], 14284.f * q, acc);
-                            acc = fma2ss<true>(f[j + 3], 3943.f * q, acc), acc = fma2ss<true>(f[j + 4], -461.f * q, acc);
-                        }
-                        if ((k == 4 || k == 6) && left) {  // the two left-most even columns of a row use swscale's edge-normalised taps
-                            if (k == 4) acc = fma2ss<true>(f[j + 3], -1345.f * q, mul2s<true>(f[j + 2], 17729.f * q));
-                            if (k == 6) acc = fma2ss<true>(f[j + 3], -1345.f * q, fma2ss<true>(f[j + 2], 13894.f * q, mul2s<true>(f[j + 1], 3835.f * q)));
-                        }
-                        const f2 r = addrm2s(acc, kMagicRm);
-                        wv[k] = __vminu2(__byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x5410u), (unsigned)kTop * 0x10001u);
-                    }
+                    chroma_up8<4>(wu, wvv, ws < 0 && lane == 0, wv);  // lane 0 of the row's first window holds row columns 0 and 2 as its columns 4 and 6
                 }
                 __syncwarp();  // pass C of the previous row has finished reading sC
                 *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);

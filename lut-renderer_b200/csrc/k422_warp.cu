@@ -25,9 +25,7 @@ namespace {
 
 // IN444: the source is yuv444p10le (ProRes 4444 and the like): one chroma sample per pixel, no upsampling filter; everything behind
 // pass A is unchanged (u17 = (C - 512) * 128 == 4 * (C << 5) - 65536, the same expression pass B applies to the 15-bit value).
-// VAR: bit 0 = chroma upsample in exact packed float arithmetic, bit 1 = RGB->YUV chroma terms scaled so that one PRMT packs them,
-// bit 2 = packed 16-bit clip of the decimated chroma (all bit-exact re-formulations; the flags exist to measure each one)
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR, bool IN444, int BM = LUTR_BMODE, int VAR = 7, int TEXV = 0>
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR, bool IN444, int BM = LUTR_BMODE, int TEXV = 0>
 __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
     __shared__ __align__(16) unsigned s_all[kWarps][kWin + kWin / 2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lane_odd = lane ^ 4;
@@ -54,15 +52,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
     C.kG = fk.kG - (unsigned)kCBias * fk.vg4 - (unsigned)kCBias * fk.ug4;
     C.kB = fk.kB - (unsigned)kCBias * fk.ub4;
     C.ry = (unsigned)b.ry, C.gy = (unsigned)b.gy, C.by = (unsigned)b.by;
-    // VAR bit 1: u14 = S >> 11 == (32 * S) >> 16 (0 <= 32 * S < 2^31 for 10-bit RGB), so the two 15-bit terms are the high halves of
-    // two registers and one PRMT builds the packed word pass C reads (coefficients pre-scaled on the host)
-    if (VAR & 2) {
-        C.ru = fk.cu5[0], C.gu = fk.cu5[1], C.bu = fk.cu5[2], C.rv = fk.cv5[0], C.gv = fk.cv5[1], C.bv = fk.cv5[2];
-        C.kU = fk.kU5, C.kV = fk.kV5;
-    } else {
-        C.ru = (unsigned)b.ru, C.gu = (unsigned)b.gu, C.bu = (unsigned)b.bu, C.rv = (unsigned)b.rv, C.gv = (unsigned)b.gv, C.bv = (unsigned)b.bv;
-        C.kU = fk.kU, C.kV = fk.kV;
-    }
+    // u14 = S >> 11 == (32 * S) >> 16 (0 <= 32 * S < 2^31 for 10-bit RGB): the chroma rows of the matrix come pre-scaled by 32 from the
+    // host, the two 15-bit terms are then the high halves of two registers and one PRMT builds the packed word pass C reads
+    C.ru = fk.cu5[0], C.gu = fk.cu5[1], C.bu = fk.cu5[2], C.rv = fk.cv5[0], C.gv = fk.cv5[1], C.bv = fk.cv5[2];
+    C.kU = fk.kU5, C.kV = fk.kV5;
     C.kY = fk.kY;
     const float4 *tab = K.lut.tab;
 
@@ -128,69 +121,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                     if (xc == 0) ul = (cu2.x & 0xFFFFu) * 0x10001u, vl = (cv2.x & 0xFFFFu) * 0x10001u;
                     if (xc == w - 8) ur = (cu2.y >> 16) * 0x10001u, vr = (cv2.y >> 16) * 0x10001u;
                 }
-                // chroma window e[0..7] = C[i0-2 .. i0+5]
-                const int eu[8] = {(int)(ul & 0xFFFF),    (int)(ul >> 16),    (int)(cu2.x & 0xFFFF), (int)(cu2.x >> 16),
-                                   (int)(cu2.y & 0xFFFF), (int)(cu2.y >> 16), (int)(ur & 0xFFFF),    (int)(ur >> 16)};
-                const int ev[8] = {(int)(vl & 0xFFFF),    (int)(vl >> 16),    (int)(cv2.x & 0xFFFF), (int)(cv2.x >> 16),
-                                   (int)(cv2.y & 0xFFFF), (int)(cv2.y >> 16), (int)(vr & 0xFFFF),    (int)(vr >> 16)};
-                constexpr int kB9 = kCBias << 9, kTop = 32767 + kCBias;
+                // chroma window C[i0-2 .. i0+5] as packed pairs; exact float filter (chroma_up8, warp_common.cuh)
+                const unsigned wu[4] = {ul, cu2.x, cu2.y, ur}, wvv[4] = {vl, cv2.x, cv2.y, vr};
                 unsigned wv[8];
-                if (VAR & 1) {
-                    // The 4-tap filter in float: on centred samples (C - 512) every partial sum is an integer below 2^24 in magnitude
-                    // (sum |tap| * 512 = 10.3 M), and so are the sums of the taps pre-scaled by 2^-9 in units of 2^-9 -- exact in fp32.
-                    // One packed instruction per tap filters U and V together.  T >> 9 = floor(Tc / 512) + 16384: adding
-                    // 1.5 * 2^23 + 16384 + kCBias rounding toward -inf leaves the biased 15-bit value in the low 16 mantissa bits.
-                    const unsigned wu[4] = {ul, cu2.x, cu2.y, ur}, wvv[4] = {vl, cv2.x, cv2.y, vr};
-                    f2 f[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const unsigned sel = (k & 1) ? 0x7632u : 0x7610u;  // bytes (sample, 0x00, 0x4B): the float 2^23 + C
-                        f[k] = add2s<true>(f2{__uint_as_float(__byte_perm(wu[k >> 1], kMagic, sel)),
-                                              __uint_as_float(__byte_perm(wvv[k >> 1], kMagic, sel))}, -(8388608.f + 512.f));
-                    }
-                    constexpr float q = 1.f / 512.f, kMagicRm = 12582912.f + 16384.f + (float)kCBias;
-                    const bool left = edge_tile && xc == 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int j = k >> 1;
-                        f2 acc;
-                        if (!(k & 1)) {
-                            acc = mul2s<true>(f[j], -461.f * q), acc = fma2ss<true>(f[j + 1], 3943.f * q, acc);
-                            acc = fma2ss<true>(f[j + 2], 14284.f * q, acc), acc = fma2ss<true>(f[j + 3], -1382.f * q, acc);
-                        } else {
-                            acc = mul2s<true>(f[j + 1], -1382.f * q), acc = fma2ss<true>(f[j + 2], 14284.f * q, acc);
-                            acc = fma2ss<true>(f[j + 3], 3943.f * q, acc), acc = fma2ss<true>(f[j + 4], -461.f * q, acc);
-                        }
-                        if ((k == 0 || k == 2) && left) {  // the two left-most even columns of a row use swscale's edge-normalised taps
-                            if (k == 0) acc = fma2ss<true>(f[3], -1345.f * q, mul2s<true>(f[2], 17729.f * q));
-                            if (k == 2) acc = fma2ss<true>(f[4], -1345.f * q, fma2ss<true>(f[3], 13894.f * q, mul2s<true>(f[2], 3835.f * q)));
-                        }
-                        const f2 r = addrm2s(acc, kMagicRm);
-                        wv[k] = __vminu2(__byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x5410u), (unsigned)kTop * 0x10001u);
-                    }
-                } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int j = k >> 1;
-                    int tu, tv;
-                    if (!(k & 1)) {  // even column 2i: taps on C[i-2 .. i+1]
-                        tu = -461 * eu[j] + 3943 * eu[j + 1] + 14284 * eu[j + 2] - 1382 * eu[j + 3] + kB9;
-                        tv = -461 * ev[j] + 3943 * ev[j + 1] + 14284 * ev[j + 2] - 1382 * ev[j + 3] + kB9;
-                    } else {  // odd column 2i+1: taps on C[i-1 .. i+2]
-                        tu = -1382 * eu[j + 1] + 14284 * eu[j + 2] + 3943 * eu[j + 3] - 461 * eu[j + 4] + kB9;
-                        tv = -1382 * ev[j + 1] + 14284 * ev[j + 2] + 3943 * ev[j + 3] - 461 * ev[j + 4] + kB9;
-                    }
-                    if (k == 0 || k == 2) {
-                        if (edge_tile && xc == 0) {  // the two left-most even columns of a row use swscale's edge-normalised taps
-                            if (k == 0) tu = 17729 * eu[2] - 1345 * eu[3] + kB9, tv = 17729 * ev[2] - 1345 * ev[3] + kB9;
-                            if (k == 2) tu = 3835 * eu[2] + 13894 * eu[3] - 1345 * eu[4] + kB9, tv = 3835 * ev[2] + 13894 * ev[3] - 1345 * ev[4] + kB9;
-                        }
-                    }
-                    // c15 = min(T >> 9, 32767), stored + 4096 (so it is never negative).  Both fit 16 bits even before the min
-                    // (10-bit samples: 0 <= (T >> 9) + 4096 < 40600), so pack first and clip both halves with one instruction.
-                    wv[k] = __vminu2((unsigned)(tv >> 9) * 65536u + (unsigned)(tu >> 9), (unsigned)kTop * 0x10001u);
-                }
-                }
+                chroma_up8<0>(wu, wvv, edge_tile && xc == 0, wv);
                 __syncwarp();  // pass C of the previous row has finished reading sC
                 *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
                 *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane + 1)) = make_uint4(wv[4], wv[5], wv[6], wv[7]);
@@ -226,8 +160,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                     const unsigned yq = (unsigned)((int)(C.ry * ro[p] + C.gy * go[p] + C.by * bo[p] + C.kY) >> 15);
                     const unsigned su = C.ru * ro[p] + C.gu * go[p] + C.bu * bo[p] + C.kU, sv = C.rv * ro[p] + C.gv * go[p] + C.bv * bo[p] + C.kV;
                     // (v14 << 16) + u14 with u14 = S >> 11;  the same lane read this slot above: in place
-                    sC[32 * (kk + p) + (p ? lane_odd : lane)] = (VAR & 2) ? __byte_perm(su, sv, 0x7632u)
-                                                                         : ((unsigned)((int)sv >> 11) << 16) + (unsigned)((int)su >> 11);
+                    sC[32 * (kk + p) + (p ? lane_odd : lane)] = __byte_perm(su, sv, 0x7632u);
                     sY[j] = (unsigned short)yq;  // in place as well; pass C stores the window's own columns 16 bytes per lane
                 }
             }
@@ -252,7 +185,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                     const uint4 v4 = *reinterpret_cast<const uint4 *>(sC + 4 * swz_chunk(2 * lane + 1 + q));
                     tt[4 * q] = v4.x, tt[4 * q + 1] = v4.y, tt[4 * q + 2] = v4.z, tt[4 * q + 3] = v4.w;
                 }
-                unsigned uo[2] = {0u, 0u}, vo[2] = {0u, 0u};
+                unsigned uo[2], vo[2];
                 int dus[4], dvs[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -264,19 +197,12 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                     const unsigned e = 0u - 230u * s0 - 692u * s1 + 1972u * s2 + 7142u * s3 + (16u << 13);
                     const int du = (int)(e - 65536u * (unsigned)dv);
                     // clip10((min(S >> 13, 32767) + 16) >> 5) == clamp((S + (16 << 13)) >> 18, 0, 1023)
-                    if (VAR & 4) {
-                        dus[j] = du >> 18, dvs[j] = (dv + (16 << 13)) >> 18;  // |.| < 2^13: they fit the halves of one register
-                    } else {
-                        uo[j >> 1] |= (unsigned)__vimin_s32_relu(du >> 18, 1023) << (16 * (j & 1));
-                        vo[j >> 1] |= (unsigned)__vimin_s32_relu((dv + (16 << 13)) >> 18, 1023) << (16 * (j & 1));
-                    }
+                    dus[j] = du >> 18, dvs[j] = (dv + (16 << 13)) >> 18;  // |.| < 2^13: they fit the halves of one register
                 }
-                if (VAR & 4) {
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {  // pack two samples, then clamp both halves to [0, 1023] with one instruction
-                        uo[q] = __vimin_s16x2_relu(__byte_perm((unsigned)dus[2 * q], (unsigned)dus[2 * q + 1], 0x5410u), 0x03FF03FFu);
-                        vo[q] = __vimin_s16x2_relu(__byte_perm((unsigned)dvs[2 * q], (unsigned)dvs[2 * q + 1], 0x5410u), 0x03FF03FFu);
-                    }
+                for (int q = 0; q < 2; ++q) {  // pack two samples, then clamp both halves to [0, 1023] with one instruction
+                    uo[q] = __vimin_s16x2_relu(__byte_perm((unsigned)dus[2 * q], (unsigned)dus[2 * q + 1], 0x5410u), 0x03FF03FFu);
+                    vo[q] = __vimin_s16x2_relu(__byte_perm((unsigned)dvs[2 * q], (unsigned)dvs[2 * q + 1], 0x5410u), 0x03FF03FFu);
                 }
                 stg_s16(oY, *reinterpret_cast<const uint4 *>(sYw + 4 * lane + 4));  // luma of columns a+8+8*lane .. +7
                 stg_s8(oU, make_uint2(uo[0], uo[1]));
@@ -330,14 +256,14 @@ int launch_k422_warp(const StageK &k, bool in444, int interp, int float_mode, vo
     const bool fold_nomin = k.fk.idx_fold && k.wk_nomin;
     KernelFn fn = nullptr;
 #ifdef LUTR_WK_EXPERIMENTS
-    // variants of the headline configuration, selected by the stage option wk_var = 100 * BM + VAR (blend mode, reformulation flags)
+    // variants of the headline configuration, selected by the stage option wk_var = 100 * BM (blend mode) / 2001, 2002 (texture path)
     if (interp == LUTR_INTERP_TETRAHEDRAL && !fma && !clamp && fold_nomin && k.lut.n == 65 && !in444 && k.wk_var >= 0) {
-#define WK_CASE(B, V) \
-    if (k.wk_var == 100 * B + V) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, B, V>;
-        WK_CASE(0, 0) WK_CASE(0, 7) WK_CASE(1, 0) WK_CASE(1, 7) WK_CASE(2, 7) WK_CASE(1, 1) WK_CASE(1, 3) WK_CASE(1, 5)
+#define WK_CASE(B) \
+    if (k.wk_var == 100 * B) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, B>;
+        WK_CASE(0) WK_CASE(1) WK_CASE(2)
 #undef WK_CASE
-        if (k.wk_var == 2001 && k.lut.tex) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, 1, 7, 1>;  // c111 through TEX
-        if (k.wk_var == 2002 && k.lut.tex) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, 1, 7, 2>;  // + second step
+        if (k.wk_var == 2001 && k.lut.tex) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, 1, 1>;  // c111 through TEX
+        if (k.wk_var == 2002 && k.lut.tex) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, 1, 2>;  // + second step
     }
 #endif
     if (!fn) {

@@ -323,7 +323,6 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         s->last_kernel = "k_any";
         return launch_k_any(k, s->d.interp, s->d.float_mode, st);
     };
-    const bool mixed = s->d.in_fmt != s->d.out_fmt;
     if (s->any_only || s->force_any) {
         rc = run_any();
     } else if (s->depth == 10 && s->d.out_fmt == LUTR_PIX_YUV420P) {

@@ -172,6 +172,45 @@ __device__ __forceinline__ f2 fma2ss(f2 a, float b, f2 c) {  // fma(a, b, c), b 
     return r;
 }
 
+// swscale's 4-tap horizontal chroma upsample (yuv422p10le / yuv420p10le -> planar RGB: hcscale with bicubic taps in Q14) for the 8
+// luma columns 2*i0 .. 2*i0 + 7 of one lane, U and V together.  wu / wvv: the chroma samples C[i0-2 .. i0+5] as packed pairs.
+// Result wv[k] = (cu | cv << 16) with c = min(T >> 9, 32767) + kCBias.
+// The filter runs in float: on centred samples (C - 512) every partial sum is an integer below 2^24 in magnitude (sum |tap| * 512 =
+// 10.3 M), and so are the sums of the taps pre-scaled by 2^-9 in units of 2^-9 -- exact in fp32, whatever the order.  One packed
+// instruction per tap filters U and V together (4 FFMA2 instead of 8 IMAD per column).  T >> 9 = floor(Tc / 512) + 16384: adding
+// 1.5 * 2^23 + 16384 + kCBias rounding toward -inf leaves the biased 15-bit value in the low 16 mantissa bits.
+// left: this lane's columns K0 and K0 + 2 are the row's columns 0 and 2, which take swscale's edge-normalised taps.
+template <int K0>
+__device__ __forceinline__ void chroma_up8(const unsigned wu[4], const unsigned wvv[4], bool left, unsigned wv[8]) {
+    f2 f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned sel = (k & 1) ? 0x7632u : 0x7610u;  // bytes (sample, 0x00, 0x4B): the float 2^23 + C
+        f[k] = add2s<true>(f2{__uint_as_float(__byte_perm(wu[k >> 1], kMagic, sel)), __uint_as_float(__byte_perm(wvv[k >> 1], kMagic, sel))},
+                           -(8388608.f + 512.f));
+    }
+    constexpr float q = 1.f / 512.f, kMagicRm = 12582912.f + 16384.f + (float)kCBias;
+    constexpr int kTop = 32767 + kCBias;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int j = k >> 1;
+        f2 acc;
+        if (!(k & 1)) {  // even column 2i: taps on C[i-2 .. i+1]
+            acc = mul2s<true>(f[j], -461.f * q), acc = fma2ss<true>(f[j + 1], 3943.f * q, acc);
+            acc = fma2ss<true>(f[j + 2], 14284.f * q, acc), acc = fma2ss<true>(f[j + 3], -1382.f * q, acc);
+        } else {         // odd column 2i+1: taps on C[i-1 .. i+2]
+            acc = mul2s<true>(f[j + 1], -1382.f * q), acc = fma2ss<true>(f[j + 2], 14284.f * q, acc);
+            acc = fma2ss<true>(f[j + 3], 3943.f * q, acc), acc = fma2ss<true>(f[j + 4], -461.f * q, acc);
+        }
+        if ((k == K0 || k == K0 + 2) && left) {
+            if (k == K0) acc = fma2ss<true>(f[j + 3], -1345.f * q, mul2s<true>(f[j + 2], 17729.f * q));                                        // column 0
+            else acc = fma2ss<true>(f[j + 3], -1345.f * q, fma2ss<true>(f[j + 2], 13894.f * q, mul2s<true>(f[j + 1], 3835.f * q)));           // column 2
+        }
+        const f2 r = addrm2s(acc, kMagicRm);
+        wv[k] = __vminu2(__byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x5410u), (unsigned)kTop * 0x10001u);
+    }
+}
+
 // prod + acc where prod comes out of a multiply.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even with
 // -fmad=false), which would drop the product's rounding; fma(prod, one, acc) with `one` a run-time 1.0f it cannot see through is
 // the same single-rounding add and cannot be merged with the multiply.
