@@ -16,7 +16,8 @@ for cfg in "$@"; do
   ncu --set full --clock-control none --import-source on --launch-skip 5 -c 1 -k regex:'k422|k420_warp|k10_warp|k_any|k_convert' \
       -o gpurun_out/${tag}_${cfg} -f python bench.py --config $cfgname $extra $B > gpurun_out/${tag}_${cfg}_ncu.log 2>&1
   python tools/ncu_summary.py gpurun_out/${tag}_${cfg}.ncu-rep gpurun_out/${tag}_${cfg}_ncu_full.json $frames > /dev/null
-  python tools/opcode_mix.py gpurun_out/${tag}_${cfg}.ncu-rep $frames > gpurun_out/${tag}_${cfg}_opcode_mix.txt 2>/dev/null
+  case $cfgname in cfg1|cfg2) px=$((frames * 1920 * 1080));; cfg4) px=$((frames * 7680 * 4320));; *) px=$((frames * 3840 * 2160));; esac
+  python tools/opcode_mix.py gpurun_out/${tag}_${cfg}.ncu-rep $px > gpurun_out/${tag}_${cfg}_opcode_mix.txt 2>/dev/null
   # gpurun brings back at most 64 MiB: keep the report of the first config only
   [ "$cfg" = "$1" ] || rm -f gpurun_out/${tag}_${cfg}.ncu-rep
 done
