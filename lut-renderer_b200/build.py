@@ -39,8 +39,6 @@ LAST_BUILD = {"nvcc_commands": 0}   # what the most recent build() call actually
 
 def build(force: bool = False, verbose: bool = False) -> str:
     LAST_BUILD["nvcc_commands"] = 0
-    if not force and not needs_build():
-        return OUT
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     common = [
@@ -58,8 +56,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         common += ["-DLUTR_WK_EXPERIMENTS"]
     # one nvcc per translation unit, in parallel (the template-heavy kernel files dominate the build time)
     procs = []
+    flag_file = os.path.join(objdir, "flags.txt")   # objects are reused only when they were built with the same flags
+    same_flags = os.path.exists(flag_file) and open(flag_file).read() == " ".join(common)
+    if not force and same_flags and not needs_build():
+        return OUT
+    hdr_time = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    objs = []
     for src in SOURCES:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        if not force and same_flags and os.path.exists(obj) and os.path.getmtime(obj) > max(hdr_time, os.path.getmtime(os.path.join(CSRC, src))):
+            continue   # this translation unit is up to date
         cmd = [nvcc_path(), "-c", "-o", obj] + common + [os.path.join(CSRC, src)]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         LAST_BUILD["nvcc_commands"] += 1
@@ -73,7 +80,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc failed building liblutr.so")
-    cmd = [nvcc_path(), "-shared", "-o", OUT, "-gencode", GENCODE, "-cudart", "static"] + [obj for _, obj, _ in procs]
+    with open(flag_file, "w") as f:
+        f.write(" ".join(common))
+    cmd = [nvcc_path(), "-shared", "-o", OUT, "-gencode", GENCODE, "-cudart", "static"] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     LAST_BUILD["nvcc_commands"] += 1
     if res.returncode != 0:
