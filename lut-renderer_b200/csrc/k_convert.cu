@@ -44,6 +44,12 @@ __global__ void __launch_bounds__(128) k_convert_422p10(const StageK K) {
     auto ld16 = [](const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); };
     auto ld8 = [](const uint8_t *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); };
     auto sample = [](const unsigned wd[], int k) { return (int)((wd[k >> 1] >> (16 * (k & 1))) & 0xFFFFu); };
+    // one row of the dither matrix with ONE uniform 8-byte constant load; a per-thread column index into constant memory would be
+    // served address by address.  drow_u / drow_v: the 4 bytes for this thread's chroma columns 4g .. 4g+3 (V shifted by 3 columns)
+    auto drow = [](int y) { return *reinterpret_cast<const uint2 *>(&kDither128[y & 7][0]); };
+    auto dbyte = [](uint2 row, int k) { return (int)(((k < 4 ? row.x : row.y) >> (8 * (k & 3))) & 0xFFu); };
+    auto drow_u = [&](uint2 row) { return (g & 1) ? row.y : row.x; };
+    auto drow_v = [&](uint2 row) { return __byte_perm(row.x, row.y, (g & 1) ? 0x2107u : 0x6543u); };
 
     if (MODE == 2) {  // planar copy: rows of this strip
         const int y0 = blockIdx.y * kStrip;
@@ -68,35 +74,91 @@ __global__ void __launch_bounds__(128) k_convert_422p10(const StageK K) {
     }
 
     const int ch = h >> 1, j0 = blockIdx.y * kStrip;
-    for (int j = j0; j < min(j0 + kStrip, ch); ++j) {
-        // ---- luma rows 2j, 2j + 1 --------------------------------------------------------------------------------------------
+    constexpr int taps[8] = {-58, -172, 492, 1786, 1786, 492, -172, -58};
+    // luma rows 2j, 2j + 1 of this thread's 8 columns
+    auto luma_rows = [&](int j) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int y = 2 * j + r;
             const uint4 yv = ld16(inY + (long)y * K.p.in_stride[0]);
+            const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
             if (MODE == 1) {  // ((v << 5) + 16) >> 5 == v for 10-bit samples; clip of the (invalid) codes above 1023 like the scaler
-                const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
                 unsigned o[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) o[q] = (unsigned)min(sample(yw, 2 * q), 1023) | ((unsigned)min(sample(yw, 2 * q + 1), 1023) << 16);
                 *reinterpret_cast<uint4 *>(outY + (long)y * K.p.out_stride[0]) = make_uint4(o[0], o[1], o[2], o[3]);
             } else {
-                const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
                 unsigned yo[2] = {0u, 0u};
+                const uint2 dr = drow(y);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) yo[k >> 2] |= (unsigned)min(((sample(yw, k) << 5) + kDither128[y & 7][k]) >> 7, 255) << (8 * (k & 3));
+                for (int k = 0; k < 8; ++k) yo[k >> 2] |= (unsigned)min(((sample(yw, k) << 5) + dbyte(dr, k)) >> 7, 255) << (8 * (k & 3));
                 *reinterpret_cast<uint2 *>(outY + (long)y * K.p.out_stride[0]) = make_uint2(yo[0], yo[1]);
             }
         }
+    };
+    // Interior strips (all 8 source rows of every chroma row inside the frame, no last chroma row): a sliding window of the 8 source
+    // rows in registers -- every chroma source row is loaded once per strip (22 row loads for 8 output rows) instead of 8 times.
+    if (j0 + kStrip <= ch - 1 && 2 * j0 - 3 >= 0 && 2 * (j0 + kStrip - 1) + 4 <= h - 1) {
+        uint2 wu[8], wvv[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) wu[t] = ld8(inU + (long)(2 * j0 - 3 + t) * K.p.in_stride[1]), wvv[t] = ld8(inV + (long)(2 * j0 - 3 + t) * K.p.in_stride[2]);
+#pragma unroll
+        for (int jj = 0; jj < kStrip; ++jj) {
+            const int j = j0 + jj;
+            uint2 nu0 = wu[0], nu1 = wu[0], nv0 = wvv[0], nv1 = wvv[0];
+            if (jj + 1 < kStrip) {  // the two rows the next output row adds, in flight while this one is computed
+                nu0 = ld8(inU + (long)(2 * j + 5) * K.p.in_stride[1]), nu1 = ld8(inU + (long)(2 * j + 6) * K.p.in_stride[1]);
+                nv0 = ld8(inV + (long)(2 * j + 5) * K.p.in_stride[2]), nv1 = ld8(inV + (long)(2 * j + 6) * K.p.in_stride[2]);
+            }
+            luma_rows(j);
+            const uint2 dj = drow(j);
+            const unsigned du4 = drow_u(dj), dv4 = drow_v(dj);
+            int su[4], sv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (MODE == 1) su[k] = sv[k] = 1 << 16;
+                else su[k] = (int)(((du4 >> (8 * k)) & 0xFFu) + 56) >> 4, sv[k] = (int)(((dv4 >> (8 * k)) & 0xFFu) + 56) >> 4;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const unsigned uw[2] = {wu[t].x, wu[t].y}, vw[2] = {wvv[t].x, wvv[t].y};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int pu_ = (sample(uw, k) << 5) * taps[t], pv_ = (sample(vw, k) << 5) * taps[t];
+                    if (MODE == 0) su[k] += pu_ >> 16, sv[k] += pv_ >> 16;
+                    else su[k] += pu_, sv[k] += pv_;
+                }
+            }
+            if (MODE == 1) {
+                const unsigned uo0 = (unsigned)clip_hi(su[0] >> 17, 1023) | ((unsigned)clip_hi(su[1] >> 17, 1023) << 16);
+                const unsigned uo1 = (unsigned)clip_hi(su[2] >> 17, 1023) | ((unsigned)clip_hi(su[3] >> 17, 1023) << 16);
+                const unsigned vo0 = (unsigned)clip_hi(sv[0] >> 17, 1023) | ((unsigned)clip_hi(sv[1] >> 17, 1023) << 16);
+                const unsigned vo1 = (unsigned)clip_hi(sv[2] >> 17, 1023) | ((unsigned)clip_hi(sv[3] >> 17, 1023) << 16);
+                *reinterpret_cast<uint2 *>(outU + (long)j * K.p.out_stride[1]) = make_uint2(uo0, uo1);
+                *reinterpret_cast<uint2 *>(outV + (long)j * K.p.out_stride[2]) = make_uint2(vo0, vo1);
+            } else {
+                unsigned uo = 0u, vo = 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) uo |= (unsigned)clip_hi(su[k] >> 3, 255) << (8 * k), vo |= (unsigned)clip_hi(sv[k] >> 3, 255) << (8 * k);
+                *reinterpret_cast<unsigned *>(outU + (long)j * K.p.out_stride[1]) = uo;
+                *reinterpret_cast<unsigned *>(outV + (long)j * K.p.out_stride[2]) = vo;
+            }
+#pragma unroll
+            for (int t = 0; t < 6; ++t) wu[t] = wu[t + 2], wvv[t] = wvv[t + 2];
+            wu[6] = nu0, wu[7] = nu1, wvv[6] = nv0, wvv[7] = nv1;
+        }
+        return;
+    }
+    for (int j = j0; j < min(j0 + kStrip, ch); ++j) {
+        luma_rows(j);
         // ---- chroma row j: luma rows 2j-3 .. 2j+4, taps of rows outside the frame folded onto the edge row ------------------------
-        constexpr int taps[8] = {-58, -172, 492, 1786, 1786, 492, -172, -58};
         int su[4], sv[4];
         const bool last = MODE == 0 && j == ch - 1;  // swscale's C vertical scaler on the last output row: exact accumulation
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (MODE == 1) su[k] = sv[k] = 1 << 16;
             else {
-                const int du = kDither128[j & 7][(4 * g + k) & 7], dv = kDither128[j & 7][(4 * g + k + 3) & 7];
+                const int du = (int)((drow_u(drow(j)) >> (8 * k)) & 0xFFu), dv = (int)((drow_v(drow(j)) >> (8 * k)) & 0xFFu);
                 su[k] = last ? du << 12 : (du + 56) >> 4, sv[k] = last ? dv << 12 : (dv + 56) >> 4;
             }
         }
