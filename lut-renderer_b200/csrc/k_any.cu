@@ -40,11 +40,18 @@ __device__ __forceinline__ int clamp_hi(int v, int hi) { return __vimin_s32_relu
 __device__ __forceinline__ int clip30(int v) { return __vimin_s32_relu(v, 0x3FFFFFFF); }
 __device__ __forceinline__ int range15(int v, int coeff, int offset) { return min((v * coeff + offset) >> 14, 32767); }
 
-__constant__ unsigned char c_dither[8][8] = {
+__constant__ __align__(8) unsigned char c_dither[8][8] = {
     {36, 68, 60, 92, 34, 66, 58, 90},   {100, 4, 124, 28, 98, 2, 122, 26}, {52, 84, 44, 76, 50, 82, 42, 74},
     {116, 20, 108, 12, 114, 18, 106, 10}, {32, 64, 56, 88, 38, 70, 62, 94},  {96, 0, 120, 24, 102, 6, 126, 30},
     {48, 80, 40, 72, 54, 86, 46, 78},   {112, 16, 104, 8, 118, 22, 110, 14},
 };
+
+// ff_dither_8x8_128[row & 7][col & 7].  The row index is (nearly) warp-uniform, the column differs per thread: one 8-byte constant load of
+// the row and a shift, instead of a per-thread index into constant memory (which is served address by address)
+__device__ __forceinline__ int dither128(int row, int col) {
+    const uint2 r = *reinterpret_cast<const uint2 *>(&c_dither[row & 7][0]);
+    return (int)((((col & 4) ? r.y : r.x) >> (8 * (col & 3))) & 0xFFu);
+}
 
 // horizontal 4-tap chroma upsample of a 10-bit 4:2:2 / 4:2:0 chroma row at luma column x (oracle chroma_up_422)
 __device__ __forceinline__ int up422(const uint16_t *C, int cw, int x) {
@@ -67,7 +74,7 @@ __device__ __forceinline__ int up422(const uint16_t *C, int cw, int x) {
 // (`scale=in_range=pc:out_range=R,format=yuv4xxp`, ffmpeg.py:211-233; oracle orc_prepass_10_to_8).  (py, px): position in the plane.
 __device__ __forceinline__ int pre10_sample(int v, int py, int px, int mode, int plane, int coeff, int offset) {
     if (mode == 1)  // generic scaler: 15-bit sample, range conversion, ordered dither (V shifted by 3 columns)
-        return clamp_hi((range15(v << 5, coeff, offset) + c_dither[py & 7][(px + (plane == 2 ? 3 : 0)) & 7]) >> 7, 255);
+        return clamp_hi((range15(v << 5, coeff, offset) + dither128(py, px + (plane == 2 ? 3 : 0))) >> 7, 255);
     const int d = (py & 1) ? ((px & 1) ? 0 : 3) : ((px & 1) ? 2 : 1);  // planar copy, 2x2 dither {{1,2},{3,0}}
     if (plane == 0) return min((v + d - (v >> 8)) >> 2, 255);
     const int t = (v + d) >> 2;
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
                 if (sd == 8) y15 = 2 * ((b.ry * ro[q] + b.gy * go[q] + b.by * bo[q] + (32 << 14) + (1 << 8)) >> 9);
                 else y15 = min(2 * ((b.ry * ro[q] + b.gy * go[q] + b.by * bo[q] + (16 << 17) + (1 << 10)) >> 11), 32767);
                 if (out_full) y15 = range15(y15, K.any.out_lc, K.any.out_lo);
-                const int d = bayer ? c_dither[y & 7][(x + q) & 7] : 64;
+                const int d = bayer ? dither128(y, x + q) : 64;
                 yq[q] = od == 8 ? clamp_hi((y15 + d) >> 7, 255) : clamp_hi((y15 + 16) >> 5, omax);
                 unsigned cu, cv;
                 if (sd == 8) {
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
                 s_h[r][i] = ((unsigned)cu & 0xFFFFu) | ((unsigned)cv << 16);
             } else {
                 const int ci = (X0 >> o_sx) + i;
-                const int du = bayer ? c_dither[y & 7][ci & 7] : 64, dv = bayer ? c_dither[y & 7][(ci + 3) & 7] : 64;
+                const int du = bayer ? dither128(y, ci) : 64, dv = bayer ? dither128(y, ci + 3) : 64;
                 if (od == 8) {
                     outU[(long)y * K.p.out_stride[1] + ci] = (uint8_t)clamp_hi((cu + du) >> 7, 255);
                     outV[(long)y * K.p.out_stride[2] + ci] = (uint8_t)clamp_hi((cv + dv) >> 7, 255);
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
             const int jr = idx / ncol, i = idx - jr * ncol;
             const int j = (Y0 >> 1) + jr, ci = (X0 >> 1) + i;
             const int taps[8] = {-58, -172, 492, 1786, 1786, 492, -172, -58};
-            const int du = bayer ? c_dither[j & 7][ci & 7] : 64, dv = bayer ? c_dither[j & 7][(ci + 3) & 7] : 64;
+            const int du = bayer ? dither128(j, ci) : 64, dv = bayer ? dither128(j, ci + 3) : 64;
             const bool c_path = od == 8 && j == cho - 1;  // swscale's C vertical scaler takes the last 8-bit output row
             int su, sv;
             if (od == 10) su = sv = 1 << 16;

@@ -19,7 +19,7 @@ namespace lutr {
 
 namespace {
 
-__constant__ unsigned char kDither128[8][8] = {
+__constant__ __align__(8) unsigned char kDither128[8][8] = {
     {36, 68, 60, 92, 34, 66, 58, 90},     {100, 4, 124, 28, 98, 2, 122, 26}, {52, 84, 44, 76, 50, 82, 42, 74},
     {116, 20, 108, 12, 114, 18, 106, 10}, {32, 64, 56, 88, 38, 70, 62, 94},  {96, 0, 120, 24, 102, 6, 126, 30},
     {48, 80, 40, 72, 54, 86, 46, 78},     {112, 16, 104, 8, 118, 22, 110, 14},
