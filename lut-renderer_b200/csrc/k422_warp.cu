@@ -25,7 +25,9 @@ namespace {
 
 // IN444: the source is yuv444p10le (ProRes 4444 and the like): one chroma sample per pixel, no upsampling filter; everything behind
 // pass A is unchanged (u17 = (C - 512) * 128 == 4 * (C << 5) - 65536, the same expression pass B applies to the 15-bit value).
-template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR, bool IN444, int BM = LUTR_BMODE, int TEXV = 0>
+// COPY: the memory path alone (same windows, halo loads, register prefetch, shared-memory round trip and 16-byte / 8-byte stores; the
+// arithmetic replaced by moving samples) for the roofline study in DESIGN.md section 6 -- never dispatched by the product path.
+template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR, bool IN444, int BM = LUTR_BMODE, int TEXV = 0, bool COPY = false>
 __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
     __shared__ __align__(16) unsigned s_all[kWarps][kWin + kWin / 2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lane_odd = lane ^ 4;
@@ -124,7 +126,12 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                 // chroma window C[i0-2 .. i0+5] as packed pairs; exact float filter (chroma_up8, warp_common.cuh)
                 const unsigned wu[4] = {ul, cu2.x, cu2.y, ur}, wvv[4] = {vl, cv2.x, cv2.y, vr};
                 unsigned wv[8];
-                chroma_up8<0>(wu, wvv, edge_tile && xc == 0, wv);
+                if (COPY) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) wv[k] = __byte_perm(wu[1 + (k >> 2)], wvv[1 + (k >> 2)], ((k >> 1) & 1) ? 0x7632u : 0x5410u);
+                } else {
+                    chroma_up8<0>(wu, wvv, edge_tile && xc == 0, wv);
+                }
                 __syncwarp();  // pass C of the previous row has finished reading sC
                 *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
                 *reinterpret_cast<uint4 *>(sC + 4 * swz_chunk(2 * lane + 1)) = make_uint4(wv[4], wv[5], wv[6], wv[7]);
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
 
             // ---------------- pass B: one column per lane, columns a + 32*k + lane ---------------------------------------
 #pragma unroll(UNR)
-            for (int kk = 0; kk < 8; kk += 2) {
+            for (int kk = 0; kk < (COPY ? 0 : 8); kk += 2) {
                 unsigned mr[2], mg[2], mb[2];
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                 unsigned uo[2], vo[2];
                 int dus[4], dvs[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < (COPY ? 0 : 4); ++j) {
                     // symmetric taps: add mirrored columns while packed (u and v sums stay below 2^16)
                     const unsigned s0 = tt[2 * j + 1] + tt[2 * j + 8], s1 = tt[2 * j + 2] + tt[2 * j + 7];
                     const unsigned s2 = tt[2 * j + 3] + tt[2 * j + 6], s3 = tt[2 * j + 4] + tt[2 * j + 5];
@@ -201,6 +208,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                 }
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {  // pack two samples, then clamp both halves to [0, 1023] with one instruction
+                    if (COPY) {
+                        uo[q] = __byte_perm(tt[4 * q + 4], tt[4 * q + 6], 0x5410u), vo[q] = __byte_perm(tt[4 * q + 4], tt[4 * q + 6], 0x7632u);
+                        continue;
+                    }
                     uo[q] = __vimin_s16x2_relu(__byte_perm((unsigned)dus[2 * q], (unsigned)dus[2 * q + 1], 0x5410u), 0x03FF03FFu);
                     vo[q] = __vimin_s16x2_relu(__byte_perm((unsigned)dvs[2 * q], (unsigned)dvs[2 * q + 1], 0x5410u), 0x03FF03FFu);
                 }
@@ -266,6 +277,7 @@ int launch_k422_warp(const StageK &k, bool in444, int interp, int float_mode, vo
         if (k.wk_var == 2002 && k.lut.tex) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, 1, 2>;  // + second step
     }
 #endif
+    if (k.wk_var == 1004 && !in444) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, LUTR_BMODE, 0, true>;  // memory path only
     if (!fn) {
         // tetrahedral: two columns per step, all four steps unrolled (8 gathers in flight); trilinear has 16 gathers per step
         fn = interp == LUTR_INTERP_TRILINEAR ? pick_sem<LUTR_INTERP_TRILINEAR, true, 2, 1>(fma, clamp, fold_nomin, k.lut.n, in444)
