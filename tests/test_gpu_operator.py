@@ -249,3 +249,67 @@ def test_task_runner_cancel_and_encoder_failure(tmp_path):
     assert events[-1] == ("finished", "canceled") and dt < 60, (events[-3:], dt)
     events, dt = run(dies)
     assert events[-1] == ("finished", "failed") and any(e[0] == "status" and e[1].startswith("failed") for e in events) and dt < 60, events[-3:]
+
+
+def test_pro_pipeline_with_gpu_stage2(tmp_path):
+    """Pro mode end to end through the runner with gpu_stage2: stage 1 = LUT + yuv422p10le master (reference ffmpeg.py:417-433,
+    436-458), stage 2 = the master converted to the delivery pix_fmt WITHOUT a LUT (ffmpeg.py:459-471) -- both through the GPU
+    stage between stand-in decoder / encoder processes.  The delivered bytes are the oracle's for the two steps chained, the master
+    is deleted afterwards (cleanup_on_success), progress is split 50 / 50."""
+    import subprocess
+    import sys
+    from lut_renderer_b200 import Task
+    from lut_renderer_b200.task_manager import TaskCallbacks, TaskRunner
+    from oracle import oracle as O
+    w, h, nframes = 264, 40, 9
+    info = VideoInfo(width=w, height=h, pix_fmt="yuv422p10le", bit_depth=10, colorspace="bt709", color_range="tv", fps=25.0, duration=nframes / 25.0)
+    cube = tmp_path / "look.cube"
+    synth.write_cube(cube, synth.look_lut(17).astype(np.float32))
+    frames = [synth.natural_frame("yuv422p10le", w, h, t=t) for t in range(nframes)]
+    src, master, out = tmp_path / "in.mov", tmp_path / "master.mov", tmp_path / "out.mp4"
+    src.write_bytes(np.concatenate(frames).tobytes())          # the stand-in "container" is the raw frames themselves
+    params = ProcessingParams(processing_mode="pro", video_codec="libx264")        # 10-bit master, libx264 delivery: yuv420p
+    task = Task("t1", src, out, cube, None, params, source_info=info, intermediate_path=master)
+    cmds = []
+
+    def popen(cmd, **kw):
+        cmds.append(list(cmd))
+        if "pipe:1" in cmd:      # decoder of whichever stage: stream the file named after -i
+            path = cmd[cmd.index("-i") + 1]
+            fake = [sys.executable, "-c", f"import sys, shutil; shutil.copyfileobj(open({path!r}, 'rb'), sys.stdout.buffer)"]
+        else:                    # encoder: stdin into the file named last
+            fake = [sys.executable, "-c", f"import sys, shutil; shutil.copyfileobj(sys.stdin.buffer, open({cmd[-1]!r}, 'wb'))"]
+        return subprocess.Popen(fake, **kw)
+
+    class Rec(TaskCallbacks):
+        events = []
+
+        def progress(self, tid, pct):
+            self.events.append(("progress", pct))
+
+        def finished(self, tid, st):
+            self.events.append(("finished", st))
+
+        def log(self, tid, msg):
+            self.events.append(("log", msg))
+
+    rec = Rec()
+    probe = lambda path: VideoInfo(width=w, height=h, pix_fmt="yuv422p10le", bit_depth=10, colorspace="bt709", color_range="tv", fps=25.0,  # noqa: E731
+                                   duration=nframes / 25.0)
+    TaskRunner(task, callbacks=rec, frames_per_batch=2, popen=popen, probe=probe, gpu_stage2=True).run()
+    assert rec.events[-1] == ("finished", "completed"), [e for e in rec.events if e[0] != "progress"][-6:]
+    assert len([c for c in cmds if "pipe:1" in c]) == 2 and len([c for c in cmds if "pipe:0" in c]) == 2       # two GPU stages, no plain ffmpeg
+    enc2 = [c for c in cmds if "pipe:0" in c][1]
+    assert enc2[enc2.index("-pix_fmt") + 1] == "yuv420p" and not any("lut3d" in t for t in enc2)
+    assert not master.exists()
+    pcts = [e[1] for e in rec.events if e[0] == "progress"]
+    assert pcts == sorted(pcts) and pcts[-1] == 100 and any(40 <= p <= 50 for p in pcts)
+    got = np.frombuffer(out.read_bytes(), np.uint8)
+    fb = w * h * 3 // 2
+    assert got.size == nframes * fb
+    L = O.OracleLut.from_path(cube)
+    for i in (0, 4, 8):
+        m = oracle_stage("yuv422p10le", w, h, frames[i], L)                                   # stage 1: the master frame
+        Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(m, "yuv422p10le", w, h)]
+        exp = synth.pack_planes(O.convert_yuv422p10("yuv420p", Y, U, V))                      # stage 2: LUT-less conversion
+        assert_bit_exact("yuv420p", w, h, got[i * fb:(i + 1) * fb], exp, f"pro pipeline frame {i}")
