@@ -182,10 +182,9 @@ int check_planes(const lutr_stage *s, const lutr_planes *pl, int fmt, int nframe
     return LUTR_OK;
 }
 
-// The fast kernels need one domain scale for all channels and luma rows whose 15-bit sum cannot saturate.
+// The fast kernels need luma rows whose 15-bit sum cannot saturate.
 bool fast_path_ok(const lutr_stage *s, const lutr_lut *lut) {
     if (!s->use_fast || s->d.interp == LUTR_INTERP_NEAREST) return false;
-    if (lut->scale[0] != lut->scale[1] || lut->scale[0] != lut->scale[2]) return false;
     const int maxv = (1 << s->depth) - 1;
     const long ysum = (long)(s->b.ry + s->b.gy + s->b.by) * maxv;
     if (s->b.ry < 0 || s->b.gy < 0 || s->b.by < 0) return false;
@@ -279,9 +278,10 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
         // arithmetic index: fold a power-of-two LUT scale into the input scale (exact: scaling by 2^k commutes with rounding)
         int exp2 = 0;
         const float sr = k.lut.sr;
-        fk.idx_fold = (sr > 0.f && std::frexp(sr, &exp2) == 0.5f) ? 1 : 0;
+        const bool one_scale = k.lut.sg == sr && k.lut.sb == sr;  // per-channel DOMAIN scales take the general (two-multiply) index
+        fk.idx_fold = (one_scale && sr > 0.f && std::frexp(sr, &exp2) == 0.5f) ? 1 : 0;
         fk.idx_mul = fk.idx_fold ? k.lut.in_scale * sr : k.lut.in_scale;
-        fk.idx_sr = fk.idx_fold ? 1.f : sr;
+        fk.idx_sr[0] = fk.idx_fold ? 1.f : sr, fk.idx_sr[1] = fk.idx_fold ? 1.f : k.lut.sg, fk.idx_sr[2] = fk.idx_fold ? 1.f : k.lut.sb;
         fk.idx_add = -(fk.idx_mul * 8388608.f);
         fk.maxv = maxv;
         {
@@ -296,8 +296,10 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             k.wk_nomin = 1;
             for (int x = 0; x <= maxv; ++x) {
                 volatile float a = (float)x * fk.idx_mul;  // volatile: one rounding per operation
-                volatile float c = a * fk.idx_sr;
-                if (c > lut_max) k.wk_nomin = 0;
+                for (int ch = 0; ch < 3; ++ch) {
+                    volatile float c = a * fk.idx_sr[ch];
+                    if (c > lut_max) k.wk_nomin = 0;
+                }
             }
         }
     }
@@ -307,7 +309,7 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     range_coeffs(pix_depth(s->d.out_fmt), true, false, &k.any.out_lc, &k.any.out_lo);
     range_coeffs(pix_depth(s->d.out_fmt), true, true, &k.any.out_cc, &k.any.out_co);
     // generic tile kernel: combinations without a specialised kernel, and specialised combinations whose fast path does not apply
-    // (per-channel LUT domain scales, interp=nearest on the master stages, rows narrower than a window)
+    // (interp = nearest / pyramid / prism, widths that are not a multiple of 8, rows narrower than a window)
     auto run_any = [&]() {
         AnyK &a = k.any;
         a.in_sub = pix_sub(s->d.in_fmt), a.in_depth = pix_depth(s->d.in_fmt);

@@ -64,8 +64,8 @@ struct FastK {
     // S >> 11 is the high half of the 32-bit sum and one PRMT packs the (u, v) pair (k422_warp.cu, pass B)
     uint32_t cu5[3], cv5[3], kU5, kV5;
     int32_t n2b, nb, totalb;      // byte steps of the LUT axes: n*n*16, n*16, sum + 16
-    // arithmetic index path: s = min(fl(fl(x*in_scale) * sr), lut_max) computed as fma(2^23+x, idx_mul, idx_add) [* idx_sr]
-    float idx_mul, idx_add, idx_sr;
+    // arithmetic index path: s = min(fl(fl(x*in_scale) * sr), lut_max) computed as fma(2^23+x, idx_mul, idx_add) [* idx_sr[c]]
+    float idx_mul, idx_add, idx_sr[3];   // idx_sr: per channel (a .cube DOMAIN may differ per channel); all 1 when folded
     int32_t idx_fold;             // 1: sr is a power of two and was folded into idx_mul (no second multiply)
     int32_t maxv;                 // 2^depth - 1
 };

@@ -240,7 +240,7 @@ __device__ __forceinline__ f2 wacc(f2 c, float w, f2 acc, float one) {
 
 // lut3d constants of one launch
 struct LutC {
-    float idx_mul, idx_add, idx_sr, lut_max, out_scale, one;
+    float idx_mul, idx_add, idx_sr[3], lut_max, out_scale, one;
     unsigned kbase;  // -0x4B000000 * (n*n + n + 1): removes the float bias of the three node indices (wrapping arithmetic)
     int n, n2;
     unsigned long long tex;  // experiments: the same table as a point-sampled linear texture (0 = none)
@@ -248,7 +248,8 @@ struct LutC {
 
 __device__ __forceinline__ LutC make_lutc(const StageK &K) {
     LutC C;
-    C.idx_mul = K.fk.idx_mul, C.idx_add = K.fk.idx_add, C.idx_sr = K.fk.idx_sr;
+    C.idx_mul = K.fk.idx_mul, C.idx_add = K.fk.idx_add;
+    C.idx_sr[0] = K.fk.idx_sr[0], C.idx_sr[1] = K.fk.idx_sr[1], C.idx_sr[2] = K.fk.idx_sr[2];
     C.lut_max = K.lut.lut_max, C.out_scale = K.lut.out_scale, C.one = K.wk_one;
     C.n = K.lut.n, C.n2 = K.lut.n2;
     C.kbase = 0u - kMagic * (unsigned)(C.n2 + C.n + 1);
@@ -278,7 +279,7 @@ __device__ __forceinline__ void lut3d_pair(const LutC &C, const float4 *tab, con
     unsigned pv[3][2], dd[3][2];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        if (IDX == 2) s[c] = mul2s<PK>(s[c], C.idx_sr);
+        if (IDX == 2) s[c] = mul2s<PK>(s[c], C.idx_sr[c]);
         if (!NOMIN) s[c].x = fminf(s[c].x, C.lut_max), s[c].y = fminf(s[c].y, C.lut_max);
         const f2 t = IDX == 2 ? addprz2s<PK>(s[c], 8388608.f, C.one) : addrz2s<PK>(s[c], 8388608.f);  // bits = 0x4B000000 | floor(s)
         const f2 nfl = rsub2s<PK>(8388608.f, t);                                   // -floor(s), exact

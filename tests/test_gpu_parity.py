@@ -426,7 +426,7 @@ def test_any_format_matrix(in_fmt, out_fmt, out_range):
 @pytest.mark.parametrize("in_fmt,out_fmt", [("yuv420p", "yuv444p"), ("yuv422p10le", "yuv420p"), ("yuv444p10le", "yuv422p10le")])
 def test_any_interps_and_domain_scales(interp, in_fmt, out_fmt):
     """All five interpolation modes of the reference's whitelist (ffmpeg.py:243) incl. pyramid / prism, a LUT that leaves [0,1]
-    and per-channel DOMAIN scales (the fast kernels need one common scale)."""
+    and per-channel DOMAIN scales."""
     w, h = 136, 36
     table = (synth.random_lut(9, 4) * 1.6 - 0.3).astype(np.float32)
     frames = _frames(in_fmt, w, h, ["noise", "ramp"])
@@ -630,7 +630,7 @@ def test_yuv420p_to_8bit_422_444(out_fmt, w, h, options, interp, lut_name, kw):
 def test_yuv422p_8bit_source(out_fmt, w, h, options, interp, lut_name, kw):
     """8-bit 4:2:2 sources (yuv422p / yuvj422p: MJPEG cameras, the 4:2:2 range-pass intermediate of ffmpeg.py:137-143) through the
     warp-window kernel's IN422 side -- one chroma row per luma row, otherwise the 4:2:0 arithmetic -- to every row-local output and
-    to yuv420p; odd heights for the 4:2:2 -> 4:2:2 case; per-channel DOMAIN scales fall back to the generic kernel."""
+    to yuv420p; odd heights for the 4:2:2 -> 4:2:2 case; per-channel DOMAIN scales."""
     kw = dict(kw)
     scale = kw.pop("scale", (1.0, 1.0, 1.0))
     if out_fmt == "yuv420p" and h % 2:
@@ -769,3 +769,40 @@ def test_full_range_output_on_the_8bit_warp_kernels(in_fmt, out_fmt, kernel, int
         exp = oracle_stage(in_fmt, w, h, f, L, interp=interp, out_pix_fmt=out_fmt, **kw)
         assert_bit_exact(out_fmt, w, h, out[i * st.out_frame_bytes:(i + 1) * st.out_frame_bytes], exp, f"pc out {in_fmt}->{out_fmt} {interp} frame {i}")
     st.close(), lut.close()
+
+
+@pytest.mark.parametrize("in_fmt,out_fmt,kernel", [("yuv422p10le", "yuv422p10le", "k422_warp"), ("yuv444p10le", "yuv422p10le", "k422_warp"),
+                                                   ("yuv420p10le", "yuv422p10le", "k10_warp"), ("yuv420p10le", "yuv420p10le", "k10_warp"),
+                                                   ("yuv422p10le", "yuv420p", "k10_warp8"), ("yuv420p", "yuv420p", "k420_warp"),
+                                                   ("yuv422p", "yuv422p10le", "k420_warp10"), ("yuv420p", "yuv444p", "k420_warp444")])
+@pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
+@pytest.mark.parametrize("scale", [(0.5, 1.0, 0.25), (0.75, 0.5, 1.0)])
+def test_per_channel_domain_scales_on_the_warp_kernels(in_fmt, out_fmt, kernel, interp, scale):
+    """A .cube whose DOMAIN_MAX differs per channel (vf_lut3d: scale.c = clip(1 / (max.c - min.c), 0, 1), one per channel; reference
+    ffmpeg.py:246 hands the file to lut3d untouched): the warp-window kernels' general index path multiplies by a per-channel
+    constant, so the stage stays off the generic kernel.  17- and 33-point tables, both float orders."""
+    import torch
+    from lut_renderer_b200.stage import ColourStage
+    from oracle import oracle as O
+    w, h = 328, 38
+    for lut_name, fm in (("rand17", "c"), ("look33", "fma")):
+        table = LUTS[lut_name]().astype(np.float32)
+        frames = _frames(in_fmt, w, h, ["natural", "noise", "extremes"])
+        st = ColourStage(w, h, in_fmt, out_pix_fmt=out_fmt, interp=interp, float_mode=fm)
+        lut = st.ctx.lut_from_table(table, scale)
+        src = torch.from_numpy(np.concatenate(frames)).cuda()
+        dst = torch.zeros(len(frames) * st.out_frame_bytes, dtype=torch.uint8, device="cuda")
+        st.run(lut, src, dst, len(frames), stream=torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        assert st.kernel_name.startswith(kernel), st.kernel_name
+        out = dst.cpu().numpy()
+        L = oracle_lut(table, scale)
+        O.set_float_mode(fm)
+        try:
+            for i, f in enumerate(frames):
+                exp = oracle_stage(in_fmt, w, h, f, L, interp=interp, out_pix_fmt=out_fmt)
+                assert_bit_exact(out_fmt, w, h, out[i * st.out_frame_bytes:(i + 1) * st.out_frame_bytes], exp,
+                                 f"per-channel DOMAIN {scale} {in_fmt}->{out_fmt} {interp} {lut_name} {fm} frame {i}")
+        finally:
+            O.set_float_mode("c")
+        st.close(), lut.close()
