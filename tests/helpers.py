@@ -22,7 +22,7 @@ def oracle_lut(table, scale=(1.0, 1.0, 1.0)):
     return O.OracleLut.from_table(table, scale)
 
 
-def gpu_stage(pix_fmt, w, h, frames, table, scale=(1.0, 1.0, 1.0), device=0, options=None, **stage_kw):
+def gpu_stage(pix_fmt, w, h, frames, table, scale=(1.0, 1.0, 1.0), device=0, options=None, info=None, **stage_kw):
     """List of packed frames -> list of packed frames through liblutr.so on the GPU (device-resident path)."""
     import torch
     from lut_renderer_b200.stage import ColourStage
@@ -36,6 +36,8 @@ def gpu_stage(pix_fmt, w, h, frames, table, scale=(1.0, 1.0, 1.0), device=0, opt
     st.run(lut, src, dst, n, stream=torch.cuda.current_stream())
     torch.cuda.synchronize()
     out = dst.cpu().numpy()
+    if info is not None:
+        info["kernel"] = st.kernel_name
     st.close()
     lut.close()
     return [out[i * st.out_frame_bytes:(i + 1) * st.out_frame_bytes] for i in range(n)]
