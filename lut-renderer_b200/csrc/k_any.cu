@@ -24,6 +24,7 @@
 
 #include "lut3d_generic.cuh"
 #include "lutr_internal.h"
+#include "warp_common.cuh"
 
 namespace lutr {
 
@@ -70,6 +71,18 @@ __device__ __forceinline__ int up422(const uint16_t *C, int cw, int x) {
     return min(s >> 9, 32767);
 }
 
+// The same filter for the two luma columns x (even) and x + 1 of one chroma sample pair: five loads instead of eight
+__device__ __forceinline__ void up422_pair(const uint16_t *C, int cw, int x, int &even, int &odd) {
+    const int i = x >> 1;
+    const int a = (int)__ldg(C + max(i - 2, 0)), b = (int)__ldg(C + max(i - 1, 0)), c = (int)__ldg(C + i);
+    const int d = (int)__ldg(C + min(i + 1, cw - 1)), e = (int)__ldg(C + min(i + 2, cw - 1));
+    // columns 0 and 2 take swscale's edge-normalised taps (there a = b = C[0])
+    const int t0 = x <= 2 ? 0 : -461, t1 = x == 0 ? 0 : (x == 2 ? 3835 : 3943), t2 = x == 0 ? 17729 : (x == 2 ? 13894 : 14284);
+    const int t3 = x <= 2 ? -1345 : -1382;
+    even = min((t0 * a + t1 * b + t2 * c + t3 * d) >> 9, 32767);
+    odd = min((-1382 * b + 14284 * c + 3943 * d - 461 * e) >> 9, 32767);
+}
+
 // One sample of a full-range 10-bit source through swscale's one-pass conversion to the 8-bit intermediate the reference inserts
 // (`scale=in_range=pc:out_range=R,format=yuv4xxp`, ffmpeg.py:211-233; oracle orc_prepass_10_to_8).  (py, px): position in the plane.
 __device__ __forceinline__ int pre10_sample(int v, int py, int px, int mode, int plane, int coeff, int offset) {
@@ -83,9 +96,9 @@ __device__ __forceinline__ int pre10_sample(int v, int py, int px, int mode, int
 
 template <int INTERP, bool FMA>
 __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
-    __shared__ unsigned s_c[kCH][kCW];       // per luma pixel: (cu | cv << 16) chroma terms (c14, or c15 for 8-bit 4:4:4)
+    __shared__ __align__(16) unsigned s_c[kCH][kCW];       // per luma pixel: (cu | cv << 16) chroma terms (c14, or c15 for 8-bit 4:4:4)
     __shared__ unsigned s_h[kCH][kTW / 2];   // 4:2:0 outputs: per chroma column and luma row, 15-bit (int16 | int16 << 16)
-    __shared__ unsigned s_up[kUpRows][kCW];  // 10-bit 4:2:0 sources: horizontally upsampled chroma rows of the tile, (int16 | int16 << 16)
+    __shared__ __align__(16) unsigned s_up[kUpRows][kCW];  // 10-bit 4:2:0 sources: horizontally upsampled chroma rows of the tile, (int16 | int16 << 16)
 
     const int w = K.w, h = K.h;
     const int pre10 = K.any.pre10;  // != 0: 10-bit full-range samples enter through the reference's 8-bit intermediate
@@ -101,6 +114,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
     const int tiles_x = (w + kTW - 1) / kTW, tiles_y = (h + kTH - 1) / kTH;
     const long total = (long)tiles_x * tiles_y * K.nframes;
     const int omax = (1 << od) - 1;
+    const LutC LC = make_lutc(K);
 
     for (long t = blockIdx.x; t < total; t += gridDim.x) {
         const int frame = (int)(t / ((long)tiles_x * tiles_y));
@@ -134,8 +148,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
             __syncthreads();
         }
         // ------------------------------------------------ phase A ---------------------------------------------------------
+        // idx / n for idx * n < 2^20 (a tile has at most 68 x 39 pairs): multiply by ceil(2^20 / n)
+        const unsigned rcp_pairs = 0xFFFFFu / (unsigned)npairs + 1u;
         for (int idx = threadIdx.x; idx < npairs * nrows; idx += kThreads) {
-            const int r = idx / npairs, pc = idx - r * npairs;
+            const int r = (int)(((unsigned)idx * rcp_pairs) >> 20), pc = idx - r * npairs;
             const int y = WY0 + r, x = px0 + 2 * pc;
             int R[2], G[2], B[2];
             if (sd == 8) {
@@ -185,51 +201,70 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
                 }
             } else {
                 const uint16_t *yr = reinterpret_cast<const uint16_t *>(inY + (long)y * K.p.in_stride[0]);
+                int u17[2], v17[2];
+                if (!in_sx) {         // yuv444p10le
+                    const uint16_t *ur = reinterpret_cast<const uint16_t *>(inU + (long)y * K.p.in_stride[1]);
+                    const uint16_t *vr = reinterpret_cast<const uint16_t *>(inV + (long)y * K.p.in_stride[2]);
+                    const unsigned up = __ldg(reinterpret_cast<const unsigned *>(ur + x)), vp = __ldg(reinterpret_cast<const unsigned *>(vr + x));
+                    u17[0] = ((int)(up & 0xFFFFu) - 512) * 128, u17[1] = ((int)(up >> 16) - 512) * 128;
+                    v17[0] = ((int)(vp & 0xFFFFu) - 512) * 128, v17[1] = ((int)(vp >> 16) - 512) * 128;
+                } else if (!in_sy) {  // yuv422p10le: 4-tap horizontal upsample of the pair's two columns
+                    const uint16_t *ur = reinterpret_cast<const uint16_t *>(inU + (long)y * K.p.in_stride[1]);
+                    const uint16_t *vr = reinterpret_cast<const uint16_t *>(inV + (long)y * K.p.in_stride[2]);
+                    int ue, uo, ve, vo;
+                    up422_pair(ur, cwi, x, ue, uo), up422_pair(vr, cwi, x, ve, vo);
+                    u17[0] = 4 * ue - 65536, u17[1] = 4 * uo - 65536, v17[0] = 4 * ve - 65536, v17[1] = 4 * vo - 65536;
+                } else {              // yuv420p10le: the staged horizontally upsampled rows, then the 4-tap vertical filter
+                    const int j = y >> 1;
+                    int r0, t0, t1, t2, t3;
+                    if (y & 1) {
+                        r0 = j - 1, t0 = -346, t1 = 3572, t2 = 985, t3 = -115;
+                    } else {
+                        r0 = j - 2;
+                        if (y == 0) t0 = 0, t1 = 0, t2 = 4432, t3 = -336;
+                        else if (y == 2) t0 = 0, t1 = 959, t2 = 3473, t3 = -336;
+                        else t0 = -115, t1 = 985, t2 = 3572, t3 = -346;
+                    }
+                    const int tp[4] = {t0, t1, t2, t3};
+                    int su[2], sv[2];
+                    su[0] = su[1] = sv[0] = sv[1] = (1 << 9) - (128 << 19);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (tp[k] == 0) continue;
+                        // the pair's two columns are neighbours in the staged row: one 64-bit load (x - WX0 is even, rows are 8-byte aligned)
+                        const uint2 pk = *reinterpret_cast<const uint2 *>(&s_up[clampi(r0 + k, 0, chi - 1) - uc0][x - WX0]);
+                        su[0] += tp[k] * (int)(short)(pk.x & 0xFFFFu), sv[0] += tp[k] * ((int)pk.x >> 16);
+                        su[1] += tp[k] * (int)(short)(pk.y & 0xFFFFu), sv[1] += tp[k] * ((int)pk.y >> 16);
+                    }
+                    u17[0] = su[0] >> 10, v17[0] = sv[0] >> 10, u17[1] = su[1] >> 10, v17[1] = sv[1] >> 10;
+                }
+                const unsigned ypair = __ldg(reinterpret_cast<const unsigned *>(yr + x));   // two 10-bit luma samples
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const int xx = x + q;
-                    int u17, v17;
-                    if (!in_sx) {         // yuv444p10le
-                        const uint16_t *ur = reinterpret_cast<const uint16_t *>(inU + (long)y * K.p.in_stride[1]);
-                        const uint16_t *vr = reinterpret_cast<const uint16_t *>(inV + (long)y * K.p.in_stride[2]);
-                        u17 = ((int)__ldg(ur + xx) - 512) * 128, v17 = ((int)__ldg(vr + xx) - 512) * 128;
-                    } else if (!in_sy) {  // yuv422p10le: 4-tap horizontal upsample
-                        const uint16_t *ur = reinterpret_cast<const uint16_t *>(inU + (long)y * K.p.in_stride[1]);
-                        const uint16_t *vr = reinterpret_cast<const uint16_t *>(inV + (long)y * K.p.in_stride[2]);
-                        u17 = 4 * up422(ur, cwi, xx) - 65536, v17 = 4 * up422(vr, cwi, xx) - 65536;
-                    } else {              // yuv420p10le: the staged horizontally upsampled rows, then the 4-tap vertical filter
-                        const int j = y >> 1;
-                        int r0, t0, t1, t2, t3;
-                        if (y & 1) {
-                            r0 = j - 1, t0 = -346, t1 = 3572, t2 = 985, t3 = -115;
-                        } else {
-                            r0 = j - 2;
-                            if (y == 0) t0 = 0, t1 = 0, t2 = 4432, t3 = -336;
-                            else if (y == 2) t0 = 0, t1 = 959, t2 = 3473, t3 = -336;
-                            else t0 = -115, t1 = 985, t2 = 3572, t3 = -346;
-                        }
-                        const int tp[4] = {t0, t1, t2, t3};
-                        int su = (1 << 9) - (128 << 19), sv = su;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (tp[k] == 0) continue;
-                            const unsigned pk = s_up[clampi(r0 + k, 0, chi - 1) - uc0][xx - WX0];
-                            su += tp[k] * (int)(short)(pk & 0xFFFFu);
-                            sv += tp[k] * ((int)pk >> 16);
-                        }
-                        u17 = su >> 10, v17 = sv >> 10;
-                    }
-                    const unsigned yy = (unsigned)__ldg(yr + xx) * yA10 + yK10;
-                    R[q] = clip30((int)(yy + (unsigned)v17 * (unsigned)f.vr)) >> 20;
-                    G[q] = clip30((int)(yy + (unsigned)v17 * (unsigned)f.vg + (unsigned)u17 * (unsigned)f.ug)) >> 20;
-                    B[q] = clip30((int)(yy + (unsigned)u17 * (unsigned)f.ub)) >> 20;
+                    const unsigned yy = (q ? ypair >> 16 : ypair & 0xFFFFu) * yA10 + yK10;
+                    R[q] = clip30((int)(yy + (unsigned)v17[q] * (unsigned)f.vr)) >> 20;
+                    G[q] = clip30((int)(yy + (unsigned)v17[q] * (unsigned)f.vg + (unsigned)u17[q] * (unsigned)f.ug)) >> 20;
+                    B[q] = clip30((int)(yy + (unsigned)u17[q] * (unsigned)f.ub)) >> 20;
                 }
             }
             // lut3d on both pixels, then the luma output and the chroma terms
             int ro[2], go[2], bo[2], yq[2];
+            unsigned cq[2];
+            if constexpr (INTERP == LUTR_INTERP_TETRAHEDRAL || INTERP == LUTR_INTERP_TRILINEAR) {
+                // the packed two-pixel evaluation of the warp-window kernels (general index, coordinate and output clips kept):
+                // codes go in as the floats 2^23 + code and come out as 0x4B000000 | code
+                const unsigned mr[2] = {kMagic | (unsigned)R[0], kMagic | (unsigned)R[1]}, mg[2] = {kMagic | (unsigned)G[0], kMagic | (unsigned)G[1]};
+                const unsigned mb[2] = {kMagic | (unsigned)B[0], kMagic | (unsigned)B[1]};
+                unsigned pr[2], pg[2], pb[2];
+                lut3d_pair<INTERP, FMA, true, 2, false, 0, true>(LC, K.lut.tab, mr, mg, mb, pr, pg, pb);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) ro[q] = (int)(pr[q] & 0xFFFFu), go[q] = (int)(pg[q] & 0xFFFFu), bo[q] = (int)(pb[q] & 0xFFFFu);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) lut3d_px<INTERP, FMA>(K.lut, R[q], G[q], B[q], (1 << sd) - 1, ro[q], go[q], bo[q]);
+            }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                lut3d_px<INTERP, FMA>(K.lut, R[q], G[q], B[q], (1 << sd) - 1, ro[q], go[q], bo[q]);
                 int y15;
                 if (sd == 8) y15 = 2 * ((b.ry * ro[q] + b.gy * go[q] + b.by * bo[q] + (32 << 14) + (1 << 8)) >> 9);
                 else y15 = min(2 * ((b.ry * ro[q] + b.gy * go[q] + b.by * bo[q] + (16 << 17) + (1 << 10)) >> 11), 32767);
@@ -248,14 +283,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
                     cu = (b.ru * ro[q] + b.gu * go[q] + b.bu * bo[q] + (128 << 17) + (1 << 10)) >> 11;
                     cv = (b.rv * ro[q] + b.gv * go[q] + b.bv * bo[q] + (128 << 17) + (1 << 10)) >> 11;
                 }
-                s_c[r][x + q - WX0] = (cu & 0xFFFFu) | (cv << 16);
+                cq[q] = (cu & 0xFFFFu) | (cv << 16);
             }
             if (sd == 8 && o_sx) {  // rgb24ToUV_half: matrix on the pair sums
                 const int rs = ro[0] + ro[1], gs = go[0] + go[1], bs = bo[0] + bo[1];
                 const unsigned cu = 2 * ((b.ru * rs + b.gu * gs + b.bu * bs + (256 << 15) + (1 << 9)) >> 10);
                 const unsigned cv = 2 * ((b.rv * rs + b.gv * gs + b.bv * bs + (256 << 15) + (1 << 9)) >> 10);
-                s_c[r][x - WX0] = (cu & 0xFFFFu) | (cv << 16);
+                cq[0] = (cu & 0xFFFFu) | (cv << 16);
             }
+            *reinterpret_cast<uint2 *>(&s_c[r][x - WX0]) = make_uint2(cq[0], cq[1]);  // x - WX0 is even: one 8-byte store per pair
             if (x >= X0 && x < X1 && y >= Y0 && y < Y1) {
                 if (od == 8) *reinterpret_cast<unsigned short *>(outY + (long)y * K.p.out_stride[0] + x) = (unsigned short)(yq[0] | yq[1] << 8);
                 else *reinterpret_cast<unsigned *>(outY + (long)y * K.p.out_stride[0] + 2 * x) = (unsigned)(yq[0] | yq[1] << 16);
@@ -265,18 +301,31 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
         // ------------------------------------------------ phase B ---------------------------------------------------------
         // chroma columns of the tile: ci = (X0 >> o_sx) + i; rows: all window rows for 4:2:0 outputs, the tile's own rows otherwise
         const int ncol = (X1 - X0) >> o_sx;
+        const unsigned rcp_col = 0xFFFFFu / (unsigned)ncol + 1u;   // idx / ncol as in phase A (at most 128 x 39 samples)
+        // no tap of this tile's decimation leaves the row: columns X0 - 3 .. X1 + 2 exist (then WX0 = X0 - 4 and tap k of chroma
+        // column i sits at word 2 i + 1 + k of the staged row)
+        const bool inner = X0 >= 4 && X1 + 3 <= w;
         for (int idx = threadIdx.x; idx < ncol * nrows; idx += kThreads) {
-            const int r = idx / ncol, i = idx - r * ncol;
+            const int r = (int)(((unsigned)idx * rcp_col) >> 20), i = idx - r * ncol;
             const int y = WY0 + r;
             int cu, cv;
             if (sd > 8 && o_sx) {  // 8-tap horizontal decimation over luma columns 2ci-3 .. 2ci+4, clamped to the row
-                const int taps[8] = {-230, -692, 1972, 7142, 7142, 1972, -692, -230};
-                int su = 0, sv = 0;
+                // the taps are symmetric and the staged words hold two 14-bit fields: add the mirrored words first (no carry between
+                // the fields), four multiplies per channel instead of eight
+                unsigned s0, s1, s2, s3;
+                if (inner) {
+                    const unsigned *row = &s_c[r][2 * i];
+                    const uint2 p23 = *reinterpret_cast<const uint2 *>(row + 2), p45 = *reinterpret_cast<const uint2 *>(row + 4);
+                    const uint2 p67 = *reinterpret_cast<const uint2 *>(row + 6);
+                    s0 = row[1] + row[8], s1 = p23.x + p67.y, s2 = p23.y + p67.x, s3 = p45.x + p45.y;
+                } else {
+                    unsigned pk[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const unsigned pk = s_c[r][clampi(X0 + 2 * i - 3 + k, 0, w - 1) - WX0];
-                    su += taps[k] * (int)(pk & 0xFFFFu), sv += taps[k] * (int)(pk >> 16);
+                    for (int k = 0; k < 8; ++k) pk[k] = s_c[r][clampi(X0 + 2 * i - 3 + k, 0, w - 1) - WX0];
+                    s0 = pk[0] + pk[7], s1 = pk[1] + pk[6], s2 = pk[2] + pk[5], s3 = pk[3] + pk[4];
                 }
+                const int su = -230 * (int)(s0 & 0xFFFFu) - 692 * (int)(s1 & 0xFFFFu) + 1972 * (int)(s2 & 0xFFFFu) + 7142 * (int)(s3 & 0xFFFFu);
+                const int sv = -230 * (int)(s0 >> 16) - 692 * (int)(s1 >> 16) + 1972 * (int)(s2 >> 16) + 7142 * (int)(s3 >> 16);
                 cu = min(su >> 13, 32767), cv = min(sv >> 13, 32767);
             } else {
                 const unsigned pk = s_c[r][X0 + (i << o_sx) - WX0];
@@ -303,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_any(const StageK K) {
         // ------------------------------------------------ phase C ---------------------------------------------------------
         const int nj = (Y1 - Y0) >> 1;
         for (int idx = threadIdx.x; idx < ncol * nj; idx += kThreads) {
-            const int jr = idx / ncol, i = idx - jr * ncol;
+            const int jr = (int)(((unsigned)idx * rcp_col) >> 20), i = idx - jr * ncol;
             const int j = (Y0 >> 1) + jr, ci = (X0 >> 1) + i;
             const int taps[8] = {-58, -172, 492, 1786, 1786, 492, -172, -58};
             const int du = bayer ? dither128(j, ci) : 64, dv = bayer ? dither128(j, ci + 3) : 64;
@@ -342,7 +391,9 @@ using KernelFn = void (*)(const StageK);
 template <int INTERP>
 KernelFn pick(bool fma) {
     // FFmpeg has assembly (contracted multiply-adds) for tetrahedral and trilinear only
-    if (fma && (INTERP == LUTR_INTERP_TETRAHEDRAL || INTERP == LUTR_INTERP_TRILINEAR)) return k_any<INTERP, true>;
+    if constexpr (INTERP == LUTR_INTERP_TETRAHEDRAL || INTERP == LUTR_INTERP_TRILINEAR) {
+        if (fma) return k_any<INTERP, true>;
+    }
     return k_any<INTERP, false>;
 }
 

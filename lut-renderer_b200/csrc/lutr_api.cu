@@ -244,6 +244,28 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
     k.idx_mode = -1;
     k.min_blocks = s->min_blocks;
     k.clamp_out = lut->needs_clamp ? 1 : 0;
+    {   // lut3d index constants of the packed evaluation (warp_common.cuh lut3d_pair), shared by the warp-window kernels and k_any
+        FastK &fk = k.fk;
+        // arithmetic index: fold a power-of-two LUT scale into the input scale (exact: scaling by 2^k commutes with rounding)
+        int exp2 = 0;
+        const float sr = k.lut.sr;
+        const bool one_scale = k.lut.sg == sr && k.lut.sb == sr;  // per-channel DOMAIN scales take the general (two-multiply) index
+        fk.idx_fold = (one_scale && sr > 0.f && std::frexp(sr, &exp2) == 0.5f) ? 1 : 0;
+        fk.idx_mul = fk.idx_fold ? k.lut.in_scale * sr : k.lut.in_scale;
+        fk.idx_sr[0] = fk.idx_fold ? 1.f : sr, fk.idx_sr[1] = fk.idx_fold ? 1.f : k.lut.sg, fk.idx_sr[2] = fk.idx_fold ? 1.f : k.lut.sb;
+        fk.idx_add = -(fk.idx_mul * 8388608.f);
+        fk.maxv = maxv;
+        k.wk_one = 1.0f;
+        // the clip of the LUT coordinate to lut_max is dead code unless some code value overshoots it: try them all
+        k.wk_nomin = 1;
+        for (int x = 0; x <= maxv; ++x) {
+            volatile float a = (float)x * fk.idx_mul;  // volatile: one rounding per operation
+            for (int ch = 0; ch < 3; ++ch) {
+                volatile float c = a * fk.idx_sr[ch];
+                if (c > lut_max) k.wk_nomin = 0;
+            }
+        }
+    }
     bool warp_kernel = false;
     if (fast_path_ok(s, lut)) {
         // warp-window kernels: 8-column lanes (w % 8, 16-byte luma / 8-byte chroma vector accesses: check_planes), 32-bit unit counter
@@ -275,32 +297,13 @@ int enqueue(lutr_stage *s, const lutr_lut *lut, const lutr_planes *in, const lut
             fk.kV = (uint32_t)((256 << 15) + (1 << 9)) - 2u * magic * (uint32_t)(s->b.rv + s->b.gv + s->b.bv);
         }
         fk.n2b = k.lut.n2 * 16, fk.nb = k.lut.n * 16, fk.totalb = fk.n2b + fk.nb + 16;
-        // arithmetic index: fold a power-of-two LUT scale into the input scale (exact: scaling by 2^k commutes with rounding)
-        int exp2 = 0;
-        const float sr = k.lut.sr;
-        const bool one_scale = k.lut.sg == sr && k.lut.sb == sr;  // per-channel DOMAIN scales take the general (two-multiply) index
-        fk.idx_fold = (one_scale && sr > 0.f && std::frexp(sr, &exp2) == 0.5f) ? 1 : 0;
-        fk.idx_mul = fk.idx_fold ? k.lut.in_scale * sr : k.lut.in_scale;
-        fk.idx_sr[0] = fk.idx_fold ? 1.f : sr, fk.idx_sr[1] = fk.idx_fold ? 1.f : k.lut.sg, fk.idx_sr[2] = fk.idx_fold ? 1.f : k.lut.sb;
-        fk.idx_add = -(fk.idx_mul * 8388608.f);
-        fk.maxv = maxv;
         {
             k.tiles_per_row = (k.w + 239) / 240;  // 4:2:2; the 4:2:0 windows are sized below
             k.wk_pk = s->wk_pk;
-            k.wk_one = 1.0f;
             k.wk_unroll = s->wk_unroll;
             k.wk_var = s->wk_var;
             k.wk_carveout = s->wk_carveout;
             k.min_blocks = s->d.interp == LUTR_INTERP_TRILINEAR ? 2 : s->wk_minb;
-            // the clip of the LUT coordinate to lut_max is dead code unless some code value overshoots it: try them all
-            k.wk_nomin = 1;
-            for (int x = 0; x <= maxv; ++x) {
-                volatile float a = (float)x * fk.idx_mul;  // volatile: one rounding per operation
-                for (int ch = 0; ch < 3; ++ch) {
-                    volatile float c = a * fk.idx_sr[ch];
-                    if (c > lut_max) k.wk_nomin = 0;
-                }
-            }
         }
     }
     k.grid_ctas = s->grid_ctas > 0 ? s->grid_ctas : k.min_blocks * s->ctx->sm_count;

@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py $B > gpurun_out/${tag}_ncu_launches.log 2>&1
 for cfg in "$@"; do
   extra=""
-  case $cfg in any444) cfgname=cfg3; extra="--in-fmt yuv444p10le --out-fmt yuv444p10le --frames-per-step 16";; *) cfgname=$cfg;; esac
+  case $cfg in any444) cfgname=cfg3; extra="--in-fmt yuv444p10le --out-fmt yuv444p10le --frames-per-step 16";; any422) cfgname=cfg3; extra="--opt any_kernel=1 --frames-per-step 16";; *) cfgname=$cfg;; esac
   frames=$([ "$extra" ] && echo 16 || ([ $cfgname = cfg4 ] && echo 16 || ([ $cfgname = cfg1 -o $cfgname = cfg2 ] && echo 256 || echo 64)))
   python bench.py --config $cfgname $extra $B > gpurun_out/${tag}_${cfg}_plain.log 2>&1 || continue
   ncu --set full --clock-control none --import-source on --launch-skip 5 -c 1 -k regex:'k422|k420_warp|k10_warp|k_any|k_convert' \
