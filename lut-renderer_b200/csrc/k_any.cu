@@ -17,9 +17,11 @@
 //            source leg straight from global memory (read-only path) -> lut3d -> luma out, per-pixel chroma terms to shared memory
 //   phase B  per chroma column: pair sum / horizontal 8-tap decimation, range conversion; 4:2:2 / 4:4:4 outputs are written here
 //   phase C  4:2:0 outputs: vertical 8-tap decimation of the rows phase B left in shared memory
-// This kernel favours coverage over speed (halo recomputation up to 29 %, no register-level pipelining; its loads come straight
-// from global memory, so it is latency-bound and built for 4 CTAs per SM: 64 registers, measured +45 % over 2 CTAs); the headline
-// configurations never reach it.
+// lut3d: tetrahedral / trilinear run the packed two-pixel evaluation of the warp-window kernels (warp_common.cuh lut3d_pair, general
+// index path, coordinate and output clips kept); nearest / pyramid / prism the scalar restatement in lut3d_generic.cuh.
+// This kernel favours coverage over speed (halo recomputation up to 29 %, run-time format switches, no register-level pipelining;
+// 271 thread-instructions per pixel, issue-bound; built for 4 CTAs per SM with 64 registers); the headline configurations never
+// reach it.
 #include <cuda_runtime.h>
 
 #include "lut3d_generic.cuh"
