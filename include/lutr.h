@@ -130,6 +130,13 @@ LUTR_API const char *lutr_last_error(void); /* thread-local; replaces ffmpeg's s
  * order [r][g][b] (release with lutr_free), scale[c] = clip(1/(DOMAIN_MAX[c]-DOMAIN_MIN[c]), 0, 1). */
 LUTR_API int lutr_cube_parse(const char *text, size_t len, int32_t *size, float scale[3], float **table);
 LUTR_API int lutr_cube_parse_file(const char *path, int32_t *size, float scale[3], float **table);
+/* The other file dialects lut3d reads, chosen by the file extension as lut3d's init does (case-insensitive: .cube .dat .3dl .m3d
+ * .csp; no / unknown extension -> LUTR_ERR_INVALID_ARG).  The reference's GUI only offers *.cube (lut_manager.py:121); a task built
+ * through the model can carry any of them to `lut3d=file=...` (ffmpeg.py:246).  Restated from memory of vf_lut3d.c, unpinned
+ * (csrc/lut_dialects.cpp has the rules); a .csp with a 1D shaper in front of the cube is LUTR_ERR_UNSUPPORTED. */
+typedef enum lutr_lut_dialect { LUTR_LUT_CUBE = 0, LUTR_LUT_DAT = 1, LUTR_LUT_3DL = 2, LUTR_LUT_M3D = 3, LUTR_LUT_CSP = 4 } lutr_lut_dialect;
+LUTR_API int lutr_lut_parse_text(const char *text, size_t len, int32_t dialect, int32_t *size, float scale[3], float **table);
+LUTR_API int lutr_lut_parse_file(const char *path, int32_t *size, float scale[3], float **table);
 LUTR_API void lutr_free(void *p);
 
 /* ---- device context ------------------------------------------------------------------------------ */
@@ -144,6 +151,7 @@ LUTR_API void lutr_host_free(lutr_ctx *ctx, void *p);
 /* ---- LUT upload: once per device and per distinct LUT --------------------------------------------- */
 LUTR_API int lutr_lut_load_cube(lutr_ctx *ctx, const char *path, lutr_lut **out);
 LUTR_API int lutr_lut_load_cube_memory(lutr_ctx *ctx, const char *text, size_t len, lutr_lut **out);
+LUTR_API int lutr_lut_load_file(lutr_ctx *ctx, const char *path, lutr_lut **out); /* any dialect, by extension (see lutr_lut_parse_file) */
 LUTR_API int lutr_lut_from_table(lutr_ctx *ctx, int32_t size, const float *rgb, const float scale[3], lutr_lut **out);
 LUTR_API int lutr_lut_size(const lutr_lut *lut);
 LUTR_API void lutr_lut_destroy(lutr_lut *lut);

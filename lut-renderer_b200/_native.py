@@ -62,6 +62,9 @@ SIGNATURES = {
     "lutr_host_alloc": (ctypes.c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "lutr_host_free": (None, [c_void_p, c_void_p]),
     "lutr_lut_load_cube": (ctypes.c_int, [c_void_p, c_char_p, POINTER(c_void_p)]),
+    "lutr_lut_load_file": (ctypes.c_int, [c_void_p, c_char_p, POINTER(c_void_p)]),
+    "lutr_lut_parse_text": (ctypes.c_int, [c_char_p, c_size_t, c_int32, POINTER(c_int32), POINTER(c_float), POINTER(POINTER(c_float))]),
+    "lutr_lut_parse_file": (ctypes.c_int, [c_char_p, POINTER(c_int32), POINTER(c_float), POINTER(POINTER(c_float))]),
     "lutr_lut_load_cube_memory": (ctypes.c_int, [c_void_p, c_char_p, c_size_t, POINTER(c_void_p)]),
     "lutr_lut_from_table": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, POINTER(c_void_p)]),
     "lutr_lut_size": (ctypes.c_int, [c_void_p]),
@@ -107,13 +110,33 @@ def check(status: int) -> int:
     return status
 
 
-def parse_cube_text(text) -> tuple:
-    """Host-only .cube parse -> (size, scale[3], table as nested python lists is avoided: returns a ctypes float array)."""
+LUT_DIALECT = {"cube": 0, "dat": 1, "3dl": 2, "m3d": 3, "csp": 4}   # lutr_lut_dialect
+
+
+def parse_lut_file(path) -> tuple:
+    """Host-only parse of any LUT file lut3d reads, the dialect chosen by the extension -> (size, scale[3], table [r][g][b][3])."""
+    import os
+    size = c_int32()
+    scale = (c_float * 3)()
+    table = POINTER(c_float)()
+    check(lib().lutr_lut_parse_file(os.fsencode(str(path)), byref(size), scale, byref(table)))
+    return _take_table(size, scale, table)
+
+
+def parse_cube_text(text, dialect: str = "cube") -> tuple:
+    """Host-only .cube (or other dialect) parse -> (size, scale[3], float32 table [r][g][b][3])."""
     data = text if isinstance(text, (bytes, bytearray)) else str(text).encode()
     size = c_int32()
     scale = (c_float * 3)()
     table = POINTER(c_float)()
-    check(lib().lutr_cube_parse(bytes(data), len(data), byref(size), scale, byref(table)))
+    if dialect == "cube":
+        check(lib().lutr_cube_parse(bytes(data), len(data), byref(size), scale, byref(table)))
+    else:
+        check(lib().lutr_lut_parse_text(bytes(data), len(data), LUT_DIALECT[dialect], byref(size), scale, byref(table)))
+    return _take_table(size, scale, table)
+
+
+def _take_table(size, scale, table) -> tuple:
     try:
         n = size.value ** 3 * 3
         values = (c_float * n).from_address(ctypes.addressof(table.contents))

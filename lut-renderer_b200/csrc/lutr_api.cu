@@ -480,6 +480,36 @@ int lutr_cube_parse_file(const char *path, int32_t *size, float scale[3], float 
     return LUTR_OK;
 }
 
+static int export_table(const CubeLut &c, int32_t *size, float scale[3], float **table) {
+    float *t = (float *)std::malloc(c.rgb.size() * sizeof(float));
+    if (!t) return LUTR_ERR_NOMEM;
+    std::memcpy(t, c.rgb.data(), c.rgb.size() * sizeof(float));
+    *size = c.size;
+    if (scale) std::memcpy(scale, c.scale, 3 * sizeof(float));
+    *table = t;
+    return LUTR_OK;
+}
+
+int lutr_lut_parse_text(const char *text, size_t len, int32_t dialect, int32_t *size, float scale[3], float **table) {
+    if (!size || !table) {
+        set_error("lutr_lut_parse_text: NULL output");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    CubeLut c;
+    const int rc = parse_lut_text(text, len, dialect, c);
+    return rc != LUTR_OK ? rc : export_table(c, size, scale, table);
+}
+
+int lutr_lut_parse_file(const char *path, int32_t *size, float scale[3], float **table) {
+    if (!size || !table) {
+        set_error("lutr_lut_parse_file: NULL output");
+        return LUTR_ERR_INVALID_ARG;
+    }
+    CubeLut c;
+    const int rc = parse_lut_file(path, c);
+    return rc != LUTR_OK ? rc : export_table(c, size, scale, table);
+}
+
 void lutr_free(void *p) { std::free(p); }
 
 int lutr_device_count(int32_t *count) {
@@ -563,6 +593,15 @@ int lutr_lut_load_cube(lutr_ctx *ctx, const char *path, lutr_lut **out) {
     *out = nullptr;
     CubeLut c;
     int rc = parse_cube_file(path, c);
+    if (rc != LUTR_OK) return rc;
+    return upload_lut(ctx, c, out);
+}
+
+int lutr_lut_load_file(lutr_ctx *ctx, const char *path, lutr_lut **out) {
+    if (!ctx || !out) return LUTR_ERR_INVALID_ARG;
+    *out = nullptr;
+    CubeLut c;
+    const int rc = parse_lut_file(path, c);
     if (rc != LUTR_OK) return rc;
     return upload_lut(ctx, c, out);
 }

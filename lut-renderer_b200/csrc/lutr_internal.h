@@ -25,6 +25,10 @@ struct CubeLut {
 // returns LUTR_OK or a negative lutr_status and sets the error text
 int parse_cube(const char *text, size_t len, CubeLut &out);
 int parse_cube_file(const char *path, CubeLut &out);
+// the other dialects lut3d reads (lut_dialects.cpp): dialect = lutr_lut_dialect, or chosen by the file extension
+int lut_dialect_of_path(const char *path);
+int parse_lut_text(const char *text, size_t len, int dialect, CubeLut &out);
+int parse_lut_file(const char *path, CubeLut &out);
 
 // ---- colour tables (integer coefficients of the swscale legs) --------------------------------------
 struct Yuv2RgbK {

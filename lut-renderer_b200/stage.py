@@ -62,6 +62,23 @@ class DeviceContext:
                 self._luts[key] = lut
         return lut
 
+    def lut_from_file(self, path) -> "DeviceLut":
+        """Any LUT file lut3d reads (.cube .dat .3dl .m3d .csp), the reader chosen by the extension as lut3d does; same cache."""
+        p = Path(path)
+        if p.suffix.lower() == ".cube":
+            return self.lut_from_cube(p)
+        st = os.stat(p)
+        key = (str(p.resolve()), st.st_mtime_ns, st.st_size)
+        with self._lock:
+            lut = self._luts.get(key)
+        if lut is None:
+            h = c_void_p()
+            N.check(N.lib().lutr_lut_load_file(self._h, os.fsencode(str(p)), byref(h)))
+            lut = DeviceLut(self, h)
+            with self._lock:
+                self._luts[key] = lut
+        return lut
+
     def prefetch_lut(self, path, cached: bool = True):
         """Start parsing + uploading a .cube on a background thread (the C calls release the GIL) and return a Future of the
         DeviceLut: a batch queue loads the next clip's LUT while the GPU works on the current clip.  cached=False always

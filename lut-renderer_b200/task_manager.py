@@ -226,7 +226,7 @@ class TaskRunner:
         Returns (first non-zero exit code of the two processes -- 0 = both fine, None when cancelled --, frames processed)."""
         from .stage import ColourStage  # deferred: loads liblutr.so, fails loudly when it is missing
         colour = ColourStage.from_plan(plan, device=device)
-        lut = colour.ctx.lut_from_cube(plan.lut_path) if plan.lut_path else None   # None: LUT-less conversion (interp="none")
+        lut = colour.ctx.lut_from_file(plan.lut_path) if plan.lut_path else None   # None: LUT-less conversion (interp="none")
         dec = self._spawn(decode_cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, bufsize=0)
         enc = self._spawn(encode_cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, bufsize=0)
         flag = ctypes.c_int32(1 if self._cancelled else 0)

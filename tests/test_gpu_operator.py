@@ -313,3 +313,39 @@ def test_pro_pipeline_with_gpu_stage2(tmp_path):
         Y, U, V = [np.ascontiguousarray(p) for p in synth.split_planes(m, "yuv422p10le", w, h)]
         exp = synth.pack_planes(O.convert_yuv422p10("yuv420p", Y, U, V))                      # stage 2: LUT-less conversion
         assert_bit_exact("yuv420p", w, h, got[i * fb:(i + 1) * fb], exp, f"pro pipeline frame {i}")
+
+
+@pytest.mark.parametrize("dialect", ["3dl", "csp", "dat"])
+def test_other_lut_dialects_through_the_stage(tmp_path, dialect):
+    """A task whose lut_path is one of the other files lut3d reads (reference ffmpeg.py:246 passes the path through; lut3d picks the
+    reader by extension): DeviceContext.lut_from_file -> lutr_lut_load_file -> the same kernels.  Expected frames: the oracle chain
+    on the table / DOMAIN scale the independent reader (oracle/lut_dialects.py) gets from the same file."""
+    import torch
+    from lut_renderer_b200.stage import ColourStage, DeviceContext
+    from oracle import lut_dialects as D
+    from oracle import oracle as O
+    from test_lut_dialects import write_3dl, write_csp, write_dat
+    w, h = 256, 32
+    path = tmp_path / f"look.{dialect}"
+    if dialect == "3dl":
+        write_3dl(path, np.round(synth.look_lut(17) * 4095).astype(np.int64))
+    elif dialect == "csp":
+        write_csp(path, synth.look_lut(9).astype(np.float32), in_rng=((0, 2), (0, 1), (0, 4)))   # per-channel input range -> DOMAIN scale
+    else:
+        write_dat(path, synth.look_lut(33).astype(np.float32))
+    size, scale, table = D.READERS[dialect](path.read_bytes())
+    frames = [synth.natural_frame("yuv422p10le", w, h, t=3), synth.noise_frame("yuv422p10le", w, h, seed=5)]
+    st = ColourStage(w, h, "yuv422p10le")
+    lut = DeviceContext.get(0).lut_from_file(path)
+    assert lut.size == size and DeviceContext.get(0).lut_from_file(path) is lut
+    src = torch.from_numpy(np.concatenate(frames)).cuda()
+    dst = torch.zeros(len(frames) * st.out_frame_bytes, dtype=torch.uint8, device="cuda")
+    st.run(lut, src, dst, len(frames), stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert st.kernel_name == "k422_warp"
+    out = dst.cpu().numpy()
+    L = O.OracleLut.from_table(table, scale)
+    for i, f in enumerate(frames):
+        assert_bit_exact("yuv422p10le", w, h, out[i * st.out_frame_bytes:(i + 1) * st.out_frame_bytes],
+                         oracle_stage("yuv422p10le", w, h, f, L), f".{dialect} frame {i}")
+    st.close()

@@ -83,7 +83,7 @@ def test_cancel_before_start(tmp_path):
 # ---- the pipelined GPU pump (reader thread | stage | writer thread) with the stage itself replaced by a byte-flipping stand-in: the
 # ---- threading, pipe, cancel, failure and sharding logic is host code and must hold without a GPU ---------------------------------
 class _FakeCtx:
-    def lut_from_cube(self, path):
+    def lut_from_file(self, path):
         return object()
 
 
