@@ -273,6 +273,8 @@ int launch_k422_warp(const StageK &k, bool in444, int interp, int float_mode, vo
     if (k.wk_var == 100 * B) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, B>;
         WK_CASE(0) WK_CASE(1) WK_CASE(2)
 #undef WK_CASE
+        if (k.wk_var == 3002) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 2, 4, false>;  // 2 CTAs / SM, up to 128 registers
+        if (k.wk_var == 3012) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 2, 2, false>;  // same, two steps unrolled
         if (k.wk_var == 2001 && k.lut.tex) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, 1, 1>;  // c111 through TEX
         if (k.wk_var == 2002 && k.lut.tex) fn = k422_warp<LUTR_INTERP_TETRAHEDRAL, false, false, 1, true, 65, true, 3, 4, false, 1, 2>;  // + second step
     }
