@@ -4,6 +4,9 @@
 #include <poll.h>
 #include <pthread.h>
 #include <signal.h>
+#include <sys/ioctl.h>
+#include <sys/uio.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -939,9 +942,7 @@ struct PumpSlot {
 
 void grow_pipe(int fd) {
     // F_SETPIPE_SZ: as large as the kernel allows (the default is 64 KB, a 4K 10-bit frame is 33 MB): fewer wake-ups on both sides
-    // (measured on the B200 hosts: 1 / 16 / 64 MB all move 2.0 GB/s each way, 4K 10-bit; a bare generator -> sink pipe does 3.3 GB/s.
-    // Splicing the pinned output pages into the pipe with vmsplice gained 14 % but ties a slot's reuse to the pipe being smaller
-    // than the slot -- not worth the hazard)
+    // (measured on the B200 hosts: 1 / 16 / 64 MB all move 2.0 GB/s each way, 4K 10-bit; a bare generator -> sink pipe does 3.3 GB/s)
     int top = 64;
     if (const char *e = std::getenv("LUTR_PIPE_MB")) top = std::atoi(e) > 0 ? std::atoi(e) : top;  // measurement knob
     for (int mb = top; mb >= 1; mb /= 2)
@@ -971,7 +972,7 @@ extern "C" int lutr_stage_pump(lutr_stage *s, const lutr_lut *lut, int fd_in, in
         return LUTR_ERR_INVALID_ARG;
     }
     CUDA_TRY(cudaSetDevice(s->ctx->device));
-    constexpr int NS = 4;
+    constexpr int NS = 5;  // reader, copy-in / kernel / copy-out, writer, and the batch whose pages the pipe still references
     const size_t per = s->in_bytes > s->out_bytes ? s->in_bytes : s->out_bytes;
     int batch = frames_per_batch > 0 ? frames_per_batch : (int)(((size_t)64 << 20) / per);
     batch = batch < 1 ? 1 : (batch > 64 ? 64 : batch);
@@ -1043,6 +1044,28 @@ extern "C" int lutr_stage_pump(lutr_stage *s, const lutr_lut *lut, int fd_in, in
         sigaddset(&pipe_set, SIGPIPE);
         pthread_sigmask(SIG_BLOCK, &pipe_set, &old_set);  // a vanished encoder is an EPIPE error here, not a fatal signal
         bool broken = false;
+        // Output side without a copy: vmsplice() lends the pinned pages of a batch to the pipe instead of copying them into it
+        // (+14 % on the B200 hosts).  The pipe then REFERENCES those pages until the encoder has read them, so a slot must not be
+        // refilled while any of its pages is still queued: the writer keeps the slot it queued last (`held`) and releases it only
+        // when no more than the bytes queued after it remain unread (FIONREAD) -- with batches larger than the pipe that is already
+        // true when the next batch has gone in.  Anything that is not a pipe (EBADF / EINVAL on the first call) falls back to write().
+        bool splice = std::getenv("LUTR_PUMP_NO_SPLICE") == nullptr, spliced_any = false;
+        int held = -1;
+        auto unread_at_most = [&](size_t limit) {  // false: gave up (cancelled, stopped, encoder gone)
+            for (;;) {
+                int n = 0;
+                if (ioctl(fd_out, FIONREAD, &n) < 0 || (size_t)n <= limit) return true;
+                if (stop.load(std::memory_order_relaxed) || (cancel && *cancel)) return false;
+                struct pollfd p = {fd_out, 0, 0};
+                if (poll(&p, 1, 0) > 0 && (p.revents & (POLLERR | POLLHUP | POLLNVAL))) {  // nobody reads the pipe any more
+                    if (werr.empty()) werr = "write to the encoder pipe failed: the encoder closed its end";
+                    stop.store(true);
+                    return false;
+                }
+                struct timespec nap = {0, 200000};
+                nanosleep(&nap, nullptr);
+            }
+        };
         for (;;) {
             const int i = out_q.pop();
             if (i < 0) break;
@@ -1052,7 +1075,18 @@ extern "C" int lutr_stage_pump(lutr_stage *s, const lutr_lut *lut, int fd_in, in
             size_t put = 0;
             while (!broken && put < want) {
                 if (!wait_fd(fd_out, POLLOUT, cancel, stop)) { broken = true; break; }
-                const ssize_t n = write(fd_out, t.hout + put, want - put);
+                ssize_t n;
+                if (splice) {
+                    struct iovec iov = {t.hout + put, want - put};
+                    n = vmsplice(fd_out, &iov, 1, SPLICE_F_NONBLOCK);
+                    if (n < 0 && !spliced_any && (errno == EBADF || errno == EINVAL || errno == ENOSYS)) {
+                        splice = false;  // not a pipe
+                        continue;
+                    }
+                    if (n > 0) spliced_any = true;
+                } else {
+                    n = write(fd_out, t.hout + put, want - put);
+                }
                 if (n > 0) put += (size_t)n;
                 else if (n < 0 && errno != EINTR && errno != EAGAIN) {
                     werr = std::string("write to the encoder pipe failed: ") + std::strerror(errno);
@@ -1065,7 +1099,19 @@ extern "C" int lutr_stage_pump(lutr_stage *s, const lutr_lut *lut, int fd_in, in
                 }
             }
             if (!broken) frames_out += t.frames;
-            free_q.push(i);
+            if (spliced_any && !broken) {
+                if (held >= 0) {
+                    if (!unread_at_most(want)) broken = true;
+                    free_q.push(held);
+                }
+                held = i;
+            } else {
+                free_q.push(i);
+            }
+        }
+        if (held >= 0) {
+            if (!broken) unread_at_most(0);  // the last batch: its pages go back to the allocator when this call returns
+            free_q.push(held);
         }
         pthread_sigmask(SIG_SETMASK, &old_set, nullptr);
     });

@@ -349,3 +349,36 @@ def test_other_lut_dialects_through_the_stage(tmp_path, dialect):
         assert_bit_exact("yuv422p10le", w, h, out[i * st.out_frame_bytes:(i + 1) * st.out_frame_bytes],
                          oracle_stage("yuv422p10le", w, h, f, L), f".{dialect} frame {i}")
     st.close()
+
+
+@pytest.mark.parametrize("pipe_mb,batch", [("1", 2), ("64", 2), ("64", 1), ("1", 0)])
+def test_pump_output_pages_are_not_reused_while_the_pipe_holds_them(tmp_path, monkeypatch, pipe_mb, batch):
+    """lutr_stage_pump lends its pinned output pages to the encoder's pipe (vmsplice) instead of copying them: a batch must not be
+    refilled before the (slow) reader has taken every page of it.  Distinct frames, a consumer that reads in small sips with pauses,
+    pipes smaller and larger than a batch; the bytes that arrive are the bytes run_host produces for the same frames.
+    Reference: the data between the two ffmpeg processes of TaskRunner._run_stage (task_manager.py:134-190)."""
+    import subprocess
+    import sys
+    from lut_renderer_b200.stage import ColourStage
+    monkeypatch.setenv("LUTR_PIPE_MB", pipe_mb)
+    w, h, nframes = 1920, 1080, 22
+    frames = np.concatenate([synth.natural_frame("yuv420p", w, h, t=t) for t in range(nframes)])
+    (tmp_path / "in.raw").write_bytes(frames.tobytes())
+    st = ColourStage(w, h, "yuv420p")
+    lut = st.ctx.lut_from_table(synth.look_lut(33).astype(np.float32))
+    expected = np.empty(nframes * st.out_frame_bytes, np.uint8)
+    st.run_host(lut, frames, expected, nframes)
+    gen = subprocess.Popen([sys.executable, "-c", f"import sys, shutil; shutil.copyfileobj(open({str(tmp_path / 'in.raw')!r}, 'rb'), sys.stdout.buffer)"],
+                           stdout=subprocess.PIPE, bufsize=0)
+    sip = ("import time\nf = open(0, 'rb', buffering=0); o = open(%r, 'wb'); n = 0\n"
+           "while True:\n    b = f.read(1 << 19)\n    if not b: break\n    o.write(b); n += 1\n    if n %% 8 == 0: time.sleep(0.004)\n" % str(tmp_path / "out.raw"))
+    sink = subprocess.Popen([sys.executable, "-c", sip], stdin=subprocess.PIPE, bufsize=0)
+    stats = st.pump(lut, gen.stdout.fileno(), sink.stdin.fileno(), batch)
+    sink.stdin.close()
+    assert sink.wait() == 0 and gen.wait() == 0
+    assert stats["frames_out"] == nframes
+    got = np.frombuffer((tmp_path / "out.raw").read_bytes(), np.uint8)
+    assert got.size == expected.size
+    bad = np.flatnonzero(got != expected)
+    assert bad.size == 0, f"{bad.size} bytes differ, first at frame {bad[0] // st.out_frame_bytes}"
+    st.close(), lut.close()
