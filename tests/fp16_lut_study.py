@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """What storing the LUT as packed fp16 (north_star's shared-memory option for 33-point tables) would cost in parity: the oracle's
 lut3d leg with the table rounded to fp16 against the same leg with the fp32 table, tetrahedral, 2 M random RGB inputs, and the
-effect on the final YUV planes of BASELINE cfg 3.  CPU only (oracle/):   python tools/fp16_lut_study.py"""
+effect on the final YUV planes of BASELINE cfg 3.  CPU only (oracle/):   python tests/fp16_lut_study.py"""
 import json
 import os
 import sys

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised parity soak: many random (layout, geometry, grid, LUT, interp, matrix, range, option) combinations through the C-ABI
 against the oracle, bit-exact.  The committed fuzz test (tests/test_gpu_parity.py) is one fixed seed of this; run other seeds here.
-    python tools/soak.py [--seed 1] [--trials 200]"""
+    python tests/soak.py [--seed 1] [--trials 200]"""
 import argparse
 import os
 import sys
