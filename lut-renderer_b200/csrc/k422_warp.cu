@@ -23,13 +23,18 @@ namespace lutr {
 
 namespace {
 
+#ifndef LUTR_K422_WARPS
+#define LUTR_K422_WARPS kWarps
+#endif
+constexpr int kW422 = LUTR_K422_WARPS;  // warps per CTA (experiments: 7 x 3 CTAs or 10 x 2 CTAs trade warps for registers; 8 x 3 shipped)
+
 // IN444: the source is yuv444p10le (ProRes 4444 and the like): one chroma sample per pixel, no upsampling filter; everything behind
 // pass A is unchanged (u17 = (C - 512) * 128 == 4 * (C << 5) - 65536, the same expression pass B applies to the 15-bit value).
 // COPY: the memory path alone (same windows, halo loads, register prefetch, shared-memory round trip and 16-byte / 8-byte stores; the
 // arithmetic replaced by moving samples) for the roofline study in DESIGN.md section 6 -- never dispatched by the product path.
 template <int INTERP, bool FMA, bool CLAMP, int IDX, bool NOMIN, int NSZ, bool PK, int MINB, int UNR, bool IN444, int BM = LUTR_BMODE, int TEXV = 0, bool COPY = false>
-__global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
-    __shared__ __align__(16) unsigned s_all[kWarps][kWin + kWin / 2];
+__global__ void __launch_bounds__(kW422 * 32, MINB) k422_warp(const StageK K) {
+    __shared__ __align__(16) unsigned s_all[kW422][kWin + kWin / 2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lane_odd = lane ^ 4;
     unsigned *sC = s_all[wib];                                                  // [256] (cu | cv << 16), later (u14 | v14 << 16)
     unsigned *sYw = sC + kWin;                                                  // [128] luma samples, two per word
@@ -92,12 +97,12 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
             return make_uint4(t.x, t.y, 0u, 0u);
         };
         if (y0 < y1) ny = ldg_s16(pY), nu = load_c(pU), nv = load_c(pV);
-        for (int y = y0; y < y1; y += kWarps) {
+        for (int y = y0; y < y1; y += kW422) {
             const uint4 cy = ny;
             const uint4 cu4 = nu, cv4 = nv;
             const uint2 cu2 = make_uint2(cu4.x, cu4.y), cv2 = make_uint2(cv4.x, cv4.y);
-            if (y + kWarps < y1) {  // prefetch this warp's next row of the window
-                pY += kWarps * (long)K.p.in_stride[0], pU += kWarps * (long)K.p.in_stride[1], pV += kWarps * (long)K.p.in_stride[2];
+            if (y + kW422 < y1) {  // prefetch this warp's next row of the window
+                pY += kW422 * (long)K.p.in_stride[0], pU += kW422 * (long)K.p.in_stride[1], pV += kW422 * (long)K.p.in_stride[2];
                 ny = ldg_s16(pY), nu = load_c(pU), nv = load_c(pV);
             }
 
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k422_warp(const StageK K) {
                 stg_s8(oU, make_uint2(uo[0], uo[1]));
                 stg_s8(oV, make_uint2(vo[0], vo[1]));
             }
-            oY += kWarps * (long)K.p.out_stride[0], oU += kWarps * (long)K.p.out_stride[1], oV += kWarps * (long)K.p.out_stride[2];
+            oY += kW422 * (long)K.p.out_stride[0], oU += kW422 * (long)K.p.out_stride[1], oV += kW422 * (long)K.p.out_stride[2];
         }
 
         // next unit
@@ -290,7 +295,7 @@ int launch_k422_warp(const StageK &k, bool in444, int interp, int float_mode, vo
     long grid = k.grid_ctas > 0 ? k.grid_ctas : 148 * minb;
     if (grid > total) grid = total;
     if (k.wk_carveout > 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, k.wk_carveout);  // experiments: % of the unified L1 / shared array
-    fn<<<(unsigned)grid, kWarps * 32, 0, (cudaStream_t)stream>>>(k);
+    fn<<<(unsigned)grid, kW422 * 32, 0, (cudaStream_t)stream>>>(k);
     return cudaGetLastError() == cudaSuccess ? LUTR_OK : LUTR_ERR_CUDA;
 }
 
