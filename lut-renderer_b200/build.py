@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblutr.so")
-SOURCES = ["cube_parser.cpp", "lut_dialects.cpp", "colour_tables.cpp", "k422_warp.cu", "k422_tma.cu", "k420_warp.cu", "k420_warp10.cu", "k420_warp422.cu", "k420_warp444.cu", "k10_warp.cu", "k10_warp8.cu", "k_any.cu", "k_convert.cu", "lutr_api.cu"]
-HEADERS = ["lutr_internal.h", "warp_common.cuh", "k420_warp.cuh", "k10_warp.cuh", "lut3d_generic.cuh", os.path.join("..", "..", "include", "lutr.h")]
+SOURCES = ["cube_parser.cpp", "lut_dialects.cpp", "colour_tables.cpp", "k422_warp.cu", "k422_tma.cu", "k420_warp.cu", "k420_warp10.cu", "k420_warp422.cu", "k420_warp444.cu", "k10_warp.cu", "k10_warp8.cu", "k_any.cu", "k_any_fixed8.cu", "k_any_fixed10.cu", "k_convert.cu", "lutr_api.cu"]
+HEADERS = ["lutr_internal.h", "warp_common.cuh", "k420_warp.cuh", "k10_warp.cuh", "lut3d_generic.cuh", "k_any.cuh", os.path.join("..", "..", "include", "lutr.h")]
 GENCODE = "arch=compute_100a,code=sm_100a"
 
 

@@ -806,3 +806,29 @@ def test_per_channel_domain_scales_on_the_warp_kernels(in_fmt, out_fmt, kernel, 
         finally:
             O.set_float_mode("c")
         st.close(), lut.close()
+
+
+FIXED_CELLS = [("yuv422p10le", "yuv422p10le"), ("yuv420p10le", "yuv422p10le"), ("yuv420p10le", "yuv420p10le"), ("yuv420p10le", "yuv420p"),
+               ("yuv422p10le", "yuv420p"), ("yuv420p", "yuv420p"), ("yuv420p", "yuv444p"), ("yuv420p", "yuv422p10le")]
+
+
+@pytest.mark.parametrize("in_fmt,out_fmt", FIXED_CELLS)
+@pytest.mark.parametrize("interp", ["tetrahedral", "trilinear"])
+def test_any_fixed_format_instantiations(in_fmt, out_fmt, interp):
+    """The generic tile kernel exists twice for the cells the reference's options reach most (k_any_fixed8.cu / k_any_fixed10.cu: the
+    layouts as compile-time constants; wk_var=4000 keeps the run-time-format instantiation): both bit-exact against the oracle, on a
+    width off the 8-column grid (what sends these cells to the generic kernel in the first place), with a pc -> tv pass in front for
+    the 8-bit sources, a per-channel DOMAIN and a table that leaves [0, 1]."""
+    w, h = 854 if "10" in in_fmt else 206, 72
+    table = (synth.random_lut(17, 77) * 1.3 - 0.1).astype(np.float32)
+    scale = (0.5, 1.0, 0.75)
+    kw = dict(in_range="pc", norm_range="tv") if "10" not in in_fmt else {}
+    frames = _frames(in_fmt, w, h, ["natural", "noise", "extremes"])
+    L = oracle_lut(table, scale)
+    exp = [oracle_stage(in_fmt, w, h, f, L, out_pix_fmt=out_fmt, interp=interp, **kw) for f in frames]
+    for options in (dict(), dict(wk_var=4000), dict(grid_ctas=3)):
+        info = {}
+        got = gpu_stage(in_fmt, w, h, frames, table, scale, out_pix_fmt=out_fmt, interp=interp, options=options, info=info, **kw)
+        assert info["kernel"] == "k_any"
+        for i in range(len(frames)):
+            assert_bit_exact(out_fmt, w, h, got[i], exp[i], f"{in_fmt}->{out_fmt} {interp} {options} frame {i}")
