@@ -1,5 +1,5 @@
 // Generic per-pixel lut3d evaluation (all interpolation modes, per-channel domain scales, clamped "next" nodes): the
-// straightforward restatement of FFmpeg vf_lut3d's C code used by the generic kernels (stage_kernels.cu, k_any.cu).
+// straightforward restatement of FFmpeg vf_lut3d's C code used by the generic tile kernel (k_any.cuh).
 // float32, one rounding per C operation unless FMA (the contracted order of FFmpeg's x86 assembly for planar formats).
 // Reference call site: src/lut_renderer/ffmpeg.py:242-247.  Oracle: oracle/lutr_oracle.c lut3d_pixel / interp_*.
 #pragma once

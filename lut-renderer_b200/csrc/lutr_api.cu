@@ -70,7 +70,7 @@ struct lutr_stage {
     // tunables
     int rows_per_cta = 0;  // 0 = auto
     int use_fast = 1;      // 0 forces the generic kernels (testing)
-    bool any_only = false; // the combination exists in the generic tile kernel (k_any.cu) only
+    bool any_only = false; // the combination exists in the generic tile kernel (k_any.cuh) only
     bool convert_only = false;  // interp = LUTR_INTERP_NONE: LUT-less conversion of the master (k_convert.cu)
     int pre10 = 0;         // full-range 10-bit source through the 8-bit intermediate: 1 = with pc -> tv, 2 = range kept
     int force_any = 0;     // option "any_kernel": 1 routes every launch through the generic tile kernel (testing)
@@ -696,7 +696,7 @@ int lutr_stage_create(lutr_ctx *ctx, const lutr_stage_desc *desc, lutr_stage **o
             return LUTR_ERR_UNSUPPORTED;
         }
     }
-    // combinations with a specialised warp-window kernel; everything else runs the generic tile kernel (k_any.cu)
+    // combinations with a specialised warp-window kernel; everything else runs the generic tile kernel (k_any.cuh)
     const bool tri_tet = d.interp == LUTR_INTERP_TRILINEAR || d.interp == LUTR_INTERP_TETRAHEDRAL;
     const bool same_fmt = d.in_fmt == d.out_fmt && (d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P10LE);
     const bool in8 = d.in_fmt == LUTR_PIX_YUV420P || d.in_fmt == LUTR_PIX_YUV422P;  // 8-bit sources of the SIMD-path arithmetic
